@@ -1,0 +1,134 @@
+/*
+ * racformer_ops.h -- C ABI of libracformer_ops.so (B200 / sm_100a).
+ *
+ * The drop-in boundary for RaCFormer's sampling hot path. Every entry point
+ * takes plain device pointers, integer sizes and a CUDA stream; the library
+ * never allocates or frees device memory, never synchronises, keeps no
+ * global state and returns an int status instead of printing.
+ *
+ * Reference interfaces replaced (paths relative to the RaCFormer tree):
+ *   racf_msmv_forward   <- ms_deformable_im2col_cuda_c{45,2345,23456}
+ *                          models/csrc/msmv_sampling/msmv_sampling_forward.cu:336-428
+ *                          (declared models/csrc/msmv_sampling/msmv_sampling.cpp:5-60)
+ *   racf_msmv_backward  <- ms_deformable_col2im_cuda_c{45,2345,23456}
+ *                          models/csrc/msmv_sampling/msmv_sampling_backward.cu:442-563
+ *   racf_msda_forward   <- mmcv-full 1.6.0 `_ext.ms_deform_attn_forward`, bound at
+ *                          models/multi_scale_deformable_attn_function.py:10-12,118-124
+ *   racf_msda_backward  <- mmcv-full 1.6.0 `_ext.ms_deform_attn_backward`, bound at
+ *                          models/multi_scale_deformable_attn_function.py:150-160
+ *
+ * All tensors are fp32, dense and contiguous in the layouts given below.
+ */
+#ifndef RACFORMER_OPS_H_
+#define RACFORMER_OPS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes. 0 = success; >0 = a cudaError_t from the launch; <0 = argument error. */
+#define RACF_OK                 0
+#define RACF_ERR_NULL_POINTER  (-1)
+#define RACF_ERR_BAD_LEVELS    (-2)  /* num_levels outside [1, RACF_MAX_LEVELS] */
+#define RACF_ERR_BAD_SHAPE     (-3)  /* a dimension is <= 0 or a per-batch extent overflows int32 */
+#define RACF_ERR_TOO_MANY_PTS  (-4)  /* num_point > RACF_MSMV_MAX_POINT (reference: msmv_sampling.cpp:159) */
+#define RACF_ERR_IM2COL_STEP   (-5)  /* batch % min(batch, im2col_step) != 0 (mmcv contract) */
+
+#define RACF_MAX_LEVELS        8
+#define RACF_MSMV_MAX_POINT    128
+
+/* Opaque stream handle: a cudaStream_t / CUstream (NULL = legacy default stream). */
+typedef void* racf_stream_t;
+
+/* ABI version of this header (major*100 + minor). */
+int racf_version(void);
+
+/* Human-readable text for a status code returned by this library (never NULL). */
+const char* racf_status_string(int status);
+
+/*
+ * Multi-scale multi-view sampling, forward.
+ *   feats[l]   : [B, N, H_l, W_l, C]   channel-last feature maps, l = 0..L-1 (host array of device pointers)
+ *   hw[2l..]   : (H_l, W_l)             host array
+ *   loc        : [B, Q, P, 3]           (x, y in normalised image units, z = view / (N-1))
+ *   weights    : [B, Q, P, L]           per-level scale weights
+ *   out        : [B, Q, C, P]           fully overwritten (no pre-zeroing needed)
+ * out[b,q,c,p] = sum_l weights[b,q,p,l] * bilinear(feats[l][b, round(z*(N-1))], x*(W_l-1), y*(H_l-1))[c]
+ * with zero padding and align_corners=True; arithmetic follows msmv_sampling_forward.cu:27-73,95-163.
+ */
+int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels,
+                      const float* loc, const float* weights,
+                      int batch, int channels, int num_views, int num_query, int num_point,
+                      float* out, racf_stream_t stream);
+
+/*
+ * Multi-scale multi-view sampling, backward (msmv_sampling_backward.cu:29-105,132-223).
+ *   grad_out      : [B, Q, C, P]
+ *   grad_feats[l] : [B, N, H_l, W_l, C]  accumulated with atomics. If zero_grad_feats != 0 the library
+ *                   zero-fills them on `stream` first (what at::zeros_like did, msmv_sampling.cpp:322-325);
+ *                   otherwise the gradients are added to the existing contents.
+ *   grad_loc      : [B, Q, P, 3]  fully overwritten; the z (view) component is always 0
+ *   grad_weights  : [B, Q, P, L]  fully overwritten
+ */
+int racf_msmv_backward(const float* grad_out,
+                       const float* const* feats, const int* hw, int num_levels,
+                       const float* loc, const float* weights,
+                       int batch, int channels, int num_views, int num_query, int num_point,
+                       float* const* grad_feats, float* grad_loc, float* grad_weights,
+                       int zero_grad_feats, racf_stream_t stream);
+
+/*
+ * Debug/verification entry: the integer decisions of the MSMV kernels.
+ *   view_index : [B, Q, P]     int32  round(z*(N-1))
+ *   tap_mask   : [B, Q, P, L]  uint8  bit0 = tap in range (msmv_sampling_forward.cu:126),
+ *                                     bit1..4 = corner (h0,w0),(h0,w1),(h1,w0),(h1,w1) is read (:48-67)
+ */
+int racf_msmv_tap_masks(const int* hw, int num_levels, const float* loc,
+                        int batch, int num_views, int num_query, int num_point,
+                        int32_t* view_index, uint8_t* tap_mask, racf_stream_t stream);
+
+/*
+ * Multi-scale deformable attention, forward (mmcv 1.6.0 ms_deformable_im2col_gpu_kernel).
+ *   value            : [B, S, M, D]
+ *   spatial_shapes   : [L, 2] int64 DEVICE pointer, (H_l, W_l)
+ *   level_start_index: [L]    int64 DEVICE pointer
+ *   loc              : [B, Q, M, L, P, 2]  (x, y) in [0,1] units of the level
+ *   attn             : [B, Q, M, L, P]
+ *   out              : [B, Q, M*D]          fully overwritten
+ * Sampling uses align_corners=False: pixel = fma(loc, size, -0.5), zero padding.
+ * im2col_step only has mmcv's divisibility contract; it does not change results.
+ */
+int racf_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* loc, const float* attn,
+                      int batch, int spatial_size, int num_heads, int head_dim,
+                      int num_levels, int num_query, int num_point, int im2col_step,
+                      float* out, racf_stream_t stream);
+
+/*
+ * Multi-scale deformable attention, backward.
+ *   grad_out   : [B, Q, M*D]
+ *   grad_value : [B, S, M, D]          accumulated with atomics into the caller's (pre-zeroed) buffer,
+ *                                      as mmcv does (multi_scale_deformable_attn_function.py:146-160)
+ *   grad_loc   : [B, Q, M, L, P, 2]    fully overwritten
+ *   grad_attn  : [B, Q, M, L, P]       fully overwritten
+ */
+int racf_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const float* loc, const float* attn, const float* grad_out,
+                       int batch, int spatial_size, int num_heads, int head_dim,
+                       int num_levels, int num_query, int num_point, int im2col_step,
+                       float* grad_value, float* grad_loc, float* grad_attn, racf_stream_t stream);
+
+/*
+ * Debug/verification entry for MSDA: tap_mask[b,q,m,l,p] uint8 with the same bit layout as
+ * racf_msmv_tap_masks (bit0 in range, bit1..4 corners read).
+ */
+int racf_msda_tap_masks(const int64_t* spatial_shapes, const float* loc,
+                        int batch, int num_heads, int num_levels, int num_query, int num_point,
+                        uint8_t* tap_mask, racf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACFORMER_OPS_H_ */

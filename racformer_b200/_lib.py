@@ -1,0 +1,69 @@
+"""ctypes binding of libracformer_ops.so (declared in include/racformer_ops.h).
+
+There is no CPU fallback: if the library is missing, loading raises. Nothing here imports `oracle/`.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_c_float_p = ctypes.c_void_p  # device pointers are passed as integers
+_i = ctypes.c_int
+
+# name -> (restype, argtypes); must match include/racformer_ops.h
+SIGNATURES = {
+    "racf_version": (_i, []),
+    "racf_status_string": (ctypes.c_char_p, [_i]),
+    "racf_msmv_forward": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
+                               _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_msmv_backward": (_i, [_c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p,
+                                _c_float_p, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
+                                _c_float_p, _i, ctypes.c_void_p]),
+    "racf_msmv_tap_masks": (_i, [ctypes.POINTER(_i), _i, _c_float_p, _i, _i, _i, _i, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "racf_msda_forward": (_i, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _c_float_p,
+                               _i, _i, _i, _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_msda_backward": (_i, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p,
+                                _i, _i, _i, _i, _i, _i, _i, _i, _c_float_p, _c_float_p, _c_float_p,
+                                ctypes.c_void_p]),
+    "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Return the loaded library (ctypes.CDLL). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = lib_path()
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"{path} not found: build it with `python -m racformer_b200.build` "
+                    "(there is no CPU fallback for the racformer_b200 ops)")
+            lib = ctypes.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the symbol is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def status_string(code):
+    return load().racf_status_string(int(code)).decode()
+
+
+def check(code, what):
+    """Turn a non-zero status into the RuntimeError the reference's ATen asserts would raise."""
+    if code != 0:
+        raise RuntimeError(f"{what}: {status_string(code)} (status {code})")

@@ -1,0 +1,570 @@
+// Multi-scale multi-view (MSMV) sampling for B200 (sm_100a): forward, backward, mask dump.
+//
+// Operator semantics: models/csrc/msmv_sampling/msmv_sampling_forward.cu:27-164 and
+// msmv_sampling_backward.cu:29-224 of the reference (restated in SURVEY.md App. A.1/A.2).
+//
+// Work decomposition (fast path, C == 64):
+//   * one warp owns one query (b, q): all P sample points, all L levels, all 64 channels. Because the
+//     warp owns every contribution to grad_loc[b,q,:,:] and grad_weights[b,q,:,:], those gradients are
+//     reduced with warp shuffles and written with plain stores -- no atomics, no pre-zeroing.
+//   * a pixel is 64 fp32 = 256 B = 16 lanes x 128 bit. In channel-last layout the two x-neighbours of
+//     a bilinear cell are adjacent in memory, so ONE warp-wide 128-bit load fetches 512 contiguous
+//     bytes = both corners of a row: lanes 0-15 hold (y, x0), lanes 16-31 hold (y, x0+1). A tap is two
+//     such loads (top row, bottom row); the two half-warps are combined with a single shfl_xor(16).
+//   * per-tap geometry (corner offset, validity bits, bilinear and level weights) is computed once by
+//     one lane per tap and staged in shared memory; every lane then reads it back as a broadcast.
+//   * backward scatters the feature gradient with red.global.add.v4.f32: one 512-byte vector
+//     reduction per row per warp instead of 128 scalar atomics.
+#include "racf_common.cuh"
+#include "racformer_ops.h"
+
+namespace racf {
+
+constexpr int kMsmvChunk = 4;   // sample points handled per inner round (also the float4 width along P)
+constexpr int kMsmvWarps = 8;   // warps (queries) per CTA on the fast path
+constexpr int kLanesPerPixel = 16;  // C == 64 -> 16 float4 lanes
+
+template <int L>
+struct MsmvArgs {
+    const float* feat[L];
+    float* grad_feat[L];
+    int H[L];
+    int W[L];
+    const float* loc;      // [B,Q,P,3]
+    const float* wts;      // [B,Q,P,L]
+    const float* grad_out; // [B,Q,C,P]
+    float* out;            // [B,Q,C,P]
+    float* grad_loc;       // [B,Q,P,3]
+    float* grad_wts;       // [B,Q,P,L]
+    int B, N, Q, P, C;
+};
+
+template <int L>
+__device__ __forceinline__ void level_dims(const MsmvArgs<L>& a, int l, int& H, int& W) {
+    H = a.H[0];
+    W = a.W[0];
+#pragma unroll
+    for (int k = 1; k < L; ++k)
+        if (k == l) { H = a.H[k]; W = a.W[k]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path, forward. grid = ceil(B*Q / kMsmvWarps), block = kMsmvWarps warps.
+// ------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kMsmvWarps * 32) msmv_fwd_c64_kernel(const MsmvArgs<L> a) {
+    constexpr int G = kLanesPerPixel;
+    constexpr int TAPS = kMsmvChunk * L;
+    static_assert(TAPS <= 32, "one lane per tap");
+    __shared__ float2 s_w[kMsmvWarps][TAPS][2];  // [tap][x-slot] = {w_top, w_bot} * level weight
+    __shared__ int2 s_om[kMsmvWarps][TAPS];      // {float4 offset of the top-left pixel, corner mask}
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bq = (long long)blockIdx.x * kMsmvWarps + warp;
+    if (bq >= (long long)a.B * a.Q) return;  // whole warp exits together; only __syncwarp below
+    const int b = (int)(bq / a.Q);
+    const int slot = lane >> 4, j = lane & 15;
+
+    const float4* base[L];
+    int row[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        base[l] = reinterpret_cast<const float4*>(a.feat[l] + (size_t)b * a.N * a.H[l] * a.W[l] * 64) + slot * G + j;
+        row[l] = a.W[l] * G;
+    }
+    const float* loc_q = a.loc + bq * a.P * 3;
+    const float* wts_q = a.wts + bq * a.P * L;
+    float* out_q = a.out + bq * 64 * a.P;
+    const bool vec_store = (a.P % 4) == 0;
+
+    for (int p0 = 0; p0 < a.P; p0 += kMsmvChunk) {
+        __syncwarp();
+        if (lane < TAPS) {
+            const int pp = lane / L, l = lane % L, p = p0 + pp;
+            float2 w0 = make_float2(0.f, 0.f), w1 = w0;
+            int2 om = make_int2(0, 0);
+            if (p < a.P) {
+                const float lx = loc_q[p * 3], ly = loc_q[p * 3 + 1], lz = loc_q[p * 3 + 2];
+                const float s = wts_q[p * L + l];
+                int H, W;
+                level_dims<L>(a, l, H, W);
+                const int v = msmv_view(lz, a.N);
+                const TapGeom g = tap_geometry(msmv_pixel(ly, H), msmv_pixel(lx, W), H, W);
+                if (g.mask != 0u && v >= 0 && v < a.N) {
+                    const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+                    w0 = make_float2(hh * hw * s, g.lh * hw * s);
+                    w1 = make_float2(hh * g.lw * s, g.lh * g.lw * s);
+                    om.x = ((v * H + g.h_low) * W + g.w_low) * G;
+                    om.y = (int)g.mask;
+                }
+            }
+            s_w[warp][lane][0] = w0;
+            s_w[warp][lane][1] = w1;
+            s_om[warp][lane] = om;
+        }
+        __syncwarp();
+
+        float4 acc[kMsmvChunk];
+#pragma unroll
+        for (int pp = 0; pp < kMsmvChunk; ++pp) {
+            acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int t = pp * L + l;
+                const int2 om = s_om[warp][t];
+                const float2 w = s_w[warp][t][slot];
+                const unsigned m = (unsigned)om.y >> slot;  // bit0 = top corner of my column, bit2 = bottom
+                const float4* p = base[l] + om.x;
+                float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
+                if (m & 1u) top = ldg128(p);
+                if (m & 4u) bot = ldg128(p + row[l]);
+                acc[pp].x = fmaf(w.y, bot.x, fmaf(w.x, top.x, acc[pp].x));
+                acc[pp].y = fmaf(w.y, bot.y, fmaf(w.x, top.y, acc[pp].y));
+                acc[pp].z = fmaf(w.y, bot.z, fmaf(w.x, top.z, acc[pp].z));
+                acc[pp].w = fmaf(w.y, bot.w, fmaf(w.x, top.w, acc[pp].w));
+            }
+        }
+        // combine the x0 / x1 half-warps
+#pragma unroll
+        for (int pp = 0; pp < kMsmvChunk; ++pp) {
+            acc[pp].x += __shfl_xor_sync(0xffffffffu, acc[pp].x, 16);
+            acc[pp].y += __shfl_xor_sync(0xffffffffu, acc[pp].y, 16);
+            acc[pp].z += __shfl_xor_sync(0xffffffffu, acc[pp].z, 16);
+            acc[pp].w += __shfl_xor_sync(0xffffffffu, acc[pp].w, 16);
+        }
+        // out[b,q,c,p]: lane (slot, j) stores channels 4j + 2*slot + {0,1}, points p0..p0+3
+        const int c0 = 4 * j + 2 * slot;
+        const float4 e0 = slot ? make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z)
+                               : make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+        const float4 e1 = slot ? make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w)
+                               : make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+        if (vec_store) {
+            *reinterpret_cast<float4*>(out_q + (size_t)c0 * a.P + p0) = e0;
+            *reinterpret_cast<float4*>(out_q + (size_t)(c0 + 1) * a.P + p0) = e1;
+        } else {
+            const float v0[4] = {e0.x, e0.y, e0.z, e0.w}, v1[4] = {e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+            for (int pp = 0; pp < kMsmvChunk; ++pp)
+                if (p0 + pp < a.P) {
+                    out_q[(size_t)c0 * a.P + p0 + pp] = v0[pp];
+                    out_q[(size_t)(c0 + 1) * a.P + p0 + pp] = v1[pp];
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path, backward. Same ownership as forward.
+// ------------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kMsmvWarps * 32) msmv_bwd_c64_kernel(const MsmvArgs<L> a) {
+    constexpr int G = kLanesPerPixel;
+    constexpr int TAPS = kMsmvChunk * L;
+    static_assert(TAPS <= 32, "one lane per tap");
+    __shared__ float4 s_rec[kMsmvWarps][TAPS];           // {lh, lw, level weight, bits(offset)}
+    __shared__ unsigned s_mask[kMsmvWarps][TAPS];
+    __shared__ __align__(16) float s_g[kMsmvWarps][kMsmvChunk][64];  // grad_out chunk, [point][channel]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long bq = (long long)blockIdx.x * kMsmvWarps + warp;
+    if (bq >= (long long)a.B * a.Q) return;
+    const int b = (int)(bq / a.Q);
+    const int slot = lane >> 4, j = lane & 15;
+
+    const float4* base[L];
+    float* gbase[L];
+    int row[L];
+    float sx_scale[L], sy_scale[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        const size_t boff = (size_t)b * a.N * a.H[l] * a.W[l] * 64;
+        base[l] = reinterpret_cast<const float4*>(a.feat[l] + boff) + slot * G + j;
+        gbase[l] = a.grad_feat[l] + boff + (size_t)(slot * G + j) * 4;
+        row[l] = a.W[l] * G;
+        sx_scale[l] = (float)(a.W[l] - 1);
+        sy_scale[l] = (float)(a.H[l] - 1);
+    }
+    const float* loc_q = a.loc + bq * a.P * 3;
+    const float* wts_q = a.wts + bq * a.P * L;
+    const float* go_q = a.grad_out + bq * 64 * a.P;
+    float* gl_q = a.grad_loc + bq * a.P * 3;
+    float* gw_q = a.grad_wts + bq * a.P * L;
+    const bool vec_load = (a.P % 4) == 0;
+    const float sgn = slot ? 1.f : -1.f;
+
+    for (int p0 = 0; p0 < a.P; p0 += kMsmvChunk) {
+        __syncwarp();
+        // stage grad_out[b,q,:,p0:p0+4] transposed to [point][channel]
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            float g4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (vec_load) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(go_q + (size_t)c * a.P + p0));
+                g4[0] = t.x; g4[1] = t.y; g4[2] = t.z; g4[3] = t.w;
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < kMsmvChunk; ++pp)
+                    if (p0 + pp < a.P) g4[pp] = __ldg(go_q + (size_t)c * a.P + p0 + pp);
+            }
+#pragma unroll
+            for (int pp = 0; pp < kMsmvChunk; ++pp) s_g[warp][pp][c] = g4[pp];
+        }
+        if (lane < TAPS) {
+            const int pp = lane / L, l = lane % L, p = p0 + pp;
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned mask = 0u;
+            if (p < a.P) {
+                const float lx = loc_q[p * 3], ly = loc_q[p * 3 + 1], lz = loc_q[p * 3 + 2];
+                const float s = wts_q[p * L + l];
+                int H, W;
+                level_dims<L>(a, l, H, W);
+                const int v = msmv_view(lz, a.N);
+                const TapGeom g = tap_geometry(msmv_pixel(ly, H), msmv_pixel(lx, W), H, W);
+                if (g.mask != 0u && v >= 0 && v < a.N) {
+                    rec = make_float4(g.lh, g.lw, s, __int_as_float(((v * H + g.h_low) * W + g.w_low) * G));
+                    mask = g.mask;
+                }
+            }
+            s_rec[warp][lane] = rec;
+            s_mask[warp][lane] = mask;
+        }
+        __syncwarp();
+
+#pragma unroll
+        for (int pp = 0; pp < kMsmvChunk; ++pp) {
+            const float4 g = *reinterpret_cast<const float4*>(&s_g[warp][pp][4 * j]);
+            float glx = 0.f, gly = 0.f;
+            float gw[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int t = pp * L + l;
+                gw[l] = 0.f;
+                const unsigned mask = s_mask[warp][t];
+                if (mask == 0u) continue;  // warp-uniform
+                const float4 rec = s_rec[warp][t];
+                const float lh = rec.x, lw = rec.y, s = rec.z;
+                const int off = __float_as_int(rec.w);
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                const float wx = slot ? lw : hw;
+                const float w_top = hh * wx, w_bot = lh * wx;
+                const unsigned m = mask >> slot;
+                const float4* p = base[l] + off;
+                float* gp = gbase[l] + (size_t)off * 4;
+                float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
+                if (m & 1u) top = ldg128(p);
+                if (m & 4u) bot = ldg128(p + row[l]);
+                if (m & 1u) {
+                    const float k = w_top * s;
+                    red_add_v4(gp, k * g.x, k * g.y, k * g.z, k * g.w);
+                }
+                if (m & 4u) {
+                    const float k = w_bot * s;
+                    red_add_v4(gp + (size_t)row[l] * 4, k * g.x, k * g.y, k * g.z, k * g.w);
+                }
+                const float A = dot4(g, top), Bv = dot4(g, bot);
+                gw[l] = fmaf(w_top, A, w_bot * Bv);                       // -> grad_weights
+                gly = fmaf(sy_scale[l] * s, wx * (Bv - A), gly);           // d/dy
+                glx = fmaf(sx_scale[l] * s, sgn * fmaf(hh, A, lh * Bv), glx);  // d/dx
+            }
+            const int p = p0 + pp;
+            if (p < a.P) {  // warp-uniform
+                glx = warp_sum(glx);
+                gly = warp_sum(gly);
+#pragma unroll
+                for (int l = 0; l < L; ++l) gw[l] = warp_sum(gw[l]);
+                if (lane == 0) {
+                    gl_q[p * 3 + 0] = glx;
+                    gl_q[p * 3 + 1] = gly;
+                    gl_q[p * 3 + 2] = 0.f;
+#pragma unroll
+                    for (int l = 0; l < L; ++l) gw_q[p * L + l] = gw[l];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic path (any C, any L <= RACF_MAX_LEVELS): one thread per (b,q,c) / (b,q,p,c). Slow but complete.
+// ------------------------------------------------------------------------------------------------
+struct MsmvArgsDyn {
+    const float* feat[RACF_MAX_LEVELS];
+    float* grad_feat[RACF_MAX_LEVELS];
+    int H[RACF_MAX_LEVELS];
+    int W[RACF_MAX_LEVELS];
+    const float* loc;
+    const float* wts;
+    const float* grad_out;
+    float* out;
+    float* grad_loc;
+    float* grad_wts;
+    int B, N, Q, P, C, L;
+};
+
+__global__ void __launch_bounds__(256) msmv_fwd_generic_kernel(const MsmvArgsDyn a) {
+    __shared__ int sH[RACF_MAX_LEVELS], sW[RACF_MAX_LEVELS];
+    if (threadIdx.x < a.L) { sH[threadIdx.x] = a.H[threadIdx.x]; sW[threadIdx.x] = a.W[threadIdx.x]; }
+    __syncthreads();
+    const long long total = (long long)a.B * a.Q * a.C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % a.C);
+        const long long bq = idx / a.C;
+        const int b = (int)(bq / a.Q);
+        for (int p = 0; p < a.P; ++p) {
+            const float* lp = a.loc + (bq * a.P + p) * 3;
+            const float lx = lp[0], ly = lp[1];
+            const int v = msmv_view(lp[2], a.N);
+            float res = 0.f;
+            if (v >= 0 && v < a.N) {
+                for (int l = 0; l < a.L; ++l) {
+                    const int H = sH[l], W = sW[l];
+                    const TapGeom g = tap_geometry(msmv_pixel(ly, H), msmv_pixel(lx, W), H, W);
+                    if (g.mask == 0u) continue;
+                    const float* f = nullptr;
+#pragma unroll
+                    for (int k = 0; k < RACF_MAX_LEVELS; ++k)
+                        if (k == l) f = a.feat[k];
+                    f += (((size_t)b * a.N + v) * H * W) * a.C + c;
+                    const size_t o = ((size_t)g.h_low * W + g.w_low) * a.C;  // may wrap for -1: only used when valid
+                    const size_t rs = (size_t)W * a.C;
+                    const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+                    const float v1 = (g.mask & kTL) ? __ldg(f + o) : 0.f;
+                    const float v2 = (g.mask & kTR) ? __ldg(f + o + a.C) : 0.f;
+                    const float v3 = (g.mask & kBL) ? __ldg(f + o + rs) : 0.f;
+                    const float v4 = (g.mask & kBR) ? __ldg(f + o + rs + a.C) : 0.f;
+                    const float val = hh * hw * v1 + hh * g.lw * v2 + g.lh * hw * v3 + g.lh * g.lw * v4;
+                    res = fmaf(val, a.wts[(bq * a.P + p) * a.L + l], res);
+                }
+            }
+            a.out[idx * a.P + p] = res;
+        }
+    }
+}
+
+// grad_loc / grad_wts must be zero on entry (the launcher memsets them).
+__global__ void __launch_bounds__(256) msmv_bwd_generic_kernel(const MsmvArgsDyn a) {
+    __shared__ int sH[RACF_MAX_LEVELS], sW[RACF_MAX_LEVELS];
+    if (threadIdx.x < a.L) { sH[threadIdx.x] = a.H[threadIdx.x]; sW[threadIdx.x] = a.W[threadIdx.x]; }
+    __syncthreads();
+    const long long total = (long long)a.B * a.Q * a.P * a.C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % a.C);
+        const long long bqp = idx / a.C;
+        const int p = (int)(bqp % a.P);
+        const long long bq = bqp / a.P;
+        const int b = (int)(bq / a.Q);
+        const float go = a.grad_out[(bq * a.C + c) * a.P + p];
+        const float* lp = a.loc + bqp * 3;
+        const float lx = lp[0], ly = lp[1];
+        const int v = msmv_view(lp[2], a.N);
+        if (v < 0 || v >= a.N) continue;
+        float glx = 0.f, gly = 0.f;
+        for (int l = 0; l < a.L; ++l) {
+            const int H = sH[l], W = sW[l];
+            const TapGeom g = tap_geometry(msmv_pixel(ly, H), msmv_pixel(lx, W), H, W);
+            if (g.mask == 0u) continue;
+            const float* f = nullptr;
+            float* gf = nullptr;
+#pragma unroll
+            for (int k = 0; k < RACF_MAX_LEVELS; ++k)
+                if (k == l) { f = a.feat[k]; gf = a.grad_feat[k]; }
+            const size_t vb = (((size_t)b * a.N + v) * H * W) * a.C + c;
+            f += vb;
+            gf += vb;
+            const size_t o = ((size_t)g.h_low * W + g.w_low) * a.C;
+            const size_t rs = (size_t)W * a.C;
+            const float s = a.wts[bqp * a.L + l];
+            const float hh = 1.f - g.lh, hw = 1.f - g.lw;
+            const float tv = go * s;
+            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+            if (g.mask & kTL) { v1 = __ldg(f + o); atomicAdd(gf + o, hh * hw * tv); }
+            if (g.mask & kTR) { v2 = __ldg(f + o + a.C); atomicAdd(gf + o + a.C, hh * g.lw * tv); }
+            if (g.mask & kBL) { v3 = __ldg(f + o + rs); atomicAdd(gf + o + rs, g.lh * hw * tv); }
+            if (g.mask & kBR) { v4 = __ldg(f + o + rs + a.C); atomicAdd(gf + o + rs + a.C, g.lh * g.lw * tv); }
+            const float val = hh * hw * v1 + hh * g.lw * v2 + g.lh * hw * v3 + g.lh * g.lw * v4;
+            const float gh = -hw * v1 - g.lw * v2 + hw * v3 + g.lw * v4;
+            const float gwd = -hh * v1 + hh * v2 - g.lh * v3 + g.lh * v4;
+            atomicAdd(a.grad_wts + bqp * a.L + l, go * val);
+            glx = fmaf((float)(W - 1) * gwd, tv, glx);
+            gly = fmaf((float)(H - 1) * gh, tv, gly);
+        }
+        atomicAdd(a.grad_loc + bqp * 3 + 0, glx);
+        atomicAdd(a.grad_loc + bqp * 3 + 1, gly);
+    }
+}
+
+struct MaskArgs {
+    int H[RACF_MAX_LEVELS];
+    int W[RACF_MAX_LEVELS];
+    const float* loc;
+    int32_t* view;
+    uint8_t* mask;
+    long long npts;
+    int N, L;
+};
+
+__global__ void __launch_bounds__(256) msmv_mask_kernel(const MaskArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.npts;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float lx = a.loc[i * 3], ly = a.loc[i * 3 + 1];
+        if (a.view) a.view[i] = msmv_view(a.loc[i * 3 + 2], a.N);
+        if (a.mask) {
+#pragma unroll
+            for (int l = 0; l < RACF_MAX_LEVELS; ++l) {
+                if (l < a.L) {
+                    const TapGeom g = tap_geometry(msmv_pixel(ly, a.H[l]), msmv_pixel(lx, a.W[l]), a.H[l], a.W[l]);
+                    a.mask[i * a.L + l] = (uint8_t)((g.in_range ? 1u : 0u) | (g.mask << 1));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host launchers
+// ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_msmv_common(const float* const* feats, const int* hw, int L, const float* loc, const float* wts,
+                             int B, int C, int N, int Q, int P) {
+    if (!feats || !hw || !loc || !wts) return RACF_ERR_NULL_POINTER;
+    if (L < 1 || L > RACF_MAX_LEVELS) return RACF_ERR_BAD_LEVELS;
+    if (B <= 0 || C <= 0 || N <= 0 || Q <= 0 || P <= 0) return RACF_ERR_BAD_SHAPE;
+    if (P > RACF_MSMV_MAX_POINT) return RACF_ERR_TOO_MANY_PTS;
+    for (int l = 0; l < L; ++l) {
+        if (!feats[l]) return RACF_ERR_NULL_POINTER;
+        if (hw[2 * l] <= 0 || hw[2 * l + 1] <= 0) return RACF_ERR_BAD_SHAPE;
+        // per-batch-element view stack is indexed with int32 float4 offsets on the fast path
+        if ((long long)N * hw[2 * l] * hw[2 * l + 1] * C >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
+    }
+    return RACF_OK;
+}
+
+template <int L>
+static int launch_fast(bool backward, const float* grad_out, const float* const* feats, float* const* grad_feats,
+                       const int* hw, const float* loc, const float* wts, int B, int C, int N, int Q, int P,
+                       float* out, float* grad_loc, float* grad_wts, cudaStream_t st) {
+    MsmvArgs<L> a;
+    for (int l = 0; l < L; ++l) {
+        a.feat[l] = feats[l];
+        a.grad_feat[l] = grad_feats ? grad_feats[l] : nullptr;
+        a.H[l] = hw[2 * l];
+        a.W[l] = hw[2 * l + 1];
+    }
+    a.loc = loc; a.wts = wts; a.grad_out = grad_out; a.out = out; a.grad_loc = grad_loc; a.grad_wts = grad_wts;
+    a.B = B; a.N = N; a.Q = Q; a.P = P; a.C = C;
+    const long long nq = (long long)B * Q;
+    const unsigned grid = (unsigned)((nq + kMsmvWarps - 1) / kMsmvWarps);
+    if (backward)
+        msmv_bwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
+    else
+        msmv_fwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+static int launch_generic(bool backward, const float* grad_out, const float* const* feats, float* const* grad_feats,
+                          const int* hw, int L, const float* loc, const float* wts, int B, int C, int N, int Q,
+                          int P, float* out, float* grad_loc, float* grad_wts, cudaStream_t st) {
+    MsmvArgsDyn a;
+    for (int l = 0; l < RACF_MAX_LEVELS; ++l) {
+        a.feat[l] = l < L ? feats[l] : nullptr;
+        a.grad_feat[l] = (l < L && grad_feats) ? grad_feats[l] : nullptr;
+        a.H[l] = l < L ? hw[2 * l] : 1;
+        a.W[l] = l < L ? hw[2 * l + 1] : 1;
+    }
+    a.loc = loc; a.wts = wts; a.grad_out = grad_out; a.out = out; a.grad_loc = grad_loc; a.grad_wts = grad_wts;
+    a.B = B; a.N = N; a.Q = Q; a.P = P; a.C = C; a.L = L;
+    const long long total = (long long)B * Q * C * (backward ? P : 1);
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148LL * 64 ? 148LL * 64 : (total + 255) / 256);
+    if (backward) {
+        cudaError_t e = cudaMemsetAsync(grad_loc, 0, sizeof(float) * (size_t)B * Q * P * 3, st);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(grad_wts, 0, sizeof(float) * (size_t)B * Q * P * L, st);
+        if (e != cudaSuccess) return (int)e;
+        msmv_bwd_generic_kernel<<<grid, 256, 0, st>>>(a);
+    } else {
+        msmv_fwd_generic_kernel<<<grid, 256, 0, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+static bool fast_ok(const float* const* feats, float* const* grad_feats, int L, int C, const float* io) {
+    if (C != 64 || !(L == 2 || L == 4 || L == 5) || !aligned16(io)) return false;
+    for (int l = 0; l < L; ++l) {
+        if (!aligned16(feats[l])) return false;
+        if (grad_feats && !aligned16(grad_feats[l])) return false;
+    }
+    return true;
+}
+
+}  // namespace racf
+
+using namespace racf;
+
+extern "C" int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels, const float* loc,
+                                 const float* weights, int batch, int channels, int num_views, int num_query,
+                                 int num_point, float* out, racf_stream_t stream) {
+    int rc = check_msmv_common(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query, num_point);
+    if (rc != RACF_OK) return rc;
+    if (!out) return RACF_ERR_NULL_POINTER;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fast_ok(feats, nullptr, num_levels, channels, out)) {
+        switch (num_levels) {
+            case 2: return launch_fast<2>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
+            case 4: return launch_fast<4>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
+            case 5: return launch_fast<5>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
+        }
+    }
+    return launch_generic(false, nullptr, feats, nullptr, hw, num_levels, loc, weights, batch, channels, num_views,
+                          num_query, num_point, out, nullptr, nullptr, st);
+}
+
+extern "C" int racf_msmv_backward(const float* grad_out, const float* const* feats, const int* hw, int num_levels,
+                                  const float* loc, const float* weights, int batch, int channels, int num_views,
+                                  int num_query, int num_point, float* const* grad_feats, float* grad_loc,
+                                  float* grad_weights, int zero_grad_feats, racf_stream_t stream) {
+    int rc = check_msmv_common(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query, num_point);
+    if (rc != RACF_OK) return rc;
+    if (!grad_out || !grad_feats || !grad_loc || !grad_weights) return RACF_ERR_NULL_POINTER;
+    for (int l = 0; l < num_levels; ++l)
+        if (!grad_feats[l]) return RACF_ERR_NULL_POINTER;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (zero_grad_feats) {
+        for (int l = 0; l < num_levels; ++l) {
+            const size_t n = (size_t)batch * num_views * hw[2 * l] * hw[2 * l + 1] * channels;
+            cudaError_t e = cudaMemsetAsync(grad_feats[l], 0, n * sizeof(float), st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (fast_ok(feats, grad_feats, num_levels, channels, grad_out)) {
+        switch (num_levels) {
+            case 2: return launch_fast<2>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st);
+            case 4: return launch_fast<4>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st);
+            case 5: return launch_fast<5>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st);
+        }
+    }
+    return launch_generic(true, grad_out, feats, grad_feats, hw, num_levels, loc, weights, batch, channels, num_views,
+                          num_query, num_point, nullptr, grad_loc, grad_weights, st);
+}
+
+extern "C" int racf_msmv_tap_masks(const int* hw, int num_levels, const float* loc, int batch, int num_views,
+                                   int num_query, int num_point, int32_t* view_index, uint8_t* tap_mask,
+                                   racf_stream_t stream) {
+    if (!hw || !loc) return RACF_ERR_NULL_POINTER;
+    if (num_levels < 1 || num_levels > RACF_MAX_LEVELS) return RACF_ERR_BAD_LEVELS;
+    if (batch <= 0 || num_views <= 0 || num_query <= 0 || num_point <= 0) return RACF_ERR_BAD_SHAPE;
+    MaskArgs a;
+    for (int l = 0; l < RACF_MAX_LEVELS; ++l) {
+        a.H[l] = l < num_levels ? hw[2 * l] : 1;
+        a.W[l] = l < num_levels ? hw[2 * l + 1] : 1;
+    }
+    a.loc = loc; a.view = view_index; a.mask = tap_mask;
+    a.npts = (long long)batch * num_query * num_point;
+    a.N = num_views; a.L = num_levels;
+    const unsigned grid = (unsigned)((a.npts + 255) / 256 > 148LL * 32 ? 148LL * 32 : (a.npts + 255) / 256);
+    msmv_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,304 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI via the reference-shaped Python API, against
+(i) the committed fixtures generated from the reference, (ii) the exact-arithmetic C oracle on seeded inputs,
+(iii) size-independent properties at the full racformer_r50_nuimg_704x256_f8 shapes, and (iv) the reference's own
+CUDA extension where oracle/_ref was built.
+
+Tolerances (also in DESIGN.md):
+  forward  vs exact-arithmetic oracle : rtol 1e-5, atol 1e-6 * max|feat|
+  forward  vs reference grid_sample   : rtol 1e-5, atol 5e-5 * max|feat|   (reference-vs-reference gap)
+  backward vs fp64-accumulating oracle: rtol 1e-4, atol 1e-5 * max|expected| (fp32 atomics / shuffle trees reorder sums)
+  view indices and validity masks     : bit-exact
+"""
+import pytest
+import torch
+
+from tests.helpers import (BWD_ATOL, BWD_RTOL, F8_SHAPES, FWD_ATOL_EXACT, FWD_ATOL_GRIDSAMPLE, FWD_RTOL, MSDA_CASES,
+                           MSMV_CASES, assert_close, load_golden, make_msda_inputs, make_msmv_inputs, msmv_feats,
+                           near_integer_pixel_msda, near_integer_pixel_msmv)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _scale(t):
+    return max(float(t.abs().max()), 1e-30)
+
+
+def _ops():
+    from racformer_b200 import wrapper
+    from racformer_b200 import multi_scale_deformable_attn_function as msda
+    return wrapper, msda
+
+
+def _oracle():
+    from oracle import c_oracle
+    return c_oracle
+
+
+# ------------------------------------------------------------------------------------------------ MSMV
+def _check_msmv_against_oracle(feats, loc, w, grad_out, what):
+    wrapper, _ = _ops()
+    co = _oracle()
+    fmax = max(_scale(f) for f in feats)
+    f_d = [f.to(DEV) for f in feats]
+    out = wrapper.msmv_forward(f_d, loc.to(DEV), w.to(DEV))
+    ref_out, ref_view, ref_mask = co.msmv_forward(feats, loc, w, with_masks=True)
+    assert_close(out, ref_out, FWD_RTOL, FWD_ATOL_EXACT * fmax, f"{what} forward vs oracle")
+    view, mask = wrapper.msmv_tap_masks([f.shape[2:4] for f in feats], loc.to(DEV), feats[0].shape[1])
+    assert torch.equal(view.cpu(), ref_view), f"{what}: view indices differ"
+    assert torch.equal(mask.cpu(), ref_mask), f"{what}: validity masks differ"
+    grads = wrapper.msmv_backward(grad_out.to(DEV), f_d, loc.to(DEV), w.to(DEV))
+    rgf, rgl, rgw = co.msmv_backward(grad_out, feats, loc, w)
+    for i, (g, r) in enumerate(zip(grads[:len(feats)], rgf)):
+        assert_close(g, r, BWD_RTOL, BWD_ATOL * _scale(r), f"{what} grad_feat{i} vs oracle")
+    assert_close(grads[-2], rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), f"{what} grad_loc vs oracle")
+    assert_close(grads[-1], rgw, BWD_RTOL, BWD_ATOL * _scale(rgw), f"{what} grad_w vs oracle")
+    assert bool((grads[-2][..., 2] == 0).all()), "grad of the view coordinate must be exactly 0"
+    return out, grads
+
+
+@pytest.mark.parametrize("case", MSMV_CASES)
+def test_msmv_golden_fixture(case):
+    d = load_golden(case)
+    feats = msmv_feats(d)
+    out, grads = _check_msmv_against_oracle(feats, d["loc"], d["w"], d["grad_out"], case)
+    fmax = max(_scale(f) for f in feats)
+    assert_close(out, d["out"], FWD_RTOL, FWD_ATOL_GRIDSAMPLE * fmax, f"{case} forward vs reference grid_sample")
+    for i in range(len(feats)):
+        assert_close(grads[i], d[f"grad_feat{i}"], BWD_RTOL, 1e-4 * _scale(d[f"grad_feat{i}"]), f"{case} grad_feat{i} vs reference")
+    assert_close(grads[-1], d["grad_w"], BWD_RTOL, 1e-4 * _scale(d["grad_w"]), f"{case} grad_w vs reference")
+    ok = ~near_integer_pixel_msmv(d["loc"], [f.shape[2:4] for f in feats])
+    assert_close(grads[-2].cpu()[..., :2][ok], d["grad_loc"][..., :2][ok], BWD_RTOL,
+                 1e-4 * _scale(d["grad_loc"][..., :2][ok]), f"{case} grad_loc vs reference")
+    wrapper, _ = _ops()
+    v2 = wrapper.msmv_sampling_v2([f.to(DEV) for f in feats], d["loc"].to(DEV), d["w"].to(DEV))
+    assert_close(v2, d["out_v2"], FWD_RTOL, FWD_ATOL_GRIDSAMPLE * fmax, f"{case} v2 vs reference")
+
+
+@pytest.mark.parametrize("levels,C,P,lo,hi", [
+    (4, 64, 12, 0.0, 1.0),      # fast path, RaCFormer point count, everything valid
+    (4, 64, 12, -0.1, 1.1),     # mixed validity
+    (4, 64, 7, -0.3, 1.3),      # ragged P (scalar store path)
+    (2, 64, 12, -0.1, 1.1),     # c45
+    (5, 64, 4, -0.1, 1.1),      # c23456
+    (3, 64, 5, -0.1, 1.1),      # level count without a fast kernel -> generic path
+    (4, 32, 6, -0.1, 1.1),      # generic path (C != 64)
+    (4, 64, 12, -5.0, -2.0),    # nothing valid at all: zeros everywhere
+])
+def test_msmv_seeded_vs_oracle(levels, C, P, lo, hi):
+    shapes = [(16, 44), (8, 22), (4, 11), (2, 6), (1, 3)][:levels]
+    feats, loc, w, g = make_msmv_inputs(11 + levels + P, Bp=3, N=6, C=C, Q=37, P=P, shapes=shapes, lo=lo, hi=hi)
+    out, grads = _check_msmv_against_oracle(feats, loc, w, g, f"L{levels} C{C} P{P} [{lo},{hi}]")
+    if hi < 0:
+        assert float(out.abs().max()) == 0.0
+        assert all(float(t.abs().max()) == 0.0 for t in grads)
+
+
+def test_msmv_special_coordinates_and_views():
+    """NaN / Inf / out-of-range view coordinates contribute exactly zero and never fault."""
+    feats, loc, w, g = make_msmv_inputs(5, Bp=2, N=3, C=64, Q=8, P=4, shapes=[(8, 12), (4, 6), (2, 3), (1, 2)])
+    loc[0, 0, 0, 0] = float("nan")
+    loc[0, 0, 1, 1] = float("inf")
+    loc[0, 0, 2, 0] = -float("inf")
+    loc[0, 1, 0, 2] = 1.5      # view index 3 >= N: reference would read out of bounds; we define it as "no contribution"
+    loc[0, 1, 1, 2] = -0.5     # view index -1
+    out, grads = _check_msmv_against_oracle(feats, loc, w, g, "special coordinates")
+    assert torch.isfinite(out).all()
+    assert float(out[0, 0, :, :3].abs().max()) == 0.0
+    assert float(out[0, 1, :, :2].abs().max()) == 0.0
+
+
+def test_msmv_f8_full_size_forward_vs_oracle_and_properties():
+    """racformer_r50_nuimg_704x256_f8, batch 1: B'=32, N=6, C=64, Q=900, P=12 (mixed case)."""
+    wrapper, _ = _ops()
+    co = _oracle()
+    feats, loc, w, g = make_msmv_inputs(0, Bp=32, N=6, C=64, Q=900, P=12, shapes=F8_SHAPES, lo=-0.1, hi=1.1)
+    f_d, loc_d, w_d, g_d = [f.to(DEV) for f in feats], loc.to(DEV), w.to(DEV), g.to(DEV)
+    out = wrapper.msmv_forward(f_d, loc_d, w_d)
+    assert torch.equal(out, wrapper.msmv_forward(f_d, loc_d, w_d)), "forward must be deterministic"
+    ref_out, ref_view, ref_mask = co.msmv_forward(feats, loc, w, with_masks=True)
+    assert_close(out, ref_out, FWD_RTOL, FWD_ATOL_EXACT * max(_scale(f) for f in feats), "f8 forward vs oracle")
+    view, mask = wrapper.msmv_tap_masks(F8_SHAPES, loc_d, 6)
+    assert torch.equal(view.cpu(), ref_view) and torch.equal(mask.cpu(), ref_mask)
+    # adjoint identities: the op is linear in the features and in the weights
+    grads = wrapper.msmv_backward(g_d, f_d, loc_d, w_d)
+    lhs = float((out.double() * g_d.double()).sum())
+    rhs_feat = sum(float((gf.double() * f.double()).sum()) for gf, f in zip(grads[:4], f_d))
+    rhs_w = float((grads[-1].double() * w_d.double()).sum())
+    assert rhs_feat == pytest.approx(lhs, rel=1e-5, abs=1e-2)
+    assert rhs_w == pytest.approx(lhs, rel=1e-5, abs=1e-2)
+    # grad_loc / grad_w against the oracle on the first two batch elements (full rows, cheap)
+    sub = slice(0, 2)
+    rgf, rgl, rgw = co.msmv_backward(g[sub], [f[sub] for f in feats], loc[sub], w[sub])
+    assert_close(grads[-2][sub], rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), "f8 grad_loc vs oracle")
+    assert_close(grads[-1][sub], rgw, BWD_RTOL, BWD_ATOL * _scale(rgw), "f8 grad_w vs oracle")
+    for i in range(4):
+        assert_close(grads[i][sub], rgf[i], BWD_RTOL, BWD_ATOL * _scale(rgf[i]), f"f8 grad_feat{i} vs oracle")
+    # constant features + weights summing to one -> constant output wherever all four corners exist on all levels
+    ones = [torch.ones_like(f) for f in f_d]
+    o1 = wrapper.msmv_forward(ones, loc_d, w_d)
+    all_valid = (mask == 31).all(-1)[:, :, None, :].expand_as(o1)
+    assert float((o1[all_valid] - 1).abs().max()) < 1e-5
+
+
+def test_msmv_training_and_3cam_shapes():
+    """B=2 training shape (B'=64, Q=1220) and the 3cam variant (N=3): adjoint identity + determinism."""
+    wrapper, _ = _ops()
+    for Bp, N, Q in ((64, 6, 1220), (32, 3, 900)):
+        feats, loc, w, g = make_msmv_inputs(3, Bp=Bp, N=N, C=64, Q=Q, P=12, shapes=F8_SHAPES, device=DEV)
+        out = wrapper.msmv_forward(feats, loc, w)
+        grads = wrapper.msmv_backward(g, feats, loc, w)
+        lhs = float((out.double() * g.double()).sum())
+        rhs = sum(float((gf.double() * f.double()).sum()) for gf, f in zip(grads[:4], feats))
+        assert rhs == pytest.approx(lhs, rel=1e-5, abs=1e-2)
+        del feats, grads, out
+        torch.cuda.empty_cache()
+
+
+def test_msmv_autograd_function_and_streams():
+    wrapper, _ = _ops()
+    co = _oracle()
+    feats, loc, w, g = make_msmv_inputs(7, Bp=2, N=6, C=64, Q=20, P=12, shapes=[(16, 44), (8, 22), (4, 11), (2, 6)],
+                                        lo=-0.1, hi=1.1)
+    f_d = [f.to(DEV).requires_grad_() for f in feats]
+    loc_d, w_d = loc.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = wrapper.msmv_sampling(f_d, loc_d, w_d)
+        # a non-contiguous upstream gradient exercises the .contiguous() in backward (wrapper.py:93)
+        (out.permute(0, 1, 3, 2) * g.to(DEV).permute(0, 1, 3, 2)).sum().backward()
+    torch.cuda.current_stream().wait_stream(side)
+    rgf, rgl, rgw = co.msmv_backward(g, feats, loc, w)
+    for f, r in zip(f_d, rgf):
+        assert_close(f.grad, r, BWD_RTOL, BWD_ATOL * _scale(r), "autograd grad_feat")
+    assert_close(loc_d.grad, rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), "autograd grad_loc")
+    assert_close(w_d.grad, rgw, BWD_RTOL, BWD_ATOL * _scale(rgw), "autograd grad_w")
+
+
+def test_msmv_empty_and_errors():
+    wrapper, _ = _ops()
+    feats = [torch.zeros(2, 6, 4, 4, 64, device=DEV), torch.zeros(2, 6, 2, 2, 64, device=DEV)]
+    out = wrapper.msmv_sampling(feats, torch.zeros(2, 0, 12, 3, device=DEV), torch.zeros(2, 0, 12, 2, device=DEV))
+    assert out.shape == (2, 0, 64, 12)
+    with pytest.raises(RuntimeError, match="num_point exceed limits"):
+        wrapper.msmv_sampling(feats, torch.zeros(2, 1, 129, 3, device=DEV), torch.zeros(2, 1, 129, 2, device=DEV))
+    with pytest.raises(RuntimeError, match="attn_weight must be"):
+        wrapper.msmv_sampling(feats, torch.zeros(2, 1, 4, 3, device=DEV), torch.zeros(2, 1, 4, 4, device=DEV))
+    with pytest.raises(RuntimeError, match="Float"):
+        wrapper.msmv_sampling([f.half() for f in feats], torch.zeros(2, 1, 4, 3, device=DEV),
+                              torch.zeros(2, 1, 4, 2, device=DEV))
+
+
+def test_msmv_vs_reference_cuda_extension():
+    """The reference's own kernel (oracle/_ref, built by oracle/build_ref.py from /root/reference) on the same inputs."""
+    from oracle import build_ref
+    ext = build_ref.load_prebuilt()
+    if ext is None:
+        pytest.skip("oracle/_ref/_msmv_sampling_cuda.so not built")
+    wrapper, _ = _ops()
+    feats, loc, w, g = make_msmv_inputs(0, Bp=8, N=6, C=64, Q=300, P=12, shapes=F8_SHAPES, lo=-0.1, hi=1.1, device=DEV)
+    out = wrapper.msmv_forward(feats, loc, w)
+    ref = ext._ms_deform_attn_cuda_c2345_forward(*feats, loc, w)
+    torch.cuda.synchronize()
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL_EXACT * max(_scale(f) for f in feats), "forward vs reference CUDA ext")
+    grads = wrapper.msmv_backward(g, feats, loc, w)
+    rgrads = ext._ms_deform_attn_cuda_c2345_backward(g, *feats, loc, w)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(grads, rgrads)):
+        assert_close(a, b, BWD_RTOL, 2e-5 * _scale(b), f"backward[{i}] vs reference CUDA ext")
+
+
+# ------------------------------------------------------------------------------------------------ MSDA
+def _check_msda_against_oracle(value, shapes, lsi, loc, aw, grad_out, what, im2col_step=64):
+    _, msda = _ops()
+    co = _oracle()
+    vmax = _scale(value)
+    args_d = [t.to(DEV) for t in (value, shapes, lsi, loc, aw)]
+    out = msda.ext_module.ms_deform_attn_forward(*args_d, im2col_step=im2col_step)
+    ref_out, ref_mask = co.msda_forward(value, shapes, lsi, loc, aw, with_masks=True)
+    assert_close(out, ref_out, FWD_RTOL, FWD_ATOL_EXACT * vmax, f"{what} forward vs oracle")
+    mask = msda.msda_tap_masks(args_d[1], args_d[3])
+    assert torch.equal(mask.cpu(), ref_mask), f"{what}: validity masks differ"
+    gv = torch.zeros_like(args_d[0])
+    gl = torch.full_like(args_d[3], 7.0)   # must be fully overwritten
+    ga = torch.full_like(args_d[4], 7.0)
+    msda.ext_module.ms_deform_attn_backward(*args_d, grad_out.to(DEV), gv, gl, ga, im2col_step=im2col_step)
+    rgv, rgl, rga = co.msda_backward(value, shapes, lsi, loc, aw, grad_out)
+    assert_close(gv, rgv, BWD_RTOL, BWD_ATOL * _scale(rgv), f"{what} grad_value vs oracle")
+    assert_close(gl, rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), f"{what} grad_loc vs oracle")
+    assert_close(ga, rga, BWD_RTOL, BWD_ATOL * _scale(rga), f"{what} grad_attn vs oracle")
+    return out, (gv, gl, ga)
+
+
+@pytest.mark.parametrize("case", MSDA_CASES)
+def test_msda_golden_fixture(case):
+    d = load_golden(case)
+    out, (gv, gl, ga) = _check_msda_against_oracle(d["value"], d["spatial_shapes"], d["level_start_index"], d["loc"],
+                                                   d["aw"], d["grad_out"], case)
+    assert_close(out, d["out"], FWD_RTOL, FWD_ATOL_GRIDSAMPLE * _scale(d["value"]), f"{case} forward vs grid_sample")
+    assert_close(gv, d["grad_value"], BWD_RTOL, 1e-4 * _scale(d["grad_value"]), f"{case} grad_value vs grid_sample")
+    assert_close(ga, d["grad_aw"], BWD_RTOL, 1e-4 * _scale(d["grad_aw"]), f"{case} grad_attn vs grid_sample")
+    ok = ~near_integer_pixel_msda(d["loc"], d["spatial_shapes"].tolist())
+    assert_close(gl.cpu()[ok], d["grad_loc"][ok], BWD_RTOL, 1e-4 * _scale(d["grad_loc"][ok]), f"{case} grad_loc vs grid_sample")
+
+
+@pytest.mark.parametrize("shapes,M,D,P,lo,hi", [
+    ([(32, 32)], 4, 64, 20, 0.0, 1.0),                 # RaCFormer configuration, scaled-down map
+    ([(32, 32)], 4, 64, 20, -0.05, 1.05),
+    ([(16, 20), (8, 10), (4, 5), (2, 3)], 8, 64, 4, -0.1, 1.1),   # Deformable-DETR style, 4 levels
+    ([(12, 7)], 2, 64, 40, -0.1, 1.1),                 # more than 32 taps per (b,q,m): two staging rounds
+    ([(16, 20), (8, 10)], 8, 32, 4, -0.1, 1.1),        # generic path
+    ([(9, 9)], 3, 16, 5, -2.0, -1.0),                  # nothing valid
+])
+def test_msda_seeded_vs_oracle(shapes, M, D, P, lo, hi):
+    value, sp, lsi, loc, aw, g = make_msda_inputs(23 + P, B=4, M=M, D=D, Q=33, P=P, shapes=shapes, lo=lo, hi=hi)
+    _check_msda_against_oracle(value, sp, lsi, loc, aw, g, f"{shapes} M{M} D{D} P{P}", im2col_step=2)
+
+
+def test_msda_f8_full_size():
+    """BEV cross-attention at the f8 shapes: value [8,16384,4,64], Q=900, 20 points, 128x128 map."""
+    _, msda = _ops()
+    co = _oracle()
+    value, sp, lsi, loc, aw, g = make_msda_inputs(0, B=8, M=4, D=64, Q=900, P=20, shapes=[(128, 128)], lo=-0.05, hi=1.05)
+    args_d = [t.to(DEV) for t in (value, sp, lsi, loc, aw)]
+    out = msda.ext_module.ms_deform_attn_forward(*args_d, im2col_step=64)
+    assert torch.equal(out, msda.ext_module.ms_deform_attn_forward(*args_d, im2col_step=64))
+    ref_out, ref_mask = co.msda_forward(value, sp, lsi, loc, aw, with_masks=True)
+    assert_close(out, ref_out, FWD_RTOL, FWD_ATOL_EXACT * _scale(value), "f8 msda forward vs oracle")
+    assert torch.equal(msda.msda_tap_masks(args_d[1], args_d[3]).cpu(), ref_mask)
+    gv, gl, ga = torch.zeros_like(args_d[0]), torch.empty_like(args_d[3]), torch.empty_like(args_d[4])
+    msda.ext_module.ms_deform_attn_backward(*args_d, g.to(DEV), gv, gl, ga, im2col_step=64)
+    rgv, rgl, rga = co.msda_backward(value, sp, lsi, loc, aw, g)
+    assert_close(gv, rgv, BWD_RTOL, BWD_ATOL * _scale(rgv), "f8 msda grad_value vs oracle")
+    assert_close(gl, rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), "f8 msda grad_loc vs oracle")
+    assert_close(ga, rga, BWD_RTOL, BWD_ATOL * _scale(rga), "f8 msda grad_attn vs oracle")
+
+
+def test_msda_autograd_function_matches_torch_port():
+    """MultiScaleDeformableAttnFunction_fp32.apply end to end vs the grid_sample port (autograd of both)."""
+    _, msda = _ops()
+    from oracle import reference_port
+    value, sp, lsi, loc, aw, g = make_msda_inputs(9, B=2, M=4, D=64, Q=50, P=20, shapes=[(32, 32)], lo=0.02, hi=0.98)
+    leaf = [t.to(DEV).requires_grad_() for t in (value, loc, aw)]
+    out = msda.MultiScaleDeformableAttnFunction_fp32.apply(leaf[0], sp.to(DEV), lsi.to(DEV), leaf[1], leaf[2], 64)
+    out.backward(g.to(DEV))
+    cpu_leaf = [t.clone().requires_grad_() for t in (value, loc, aw)]
+    ref = reference_port.msda_torch(cpu_leaf[0], sp, cpu_leaf[1], cpu_leaf[2])
+    ref.backward(g)
+    assert_close(out, ref, FWD_RTOL, FWD_ATOL_GRIDSAMPLE * _scale(value), "Function forward vs port")
+    assert_close(leaf[0].grad, cpu_leaf[0].grad, BWD_RTOL, 1e-4 * _scale(cpu_leaf[0].grad), "Function grad_value vs port")
+    assert_close(leaf[2].grad, cpu_leaf[2].grad, BWD_RTOL, 1e-4 * _scale(cpu_leaf[2].grad), "Function grad_attn vs port")
+    ok = ~near_integer_pixel_msda(loc, sp.tolist())
+    assert_close(leaf[1].grad.cpu()[ok], cpu_leaf[1].grad[ok], BWD_RTOL, 1e-4 * _scale(cpu_leaf[1].grad), "Function grad_loc vs port")
+
+
+def test_msda_errors():
+    _, msda = _ops()
+    value = torch.zeros(6, 16, 1, 64, device=DEV)
+    sp, lsi = torch.tensor([[4, 4]], device=DEV), torch.tensor([0], device=DEV)
+    loc, aw = torch.zeros(6, 1, 1, 1, 1, 2, device=DEV), torch.zeros(6, 1, 1, 1, 1, device=DEV)
+    with pytest.raises(RuntimeError, match="im2col_step"):
+        msda.ext_module.ms_deform_attn_forward(value, sp, lsi, loc, aw, im2col_step=4)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        msda.ext_module.ms_deform_attn_forward(value.permute(0, 2, 1, 3), sp, lsi, loc, aw, im2col_step=64)

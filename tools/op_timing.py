@@ -1,0 +1,104 @@
+"""Time the four hot-path kernels at the racformer_r50_nuimg_704x256_f8 shapes (CUDA events, L2 flushed between
+iterations) and print one JSON object. Also the short command profiled with ncu (see profiles/).
+
+    python tools/op_timing.py [--iters 20] [--case allvalid|mixed] [--ops msmv_fwd,msmv_bwd,msda_fwd,msda_bwd]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from racformer_b200 import wrapper  # noqa: E402
+from racformer_b200.multi_scale_deformable_attn_function import ext_module  # noqa: E402
+from racformer_b200.roofline import msda_bytes, msmv_bytes  # noqa: E402
+
+F8_SHAPES = [(64, 176), (32, 88), (16, 44), (8, 22)]
+
+
+def make_inputs(case, Bp=32, N=6, C=64, Q=900, P=12, dev="cuda"):
+    torch.manual_seed(0)
+    lo, hi = (0.0, 1.0) if case == "allvalid" else (-0.1, 1.1)
+    feats = [torch.randn(Bp, N, h, w, C, device=dev) for h, w in F8_SHAPES]
+    xy = torch.rand(Bp, Q, P, 2, device=dev) * (hi - lo) + lo
+    view = torch.randint(0, N, (Bp, Q, P, 1), device=dev).float() / (N - 1)
+    loc = torch.cat([xy, view], -1).contiguous()
+    w = torch.softmax(torch.randn(Bp, Q, P, 4, device=dev), -1).contiguous()
+    g = torch.randn(Bp, Q, C, P, device=dev)
+    B, S, M, D, MP = 8, 128 * 128, 4, 64, 20
+    mlo, mhi = (0.0, 1.0) if case == "allvalid" else (-0.05, 1.05)
+    value = torch.randn(B, S, M, D, device=dev)
+    mloc = (torch.rand(B, Q, M, 1, MP, 2, device=dev) * (mhi - mlo) + mlo).contiguous()
+    aw = torch.softmax(torch.randn(B, Q, M, 1, MP, device=dev), -1).contiguous()
+    mg = torch.randn(B, Q, M * D, device=dev)
+    sp = torch.tensor([[128, 128]], dtype=torch.long, device=dev)
+    lsi = torch.tensor([0], dtype=torch.long, device=dev)
+    return dict(feats=feats, loc=loc, w=w, g=g, value=value, sp=sp, lsi=lsi, mloc=mloc, aw=aw, mg=mg)
+
+
+def time_op(fn, iters, warm, flush):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return {"best_ms": ts[0], "median_ms": ts[len(ts) // 2], "mean_ms": sum(ts) / len(ts)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--case", default="allvalid")
+    ap.add_argument("--ops", default="msmv_fwd,msmv_bwd,msda_fwd,msda_bwd")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    d = make_inputs(args.case)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    peaks = {"hbm_gbs": 6541.8}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    gv = torch.empty_like(d["value"])
+    gl, ga = torch.empty_like(d["mloc"]), torch.empty_like(d["aw"])
+
+    def msda_bwd():
+        gv.zero_()
+        ext_module.ms_deform_attn_backward(d["value"], d["sp"], d["lsi"], d["mloc"], d["aw"], d["mg"], gv, gl, ga,
+                                           im2col_step=64)
+
+    ops = {
+        "msmv_fwd": lambda: wrapper.msmv_forward(d["feats"], d["loc"], d["w"]),
+        "msmv_bwd": lambda: wrapper.msmv_backward(d["g"], d["feats"], d["loc"], d["w"]),
+        "msda_fwd": lambda: ext_module.ms_deform_attn_forward(d["value"], d["sp"], d["lsi"], d["mloc"], d["aw"], im2col_step=64),
+        "msda_bwd": msda_bwd,
+    }
+    _, mask = wrapper.msmv_tap_masks(F8_SHAPES, d["loc"], 6)
+    from racformer_b200.multi_scale_deformable_attn_function import msda_tap_masks
+    mmask = msda_tap_masks(d["sp"], d["mloc"])
+    algo = {}
+    algo["msmv_fwd"], algo["msmv_bwd"] = msmv_bytes(mask, C=64, L=4, feat_bytes=sum(f.numel() * 4 for f in d["feats"]))
+    algo["msda_fwd"], algo["msda_bwd"] = msda_bytes(mmask, D=64, value_bytes=d["value"].numel() * 4)
+    res = {"case": args.case, "gpu": torch.cuda.get_device_name(0), "l2_flush": not args.no_flush, "peak_hbm_gbs": peaks["hbm_gbs"]}
+    for name in args.ops.split(","):
+        t = time_op(ops[name], args.iters, args.warmup, flush)
+        gbs = algo[name] / (t["median_ms"] * 1e-3) / 1e9
+        res[name] = dict(t, algo_bytes=algo[name], gbs=gbs, frac_of_measured_peak=gbs / peaks["hbm_gbs"])
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
