@@ -1,0 +1,229 @@
+"""bench.py -- the driver's benchmark contract for the RaCFormer sampling hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one sample of synthetic input at the racformer_r50_nuimg_704x256_f8
+shapes (see bench_workloads.py for the workloads). One process per GPU; the path shards by sample with no
+data-path collective, so N GPUs run N independent samples per step ("scaling": "weak").
+
+Prints ONE JSON line on rank 0 (keys: see the task contract): value = whole-job samples/s with inputs resident in
+HBM; e2e = the same through the public API with pinned-host inputs copied in and the result read back every step;
+roofline = dominant kernel (MSMV forward), live CUDA-event time vs MEASURED_PEAKS.json; cpu_baseline = the reference's
+PyTorch grid_sample path (oracle port) on the host cores.
+
+`--impl reference` times only that CPU path (rank 0 only) on the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference_arm(args, rank):
+    """The reference's own CPU implementation of the path (PyTorch grid_sample; oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import bench_workloads as workloads
+    wl = workloads.build(args.workload, device="cpu", seed=0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(args.warmup):
+        wl.reference_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wl.reference_step()
+    dt = time.perf_counter() - t0
+    value = args.steps * wl.reference_samples_per_step / dt
+    line = {
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+        "cpu_baseline": {"value": value, "unit": wl.unit, "cores": cores, "kind": "port",
+                         "sample": wl.reference_sample_description},
+        "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("RACF_BENCH_WORKLOAD", "decoder_sampling_f8"))
+    ap.add_argument("--cpu-baseline-steps", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    import bench_workloads as workloads
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the ops)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = workloads.build(args.workload, device=dev, seed=rank)
+    hbm_peak, peak_src = load_peaks()
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        wl.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    wl.reset_kernel_timers()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        wl.step(time_kernels=True)
+    stop.record()
+    barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    value = world * args.steps * wl.samples_per_step / (total_ms * 1e-3)
+    roof = wl.roofline(hbm_peak, peak_src)
+    launches = wl.launches_per_step * args.steps
+
+    # ---- end to end: pinned host inputs -> H2D -> ops -> D2H result, every step --------------------------------
+    wl.prepare_host_inputs()
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s2.record()
+    for _ in range(e2e_steps):
+        wl.e2e_step()
+    e2.record()
+    barrier()
+    ms2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * wl.samples_per_step / (float(ms2) * 1e-3)
+    clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's PyTorch path on a bounded sample ----------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_wl = workloads.build(args.workload, device="cpu", seed=0)
+        cpu_wl.reference_step()
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_baseline_steps):
+            cpu_wl.reference_step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": args.cpu_baseline_steps * cpu_wl.reference_samples_per_step / dt, "unit": wl.unit,
+                        "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_baseline_steps} steps of: {cpu_wl.reference_sample_description}"}
+
+    if rank == 0:
+        line = {
+            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": wl.d2h_bytes_per_step, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu_baseline,
+            "kernels": wl.kernel_report(hbm_peak),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -301,4 +301,5 @@ def test_msda_errors():
     with pytest.raises(RuntimeError, match="im2col_step"):
         msda.ext_module.ms_deform_attn_forward(value, sp, lsi, loc, aw, im2col_step=4)
     with pytest.raises(RuntimeError, match="contiguous"):
-        msda.ext_module.ms_deform_attn_forward(value.permute(0, 2, 1, 3), sp, lsi, loc, aw, im2col_step=64)
+        strided = torch.zeros(6, 16, 1, 128, device=DEV)[..., ::2]
+        msda.ext_module.ms_deform_attn_forward(strided, sp, lsi, loc, aw, im2col_step=64)
