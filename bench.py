@@ -123,8 +123,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("RACF_BENCH_WORKLOAD", "decoder_sampling_f8"))
-    ap.add_argument("--cpu-baseline-steps", type=int, default=12)
+    ap.add_argument("--workload", default=os.environ.get("RACF_BENCH_WORKLOAD", "decoder_forward_f8"))
+    ap.add_argument("--cpu-baseline-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -136,17 +136,12 @@ def main():
 
     import torch.distributed as dist
     import bench_workloads as workloads
+    from racformer_b200 import parallel
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the ops)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev = parallel.init_distributed("nccl")
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        parallel.barrier(dev)
 
     wl = workloads.build(args.workload, device=dev, seed=rank)
     hbm_peak, peak_src = load_peaks()
@@ -165,10 +160,7 @@ def main():
         wl.step(time_kernels=True)
     stop.record()
     barrier()
-    ms = torch.tensor([start.elapsed_time(stop)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms)
+    total_ms = parallel.max_over_ranks(start.elapsed_time(stop), dev)   # device time, max over ranks
     value = world * args.steps * wl.samples_per_step / (total_ms * 1e-3)
     roof = wl.roofline(hbm_peak, peak_src)
     launches = wl.launches_per_step * args.steps
@@ -186,15 +178,13 @@ def main():
         wl.e2e_step()
     e2.record()
     barrier()
-    ms2 = torch.tensor([s2.elapsed_time(e2)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * wl.samples_per_step / (float(ms2) * 1e-3)
+    ms2 = parallel.max_over_ranks(s2.elapsed_time(e2), dev)
+    e2e_value = world * e2e_steps * wl.samples_per_step / (ms2 * 1e-3)
     clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's PyTorch path on a bounded sample ----------------------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and "train" not in args.workload:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         cpu_wl = workloads.build(args.workload, device="cpu", seed=0)

@@ -238,7 +238,253 @@ class SamplingWorkload:
         return out
 
 
+class DecoderWorkload:
+    """Config 2: RaCFormer decoder forward (6 iterations: SASA, radar/LSS BEV deformable attention, MSMV image
+    sampling, adaptive mixing, FFN, heads) at 704x256 f8, batch 1, synthetic features, random-init weights."""
+    metric = "decoder samples/s (RaCFormer R50 704x256 f8 decoder forward, batch 1)"
+    unit = "samples/s"
+    reference_sample_description = ("one of the six decoder iterations per step (1/6 sample) of the same decoder on the "
+                                    "reference's PyTorch CPU path (grid_sample ops, reference schedule without hoisting), "
+                                    "full f8 shapes, all host threads")
+
+    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True):
+        from racformer_b200.decoder import RaCFormerTransformer, SamplingOps
+        from racformer_b200.synthetic import D_REGION_LIST, PC_RANGE, make_decoder_inputs
+        self.name, self.device, self.layers, self.hoist = name, torch.device(device), num_layers, hoist
+        self.samples_per_step = 1
+        self.on_gpu = self.device.type == "cuda"
+        self.cfg = dict(embed_dims=256, num_frames=8, num_points=4, num_points_bev=4, num_layers=num_layers, num_levels=4,
+                        num_classes=10, code_size=10, img_depth_num=3, bev_depth_num=5, pc_range=PC_RANGE, num_ray=150,
+                        d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=6)
+        self.timers = {}
+        self._time_kernels = False
+        if self.on_gpu:
+            base = SamplingOps()
+            ops = SamplingOps(msmv=lambda *a: self._timed("msmv_fwd", base.msmv, a),
+                              msda=lambda *a: self._timed("msda_fwd", base.msda, a))
+        else:   # CPU baseline leg: the oracle's port of the reference's PyTorch ops (never used for the GPU numbers)
+            from oracle import reference_port
+            ops = SamplingOps(msmv=reference_port.msmv_sampling_torch_channel_last,
+                              msda=lambda v, sh, lsi, loc, aw, step: reference_port.msda_torch(v, sh, loc, aw))
+        torch.manual_seed(0)
+        self.model = RaCFormerTransformer(**self.cfg, ops=ops, hoist_invariants=hoist if self.on_gpu else False)
+        self.model.init_weights()
+        self.model.eval().to(self.device)
+        self.inp = make_decoder_inputs(seed=100 + seed, device=self.device)
+        self.launches_per_step = 3 * num_layers
+        self.h2d_bytes_per_step = 0
+        self.d2h_bytes_per_step = 0
+        self._captured = None
+
+    def config(self):
+        return {"workload": self.name, "shapes": "racformer_r50_nuimg_704x256_f8", "batch_per_gpu": 1, "num_query": 900,
+                "frames": 8, "cams": 6, "fpn_levels": 4, "embed_dims": 256, "decoder_layers": self.layers,
+                "msmv_points": 12, "msda_points": 20, "bev": [128, 128], "weights": "random init (seed 0)",
+                "hoist_invariants": self.hoist, "includes_channel_last_relayout": True,
+                "conv_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                "sharding": "one sample per GPU, no data-path collective",
+                "l2_policy": "inputs larger than L2 (735 MB pyramid + 2x134 MB BEV maps vs 126 MB L2); no flush"}
+
+    def _timed(self, key, fn, args):
+        if not self._time_kernels:
+            return fn(*args)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args)
+        b.record()
+        self.timers.setdefault(key, []).append((a, b))
+        if self._captured is None and key == "msmv_fwd":
+            self._captured = (args[1].detach().clone(), [tuple(f.shape[2:4]) for f in args[0]], args[0][0].shape[1])
+        return out
+
+    def reset_kernel_timers(self):
+        self.timers = {}
+
+    def _forward(self, inp):
+        with torch.no_grad():
+            return self.model(inp["query_bbox"], inp["query_feat"], inp["mlvl_feats"], inp["lss_bev"], inp["radar_bev"],
+                              None, inp["img_metas"])
+
+    def step(self, time_kernels=False):
+        self._time_kernels = time_kernels
+        out = self._forward(self.inp)
+        self._time_kernels = False
+        return out
+
+    def kernel_report(self, hbm_peak):
+        from racformer_b200 import wrapper
+        from racformer_b200.roofline import msmv_bytes
+        torch.cuda.synchronize()
+        rep = {}
+        algo = {}
+        if self._captured is not None:
+            loc, hw, n_views = self._captured
+            _, mask = wrapper.msmv_tap_masks(hw, loc, n_views)
+            feat_bytes = sum(loc.shape[0] * n_views * h * w * 64 * 4 for h, w in hw)
+            algo["msmv_fwd"] = msmv_bytes(mask, C=64, L=len(hw), feat_bytes=feat_bytes)[0]
+            rep["msmv_valid_corner_fraction"] = float(((mask.int() >> 1) & 1).float().mean() + ((mask.int() >> 2) & 1).float().mean()
+                                                      + ((mask.int() >> 3) & 1).float().mean() + ((mask.int() >> 4) & 1).float().mean()) / 4
+        for key, pairs in self.timers.items():
+            ms = [a.elapsed_time(b) for a, b in pairs]
+            avg = sum(ms) / len(ms)
+            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / max(1, len(ms) // (
+                self.layers * (2 if key == "msda_fwd" else 1)))}
+            if key in algo:
+                gbs = algo[key] / (avg * 1e-3) / 1e9
+                rep[key].update({"algorithmic_bytes": algo[key], "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+        return rep
+
+    def roofline(self, hbm_peak, peak_src):
+        rep = self.kernel_report(hbm_peak)
+        k = rep["msmv_fwd"]
+        traffic = None
+        try:
+            import json
+            import os
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+            traffic = json.load(open(path)).get("msmv_fwd")
+        except Exception:
+            pass
+        return {"kernel": "msmv_fwd (timed with its wrapper-side allocation inside the decoder)", "bound": "hbm",
+                "achieved": k.get("gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": k.get("frac_of_hbm_peak"),
+                "traffic": traffic, "peak_source": peak_src, "avg_launch_us": k["avg_us"],
+                "algorithmic_bytes_per_launch": k.get("algorithmic_bytes"),
+                "note": "algorithmic bytes count every valid corner read of every tap (SURVEY 8d) of the decoder's actual "
+                        "sampling locations (first iteration); repeated pixels and coarse levels hit the 126 MB L2 so "
+                        "achieved may exceed the HBM copy peak; `traffic` = DRAM bytes/launch from ncu at the op-benchmark "
+                        "shapes (profiles/)"}
+
+    # end to end: pinned host inputs -> H2D -> decoder -> D2H of (cls_scores, bbox_preds)
+    def prepare_host_inputs(self):
+        keys = ["query_bbox", "query_feat", "lss_bev", "radar_bev"]
+        self._host = {k: self.inp[k].detach().cpu().pin_memory() for k in keys}
+        self._host_feats = [f.detach().cpu().pin_memory() for f in self.inp["mlvl_feats"]]
+        self._dev = {k: torch.empty_like(v, device=self.device) for k, v in self._host.items()}
+        self._dev_feats = [torch.empty_like(f, device=self.device) for f in self._host_feats]
+        self.h2d_bytes_per_step = sum(t.numel() * 4 for t in list(self._host.values()) + self._host_feats)
+        cls, box = self.step()
+        self._host_out = [torch.empty(cls.shape).pin_memory(), torch.empty(box.shape).pin_memory()]
+        self.d2h_bytes_per_step = (cls.numel() + box.numel()) * 4
+
+    def e2e_step(self):
+        for k, h in self._host.items():
+            self._dev[k].copy_(h, non_blocking=True)
+        for h, d in zip(self._host_feats, self._dev_feats):
+            d.copy_(h, non_blocking=True)
+        inp = dict(self._dev, mlvl_feats=self._dev_feats, img_metas=self.inp["img_metas"])
+        cls, box = self._forward(inp)
+        self._host_out[0].copy_(cls, non_blocking=True)
+        self._host_out[1].copy_(box, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_out
+
+    # CPU reference leg
+    @property
+    def reference_samples_per_step(self):
+        return 1.0 / 6.0
+
+    def reference_step(self):
+        """One decoder iteration (a bounded 1/6 sample) on the reference's PyTorch CPU path, reference schedule."""
+        assert not self.on_gpu
+        if not hasattr(self, "_ref_model"):
+            from racformer_b200.decoder import RaCFormerTransformer
+            m = RaCFormerTransformer(**dict(self.cfg, num_layers=1), ops=self.model.ops, hoist_invariants=False)
+            m.load_state_dict(self.model.state_dict())
+            self._ref_model = m.eval()
+        with torch.no_grad():
+            return self._ref_model(self.inp["query_bbox"], self.inp["query_feat"], self.inp["mlvl_feats"],
+                                   self.inp["lss_bev"], self.inp["radar_bev"], None, self.inp["img_metas"])
+
+
+class DecoderTrainWorkload(DecoderWorkload):
+    """Config 4 (decoder part): training step of the decoder at 704x256 f8 -- B=2 per GPU, 900 + 320 denoising queries
+    with the denoising attention mask, activation checkpointing and dropout as in the reference, gradients flowing to
+    the FPN/BEV features, bucketed NCCL all-reduce of the parameter gradients, AdamW step. The loss is a fixed random
+    projection of the outputs (Hungarian assignment / losses are outside the path)."""
+    metric = "decoder training samples/s (RaCFormer R50 704x256 f8 decoder fwd+bwd+allreduce+AdamW, batch 2/GPU)"
+
+    def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320):
+        from racformer_b200.parallel import GradientAllReducer
+        from racformer_b200.synthetic import make_decoder_inputs
+        super().__init__(device, seed=seed, name=name)
+        self.samples_per_step = batch
+        self.batch, self.dn = batch, dn_queries
+        self.model.train()
+        q = 900 + dn_queries
+        self.inp = make_decoder_inputs(seed=100 + seed, batch=batch, num_query=900, device=self.device)
+        g = torch.Generator().manual_seed(7 + seed)
+        dn_bbox = torch.rand(batch, dn_queries, 10, generator=g).to(self.device) * 0.8 + 0.1
+        dn_bbox[..., 8:] = 0
+        self.inp["query_bbox"] = torch.cat([dn_bbox, self.inp["query_bbox"]], 1)
+        self.inp["query_feat"] = torch.cat([torch.randn(batch, dn_queries, 256, generator=g).to(self.device) * 0.1,
+                                            self.inp["query_feat"]], 1)
+        mask = torch.zeros(q, q, dtype=torch.bool)
+        mask[dn_queries:, :dn_queries] = True                       # matching queries cannot see denoising queries
+        group = dn_queries // 10
+        for i in range(10):                                          # denoising groups cannot see each other
+            mask[i * group:(i + 1) * group, :i * group] = True
+            mask[i * group:(i + 1) * group, (i + 1) * group:dn_queries] = True
+        self.mask = mask.to(self.device)
+        for k in ("lss_bev", "radar_bev"):
+            self.inp[k].requires_grad_()
+        for f in self.inp["mlvl_feats"]:
+            f.requires_grad_()
+        self.proj_cls = torch.randn(6, batch, q, 10, generator=g).to(self.device)
+        self.proj_box = torch.randn(6, batch, q, 10, generator=g).to(self.device)
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=4e-4, weight_decay=0.01)
+        self.reducer = GradientAllReducer(list(self.model.parameters()))
+        self.launches_per_step = 3 * self.layers * 3     # forward, checkpoint recompute, backward
+        self.allreduce_bytes = 0
+
+    def config(self):
+        c = super().config()
+        c.update({"batch_per_gpu": self.batch, "num_query": 900 + self.dn, "mode": "train", "activation_checkpoint": True,
+                  "optimizer": "AdamW", "grad_allreduce": "bucketed NCCL all-reduce of decoder parameter grads (25 MB buckets)",
+                  "loss": "fixed random projection of cls/bbox outputs (assignment + losses out of scope)"})
+        return c
+
+    def step(self, time_kernels=False):
+        self._time_kernels = time_kernels
+        inp = self.inp
+        for t in [inp["lss_bev"], inp["radar_bev"]] + inp["mlvl_feats"]:
+            t.grad = None
+        self.opt.zero_grad(set_to_none=True)
+        qf = inp["query_feat"].detach().requires_grad_()
+        cls, box = self.model(inp["query_bbox"], qf, inp["mlvl_feats"], inp["lss_bev"], inp["radar_bev"], self.mask,
+                              inp["img_metas"])
+        loss = (cls * self.proj_cls).mean() + (box * self.proj_box).mean()
+        loss.backward()
+        self.allreduce_bytes = self.reducer.all_reduce()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 35.0)
+        self.opt.step()
+        self._time_kernels = False
+        return loss.detach()
+
+    def prepare_host_inputs(self):
+        self._host_feats = [f.detach().cpu().pin_memory() for f in self.inp["mlvl_feats"]]
+        self._host_bev = [self.inp[k].detach().cpu().pin_memory() for k in ("lss_bev", "radar_bev")]
+        self.h2d_bytes_per_step = sum(t.numel() * 4 for t in self._host_feats + self._host_bev)
+        self.d2h_bytes_per_step = 4
+
+    def e2e_step(self):
+        with torch.no_grad():
+            for h, d in zip(self._host_feats, self.inp["mlvl_feats"]):
+                d.copy_(h, non_blocking=True)
+            for h, k in zip(self._host_bev, ("lss_bev", "radar_bev")):
+                self.inp[k].copy_(h, non_blocking=True)
+        return float(self.step())   # .item(): D2H of the loss
+
+    def reference_step(self):
+        raise NotImplementedError("the CPU reference arm is defined for the forward workloads")
+
+
 def build(name, device, seed=0):
+    if name == "decoder_train_f8":
+        return DecoderTrainWorkload(device, seed=seed)
+    if name == "decoder_forward_f8":
+        return DecoderWorkload(device, seed=seed)
+    if name == "decoder_forward_f8_nohoist":
+        return DecoderWorkload(device, seed=seed, name=name, hoist=False)
     if name == "decoder_sampling_f8":
         return SamplingWorkload(device, seed=seed)
     if name == "decoder_sampling_f8_train":

@@ -50,14 +50,26 @@ __device__ __forceinline__ void level_dims(const MsmvArgs<L>& a, int l, int& H, 
 
 // ------------------------------------------------------------------------------------------------
 // Fast path, forward. grid = ceil(B*Q / kMsmvWarps), block = kMsmvWarps warps.
+//
+// Latency, not bandwidth, limited the first version (ncu r01: 75 % long-scoreboard stalls, DRAM 50 %), so the
+// loads are software-pipelined: the geometry of a whole batch of points (up to 64 taps) is staged once, and the
+// 2L 128-bit loads of point p+1 are issued into a second register buffer before the FMAs of point p run.
 // ------------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kMsmvWarps * 32) msmv_fwd_c64_kernel(const MsmvArgs<L> a) {
+struct PointRegs {
+    float4 top[L];
+    float4 bot[L];
+};
+
+template <int L>
+__global__ void __launch_bounds__(kMsmvWarps * 32, 2) msmv_fwd_c64_kernel(const MsmvArgs<L> a) {
     constexpr int G = kLanesPerPixel;
-    constexpr int TAPS = kMsmvChunk * L;
-    static_assert(TAPS <= 32, "one lane per tap");
-    __shared__ float2 s_w[kMsmvWarps][TAPS][2];  // [tap][x-slot] = {w_top, w_bot} * level weight
-    __shared__ int2 s_om[kMsmvWarps][TAPS];      // {float4 offset of the top-left pixel, corner mask}
+    constexpr int PB = (L <= 4) ? 16 : 12;      // points per staged batch (multiple of kMsmvChunk)
+    constexpr int NT = PB * L;                  // taps per batch (<= 64)
+    constexpr int NTP = NT + L;                 // + one all-invalid pad point so the pipeline can run one ahead
+    static_assert(NT <= 64 && PB % kMsmvChunk == 0, "batch geometry");
+    __shared__ float2 s_w[kMsmvWarps][NTP][2];  // [tap][x-slot] = {w_top, w_bot} * level weight
+    __shared__ int2 s_om[kMsmvWarps][NTP];      // {float4 offset of the top-left pixel, corner mask}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long bq = (long long)blockIdx.x * kMsmvWarps + warp;
@@ -76,11 +88,40 @@ __global__ void __launch_bounds__(kMsmvWarps * 32) msmv_fwd_c64_kernel(const Msm
     const float* wts_q = a.wts + bq * a.P * L;
     float* out_q = a.out + bq * 64 * a.P;
     const bool vec_store = (a.P % 4) == 0;
+    if (lane < L) {
+        s_w[warp][NT + lane][0] = make_float2(0.f, 0.f);
+        s_w[warp][NT + lane][1] = make_float2(0.f, 0.f);
+        s_om[warp][NT + lane] = make_int2(0, 0);
+    }
 
-    for (int p0 = 0; p0 < a.P; p0 += kMsmvChunk) {
+    auto issue = [&](PointRegs<L>& r, int pt) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int2 om = s_om[warp][pt * L + l];
+            const unsigned m = (unsigned)om.y >> slot;  // bit0 = top corner of my column, bit2 = bottom
+            const float4* p = base[l] + om.x;
+            r.top[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r.bot[l] = r.top[l];
+            if (m & 1u) r.top[l] = ldg128(p);
+            if (m & 4u) r.bot[l] = ldg128(p + row[l]);
+        }
+    };
+    auto consume = [&](const PointRegs<L>& r, int pt, float4& acc) {
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const float2 w = s_w[warp][pt * L + l][slot];
+            acc.x = fmaf(w.y, r.bot[l].x, fmaf(w.x, r.top[l].x, acc.x));
+            acc.y = fmaf(w.y, r.bot[l].y, fmaf(w.x, r.top[l].y, acc.y));
+            acc.z = fmaf(w.y, r.bot[l].z, fmaf(w.x, r.top[l].z, acc.z));
+            acc.w = fmaf(w.y, r.bot[l].w, fmaf(w.x, r.top[l].w, acc.w));
+        }
+    };
+
+    for (int pb = 0; pb < a.P; pb += PB) {
         __syncwarp();
-        if (lane < TAPS) {
-            const int pp = lane / L, l = lane % L, p = p0 + pp;
+        for (int t = lane; t < NT; t += 32) {
+            const int pp = t / L, l = t % L, p = pb + pp;
             float2 w0 = make_float2(0.f, 0.f), w1 = w0;
             int2 om = make_int2(0, 0);
             if (p < a.P) {
@@ -98,57 +139,52 @@ __global__ void __launch_bounds__(kMsmvWarps * 32) msmv_fwd_c64_kernel(const Msm
                     om.y = (int)g.mask;
                 }
             }
-            s_w[warp][lane][0] = w0;
-            s_w[warp][lane][1] = w1;
-            s_om[warp][lane] = om;
+            s_w[warp][t][0] = w0;
+            s_w[warp][t][1] = w1;
+            s_om[warp][t] = om;
         }
         __syncwarp();
 
-        float4 acc[kMsmvChunk];
+        const int npts = min(PB, a.P - pb);
+        PointRegs<L> ra, rb;
+        issue(ra, 0);
+        for (int c = 0; c < npts; c += kMsmvChunk) {
+            float4 acc[kMsmvChunk];
+            issue(rb, c + 1);
+            consume(ra, c + 0, acc[0]);
+            issue(ra, c + 2);
+            consume(rb, c + 1, acc[1]);
+            issue(rb, c + 3);
+            consume(ra, c + 2, acc[2]);
+            issue(ra, c + 4);  // first point of the next chunk (or the all-invalid pad point)
+            consume(rb, c + 3, acc[3]);
+            // combine the x0 / x1 half-warps
 #pragma unroll
-        for (int pp = 0; pp < kMsmvChunk; ++pp) {
-            acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                const int t = pp * L + l;
-                const int2 om = s_om[warp][t];
-                const float2 w = s_w[warp][t][slot];
-                const unsigned m = (unsigned)om.y >> slot;  // bit0 = top corner of my column, bit2 = bottom
-                const float4* p = base[l] + om.x;
-                float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
-                if (m & 1u) top = ldg128(p);
-                if (m & 4u) bot = ldg128(p + row[l]);
-                acc[pp].x = fmaf(w.y, bot.x, fmaf(w.x, top.x, acc[pp].x));
-                acc[pp].y = fmaf(w.y, bot.y, fmaf(w.x, top.y, acc[pp].y));
-                acc[pp].z = fmaf(w.y, bot.z, fmaf(w.x, top.z, acc[pp].z));
-                acc[pp].w = fmaf(w.y, bot.w, fmaf(w.x, top.w, acc[pp].w));
+            for (int pp = 0; pp < kMsmvChunk; ++pp) {
+                acc[pp].x += __shfl_xor_sync(0xffffffffu, acc[pp].x, 16);
+                acc[pp].y += __shfl_xor_sync(0xffffffffu, acc[pp].y, 16);
+                acc[pp].z += __shfl_xor_sync(0xffffffffu, acc[pp].z, 16);
+                acc[pp].w += __shfl_xor_sync(0xffffffffu, acc[pp].w, 16);
             }
-        }
-        // combine the x0 / x1 half-warps
+            // out[b,q,c,p]: lane (slot, j) stores channels 4j + 2*slot + {0,1}, points p0..p0+3
+            const int p0 = pb + c;
+            const int c0 = 4 * j + 2 * slot;
+            const float4 e0 = slot ? make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z)
+                                   : make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+            const float4 e1 = slot ? make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w)
+                                   : make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+            if (vec_store) {
+                *reinterpret_cast<float4*>(out_q + (size_t)c0 * a.P + p0) = e0;
+                *reinterpret_cast<float4*>(out_q + (size_t)(c0 + 1) * a.P + p0) = e1;
+            } else {
+                const float v0[4] = {e0.x, e0.y, e0.z, e0.w}, v1[4] = {e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-        for (int pp = 0; pp < kMsmvChunk; ++pp) {
-            acc[pp].x += __shfl_xor_sync(0xffffffffu, acc[pp].x, 16);
-            acc[pp].y += __shfl_xor_sync(0xffffffffu, acc[pp].y, 16);
-            acc[pp].z += __shfl_xor_sync(0xffffffffu, acc[pp].z, 16);
-            acc[pp].w += __shfl_xor_sync(0xffffffffu, acc[pp].w, 16);
-        }
-        // out[b,q,c,p]: lane (slot, j) stores channels 4j + 2*slot + {0,1}, points p0..p0+3
-        const int c0 = 4 * j + 2 * slot;
-        const float4 e0 = slot ? make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z)
-                               : make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
-        const float4 e1 = slot ? make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w)
-                               : make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
-        if (vec_store) {
-            *reinterpret_cast<float4*>(out_q + (size_t)c0 * a.P + p0) = e0;
-            *reinterpret_cast<float4*>(out_q + (size_t)(c0 + 1) * a.P + p0) = e1;
-        } else {
-            const float v0[4] = {e0.x, e0.y, e0.z, e0.w}, v1[4] = {e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-            for (int pp = 0; pp < kMsmvChunk; ++pp)
-                if (p0 + pp < a.P) {
-                    out_q[(size_t)c0 * a.P + p0 + pp] = v0[pp];
-                    out_q[(size_t)(c0 + 1) * a.P + p0 + pp] = v1[pp];
-                }
+                for (int pp = 0; pp < kMsmvChunk; ++pp)
+                    if (p0 + pp < a.P) {
+                        out_q[(size_t)c0 * a.P + p0 + pp] = v0[pp];
+                        out_q[(size_t)(c0 + 1) * a.P + p0 + pp] = v1[pp];
+                    }
+            }
         }
     }
 }

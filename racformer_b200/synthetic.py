@@ -1,0 +1,75 @@
+"""Seeded synthetic inputs for the decoder harness: a 6-camera ring, timestamps,
+FPN / BEV features and the polar query grid. There is no dataset or checkpoint in this environment."""
+import math
+import zlib
+
+import numpy as np
+import torch
+
+from .decoder import initial_query_bbox
+
+PC_RANGE = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]        # configs/racformer_r50_nuimg_704x256_f8.py:23
+D_REGION_LIST = [0.08, 0.07, 0.06, 0.05, 0.04, 0.03]    # :36
+CAMERA_YAWS_DEG = (55.0, 0.0, -55.0, 110.0, 180.0, -110.0)
+F8_LEVEL_SHAPES = [(64, 176), (32, 88), (16, 44), (8, 22)]
+
+
+def lidar2img_matrix(yaw_rad, focal=557.0, cx=352.0, cy=128.0, cam_height=1.5):
+    """Pinhole camera looking along `yaw` in the lidar frame (x fwd, y left, z up) -> 4x4 lidar-to-pixel matrix."""
+    c, s = math.cos(yaw_rad), math.sin(yaw_rad)
+    rot = np.array([[s, -c, 0.0], [0.0, 0.0, -1.0], [c, s, 0.0]], dtype=np.float64)   # rows: camera x, y, z axes
+    ext = np.eye(4)
+    ext[:3, :3] = rot
+    ext[:3, 3] = -rot @ np.array([0.0, 0.0, cam_height])
+    intr = np.eye(4)
+    intr[0, 0] = intr[1, 1] = focal
+    intr[0, 2], intr[1, 2] = cx, cy
+    return intr @ ext
+
+
+def make_img_metas(batch=1, num_frames=8, num_cams=6, image_hw=(256, 704), frame_dt=0.5, focal=557.0):
+    """Frame-major, cameras inner (loaders/pipelines/loading.py:662-678); same rig for every frame."""
+    h, w = image_hw
+    yaws = CAMERA_YAWS_DEG[:num_cams] if num_cams <= len(CAMERA_YAWS_DEG) else \
+        tuple(360.0 * i / num_cams for i in range(num_cams))
+    mats = [lidar2img_matrix(math.radians(a), focal=focal * w / 704.0, cx=w / 2.0, cy=h / 2.0) for a in yaws] * num_frames
+    meta = dict(lidar2img=mats, img_timestamp=[-frame_dt * (i // num_cams) for i in range(num_frames * num_cams)],
+                img_shape=[(h, w, 3)] * (num_frames * num_cams))
+    return [dict(meta) for _ in range(batch)]
+
+
+def make_decoder_inputs(seed=0, batch=1, num_frames=8, num_cams=6, embed_dims=256, num_query=900, num_clusters=6,
+                        level_shapes=None, bev_hw=(128, 128), image_hw=(256, 704), device="cpu"):
+    """Returns dict(query_bbox, query_feat, mlvl_feats, lss_bev, radar_bev, img_metas)."""
+    level_shapes = level_shapes or F8_LEVEL_SHAPES
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(batch, num_frames * num_cams, embed_dims, h, w, generator=g) for h, w in level_shapes]
+    lss = torch.randn(batch, num_frames, embed_dims, *bev_hw, generator=g)
+    radar = torch.randn(batch, num_frames, embed_dims, *bev_hw, generator=g)
+    qb = initial_query_bbox(num_query, num_clusters)[None].repeat(batch, 1, 1)
+    qf = torch.randn(batch, num_query, embed_dims, generator=g) * 0.1
+    mv = lambda t: t.to(device)
+    return dict(query_bbox=mv(qb), query_feat=mv(qf), mlvl_feats=[mv(f) for f in feats], lss_bev=mv(lss),
+                radar_bev=mv(radar), img_metas=make_img_metas(batch, num_frames, num_cams, image_hw))
+
+
+@torch.no_grad()
+def fill_parameters_by_name(module, seed=0):
+    """Deterministic weights that depend only on (seed, parameter name, shape): two module trees with the same
+    parameter names -- this repo's decoder and the reference's -- get bit-identical weights without a checkpoint."""
+    for name, p in sorted(module.state_dict().items()):
+        if not p.is_floating_point():
+            continue
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2 ** 31))
+        if p.dim() >= 2:
+            fan_in = p[0].numel()
+            val = torch.randn(p.shape, generator=g) / math.sqrt(fan_in)
+            if name.endswith("embed.weight"):
+                val = torch.rand(p.shape, generator=g)
+        elif name.endswith("weight"):           # LayerNorm scale
+            val = 1.0 + 0.1 * torch.randn(p.shape, generator=g)
+        else:                                   # biases
+            val = 0.1 * torch.randn(p.shape, generator=g)
+        if "sampling_offset.bias" in name:      # spread the sample points like the reference's init does
+            val = torch.rand(p.shape, generator=g) - 0.5
+        p.copy_(val.to(p.dtype))

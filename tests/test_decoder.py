@@ -1,0 +1,165 @@
+"""Decoder harness (racformer_b200/decoder.py) against the UNCHANGED reference decoder.
+
+CPU: the harness' host logic with the oracle's torch ops injected vs (i) the committed fixture produced by the
+reference, (ii) the live reference when /root/reference is present (forward, gradients, denoising mask, B=2 quirks,
+state_dict compatibility). GPU: the same fixture through the sm_100a kernels.
+"""
+import pytest
+import torch
+
+from racformer_b200.decoder import RaCFormerTransformer
+from racformer_b200.synthetic import fill_parameters_by_name
+from tests import reference_shim
+from tests.decoder_cases import SMALL, cpu_oracle_ops, small_inputs
+from tests.helpers import load_golden
+
+DEC_RTOL, DEC_ATOL = 1e-4, 2e-4   # fp32 through 2 decoder iterations (LayerNorms, softmaxes, atan2/sin/cos)
+
+
+def _close(a, b, what, rtol=DEC_RTOL, atol=DEC_ATOL, max_outlier_frac=0.0):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    frac = float(bad.float().mean())
+    assert frac <= max_outlier_frac, f"{what}: {frac:.2e} of elements differ, worst {float((a - b).abs().max()):.3g}"
+
+
+def _fixture_inputs(device="cpu"):
+    d = load_golden("decoder_small")
+    feats = [d[f"feat{i}"].to(device) for i in range(4)]
+    metas = small_inputs(seed=5)["img_metas"]
+    return d, feats, metas
+
+
+def _my_model(ops=None, **kw):
+    model = RaCFormerTransformer(**SMALL, ops=ops, **kw)
+    model.init_weights()
+    fill_parameters_by_name(model, seed=3)
+    return model.eval()
+
+
+@pytest.mark.parametrize("hoist", [True, False])
+def test_decoder_matches_reference_fixture_cpu(hoist):
+    d, feats, metas = _fixture_inputs()
+    model = _my_model(ops=cpu_oracle_ops(), hoist_invariants=hoist)
+    with torch.no_grad():
+        cls, box = model(d["query_bbox"], d["query_feat"], feats, d["lss_bev"], d["radar_bev"], None, metas)
+    _close(cls, d["cls_scores"], "cls_scores vs reference fixture")
+    _close(box, d["bbox_preds"], "bbox_preds vs reference fixture")
+
+
+@pytest.mark.gpu
+def test_decoder_matches_reference_fixture_gpu():
+    d, feats, metas = _fixture_inputs("cuda")
+    model = _my_model().cuda()
+    with torch.no_grad():
+        cls, box = model(d["query_bbox"].cuda(), d["query_feat"].cuda(), feats, d["lss_bev"].cuda(),
+                         d["radar_bev"].cuda(), None, metas)
+    # cuDNN convolutions may use TF32 (PyTorch default, as for the reference on GPU): looser than the CPU comparison
+    _close(cls, d["cls_scores"], "cls_scores vs reference fixture (GPU)", rtol=2e-3, atol=5e-3, max_outlier_frac=0.01)
+    _close(box, d["bbox_preds"], "bbox_preds vs reference fixture (GPU)", rtol=2e-3, atol=5e-3, max_outlier_frac=0.01)
+
+
+@pytest.mark.gpu
+def test_decoder_gpu_strict_fp32_and_hoisting_equivalence():
+    """With TF32 off, the CUDA path must meet the CPU tolerance, and hoisting must not change the result."""
+    d, feats, metas = _fixture_inputs("cuda")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        outs = []
+        for hoist in (True, False):
+            model = _my_model(hoist_invariants=hoist).cuda()
+            with torch.no_grad():
+                outs.append(model(d["query_bbox"].cuda(), d["query_feat"].cuda(), feats, d["lss_bev"].cuda(),
+                                  d["radar_bev"].cuda(), None, metas))
+        _close(outs[0][0], d["cls_scores"], "cls (GPU, fp32 conv)", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+        _close(outs[0][1], d["bbox_preds"], "box (GPU, fp32 conv)", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+        _close(outs[0][0], outs[1][0], "hoisted vs per-layer cls", rtol=1e-5, atol=1e-5)
+        _close(outs[0][1], outs[1][1], "hoisted vs per-layer box", rtol=1e-5, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+needs_ref = pytest.mark.skipif(not reference_shim.available(), reason="/root/reference not present")
+
+
+def _ref_model():
+    rt = reference_shim.load_reference_transformer_module()
+    model = rt.RaCFormerTransformer(**SMALL)
+    model.init_weights()
+    fill_parameters_by_name(model, seed=3)
+    return model
+
+
+@needs_ref
+def test_state_dict_is_interchangeable_with_reference():
+    ref, mine = _ref_model(), _my_model(ops=cpu_oracle_ops())
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert set(rs) == set(ms), (sorted(set(rs) - set(ms)), sorted(set(ms) - set(rs)))
+    for k in rs:
+        assert rs[k].shape == ms[k].shape, k
+    mine.load_state_dict(rs, strict=True)
+
+
+def _ref_model_layers(num_layers):
+    rt = reference_shim.load_reference_transformer_module()
+    model = rt.RaCFormerTransformer(**dict(SMALL, num_layers=num_layers))
+    model.init_weights()
+    fill_parameters_by_name(model, seed=3)
+    return model
+
+
+@needs_ref
+@pytest.mark.parametrize("batch,with_dn_mask,num_layers,grad_tol", [(1, False, 1, 1e-4), (2, True, 1, 1e-4),
+                                                                    (2, True, 2, 3e-2)])
+def test_decoder_forward_and_gradients_match_live_reference(batch, with_dn_mask, num_layers, grad_tol):
+    """Autograd through the whole decoder (eval mode so dropout is off): outputs and the gradients w.r.t. query
+    features, FPN features, BEV maps and parameters match the unchanged reference. B=2 exercises the reference's
+    B*T*G / B*G*T and queue-major packing quirks; the mask exercises query denoising.
+
+    One decoder iteration: gradients agree to 1e-4 of their max. Two iterations: fp32 rounding of the first
+    iteration's outputs (1e-5) is amplified by the second iteration's sampling derivatives -- measured against an
+    fp64 evaluation of the same graph, the reference itself and this harness are both ~1e-2 off (relative to max|g|),
+    so they are compared at 3e-2."""
+    ref = _ref_model_layers(num_layers).eval()
+    mine = RaCFormerTransformer(**dict(SMALL, num_layers=num_layers), ops=cpu_oracle_ops())
+    mine.init_weights()
+    fill_parameters_by_name(mine, seed=3)
+    mine.eval()
+    d = small_inputs(seed=11, batch=batch)
+    Q = d["query_bbox"].shape[1]
+    mask = None
+    if with_dn_mask:
+        mask = torch.zeros(Q, Q, dtype=torch.bool)
+        mask[: Q // 2, Q // 2:] = True
+
+    def run(model, is_ref):
+        qf = d["query_feat"].clone().requires_grad_()
+        feats = [f.clone().requires_grad_() for f in d["mlvl_feats"]]
+        lss, radar = d["lss_bev"].clone().requires_grad_(), d["radar_bev"].clone().requires_grad_()
+        metas = [dict(m) for m in d["img_metas"]]
+        feats_in = list(feats)   # the reference mutates the list it is given (quirk vii)
+        cls, box = model(d["query_bbox"].clone(), qf, feats_in, lss, radar, mask, metas)
+        g = torch.Generator().manual_seed(0)
+        loss = (cls * torch.randn(cls.shape, generator=g)).sum() + (box * torch.randn(box.shape, generator=g)).sum()
+        model.zero_grad()
+        loss.backward()
+        grads = {"query_feat": qf.grad, "lss": lss.grad, "radar": radar.grad}
+        for i, f in enumerate(feats):
+            grads[f"feat{i}"] = f.grad
+        for name in ("decoder.decoder_layer.sampling.scale_weights.weight", "decoder.decoder_layer.mixing.out_proj.bias",
+                     "decoder.decoder_layer.sampling_radar_bev.attention.value_proj.weight",
+                     "decoder.decoder_layer.sampling_lss_bev.sampling_offset.bias",
+                     "decoder.decoder_layer.sampling_radar_bev.temporal_encoder.temporal_fusion.weight"):
+            grads[name] = dict(model.named_parameters())[name].grad
+        return cls, box, grads
+
+    rc, rb, rg = run(ref, True)
+    mc, mb, mg = run(mine, False)
+    _close(mc, rc, "cls vs live reference")
+    _close(mb, rb, "box vs live reference")
+    for k in rg:
+        assert rg[k] is not None and mg[k] is not None, k
+        scale = float(rg[k].abs().max())
+        _close(mg[k], rg[k], f"grad {k} vs live reference", rtol=0.0, atol=grad_tol * max(scale, 1e-6))
