@@ -1,0 +1,44 @@
+"""torch.profiler breakdown of one decoder forward (GPU kernel time by kernel, and total GPU-busy vs step time)."""
+import json
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench_workloads  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "decoder_forward_f8"
+wl = bench_workloads.build(name, torch.device("cuda", 0))
+for _ in range(3):
+    wl.step()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    wl.step()
+b.record()
+torch.cuda.synchronize()
+step_ms = a.elapsed_time(b) / 5
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    wl.step()
+    torch.cuda.synchronize()
+rows = []
+total = 0.0
+for e in prof.key_averages():
+    t = getattr(e, "device_time_total", 0) or getattr(e, "cuda_time_total", 0)
+    if e.device_type.name == "CUDA" or (t and e.key.startswith(("void", "sm", "cutlass", "ampere", "cudnn", "racf", "nvjet", "Memcpy", "Memset", "msda", "msmv"))):
+        pass
+evs = [e for e in prof.events() if e.device_type.name == "CUDA"]
+agg = {}
+for e in evs:
+    k = e.name[:90]
+    d = agg.setdefault(k, [0.0, 0])
+    d[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    d[1] += 1
+total = sum(v[0] for v in agg.values())
+top = sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]
+print(json.dumps({"workload": name, "step_ms": step_ms, "gpu_busy_ms": total / 1e3, "num_gpu_kernels": sum(v[1] for v in agg.values()),
+                  "top": [{"name": k, "ms": v[0] / 1e3, "calls": v[1]} for k, v in top]}, indent=1))
