@@ -247,8 +247,10 @@ class DecoderWorkload:
                                     "reference's PyTorch CPU path (grid_sample ops, reference schedule without hoisting), "
                                     "full f8 shapes, all host threads")
 
-    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True):
+    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True):
         from racformer_b200.decoder import RaCFormerTransformer, SamplingOps
+        self.use_graph = graph and torch.device(device).type == "cuda"
+        self._graphed = None
         from racformer_b200.synthetic import D_REGION_LIST, PC_RANGE, make_decoder_inputs
         self.name, self.device, self.layers, self.hoist = name, torch.device(device), num_layers, hoist
         self.samples_per_step = 1
@@ -280,7 +282,7 @@ class DecoderWorkload:
         return {"workload": self.name, "shapes": "racformer_r50_nuimg_704x256_f8", "batch_per_gpu": 1, "num_query": 900,
                 "frames": 8, "cams": 6, "fpn_levels": 4, "embed_dims": 256, "decoder_layers": self.layers,
                 "msmv_points": 12, "msda_points": 20, "bev": [128, 128], "weights": "random init (seed 0)",
-                "hoist_invariants": self.hoist, "includes_channel_last_relayout": True,
+                "hoist_invariants": self.hoist, "includes_channel_last_relayout": True, "cuda_graph": self.use_graph,
                 "conv_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
                 "sharding": "one sample per GPU, no data-path collective",
                 "l2_policy": "inputs larger than L2 (735 MB pyramid + 2x134 MB BEV maps vs 126 MB L2); no flush"}
@@ -306,6 +308,11 @@ class DecoderWorkload:
                               None, inp["img_metas"])
 
     def step(self, time_kernels=False):
+        if self.use_graph and not time_kernels:
+            if self._graphed is None:
+                from racformer_b200.graphs import GraphedDecoderForward
+                self._graphed = GraphedDecoderForward(self.model, self.inp)   # its static buffers = the resident inputs
+            return self._graphed()
         self._time_kernels = time_kernels
         out = self._forward(self.inp)
         self._time_kernels = False
@@ -349,6 +356,8 @@ class DecoderWorkload:
                 "achieved": k.get("gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": k.get("frac_of_hbm_peak"),
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_us": k["avg_us"],
                 "algorithmic_bytes_per_launch": k.get("algorithmic_bytes"),
+                "timing": "CUDA events around each launch in an eager pass of the same workload right after the timed "
+                          "region (events cannot bracket kernels inside a graph replay)",
                 "note": "algorithmic bytes count every valid corner read of every tap (SURVEY 8d) of the decoder's actual "
                         "sampling locations (first iteration); repeated pixels and coarse levels hit the 126 MB L2 so "
                         "achieved may exceed the HBM copy peak; `traffic` = DRAM bytes/launch from ncu at the op-benchmark "
@@ -367,6 +376,13 @@ class DecoderWorkload:
         self.d2h_bytes_per_step = (cls.numel() + box.numel()) * 4
 
     def e2e_step(self):
+        if self.use_graph:   # H2D straight into the graph's static buffers, replay, D2H
+            self._graphed.load(dict(self._host, mlvl_feats=self._host_feats))
+            cls, box = self._graphed()
+            self._host_out[0].copy_(cls, non_blocking=True)
+            self._host_out[1].copy_(box, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self._host_out
         for k, h in self._host.items():
             self._dev[k].copy_(h, non_blocking=True)
         for h, d in zip(self._host_feats, self._dev_feats):
@@ -406,7 +422,7 @@ class DecoderTrainWorkload(DecoderWorkload):
     def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320):
         from racformer_b200.parallel import GradientAllReducer
         from racformer_b200.synthetic import make_decoder_inputs
-        super().__init__(device, seed=seed, name=name)
+        super().__init__(device, seed=seed, name=name, graph=False)
         self.samples_per_step = batch
         self.batch, self.dn = batch, dn_queries
         self.model.train()
@@ -484,7 +500,9 @@ def build(name, device, seed=0):
     if name == "decoder_forward_f8":
         return DecoderWorkload(device, seed=seed)
     if name == "decoder_forward_f8_nohoist":
-        return DecoderWorkload(device, seed=seed, name=name, hoist=False)
+        return DecoderWorkload(device, seed=seed, name=name, hoist=False, graph=False)
+    if name == "decoder_forward_f8_eager":
+        return DecoderWorkload(device, seed=seed, name=name, graph=False)
     if name == "decoder_sampling_f8":
         return SamplingWorkload(device, seed=seed)
     if name == "decoder_sampling_f8_train":

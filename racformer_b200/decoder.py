@@ -46,6 +46,21 @@ class SamplingOps:
         self.msmv, self.msda = msmv, msda
 
 
+_CONST_CACHE = {}
+
+
+def _const_long(values, device):
+    """Small int64 device constants (MSDA spatial_shapes / level_start_index), created once per device so that the
+    forward issues no host-to-device copy (the reference rebuilds them every call, bev_self_attention.py:189-190) and
+    can be captured in a CUDA graph."""
+    key = (str(device), values)
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(values, dtype=torch.long, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 # ---------------------------------------------------------------------------------------------- coordinate helpers
 MAP_SIZE, RAY_R = 102.4, 65.0   # models/bbox/utils.py:82,93
 
@@ -230,8 +245,8 @@ class ScaleAdaptiveSelfAttention(nn.Module):
         dist = self.calc_bbox_dists(theta_d2xy_coods(query_bbox))
         tau = self.gen_tau(query_feat).permute(0, 2, 1)                                   # [B,8,Q]
         attn_mask = dist[:, None, :, :] * tau[..., None]                                  # [B,8,Q,Q]
-        if pre_attn_mask is not None:
-            attn_mask[:, :, pre_attn_mask] = float("-inf")
+        if pre_attn_mask is not None:   # query denoising: blocked pairs
+            attn_mask = attn_mask.masked_fill(pre_attn_mask[None, None], float("-inf"))
         return self.attention(query_feat, attn_mask=attn_mask.flatten(0, 1))
 
     def forward(self, query_bbox, query_feat, pre_attn_mask=None):
@@ -319,8 +334,8 @@ class BEVSelfAttention(nn.Module):
         T, M, L, P = self.num_bev_queue, self.num_heads, self.num_levels, self.num_points
         loc = sampling_locations.view(B, Q, M, T, L, P, 2).permute(3, 0, 1, 2, 4, 5, 6).reshape(B * T, Q, M, L, P, 2)
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
-        shapes = torch.tensor([list(spatial_shapes)], dtype=torch.long, device=value.device)
-        lsi = torch.tensor([0], dtype=torch.long, device=value.device)
+        shapes = _const_long((tuple(int(v) for v in spatial_shapes),), value.device)
+        lsi = _const_long((0,), value.device)
         out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
         out = out.permute(1, 2, 0).reshape(Q, C, B, T)
         if self.queue_weight:
@@ -560,8 +575,7 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         bbox_pred = self.refine_bbox(query_bbox, self.reg_branch(query_feat))
         time_diff = meta["time_diff"]
         if time_diff.shape[1] > 1:   # relative -> absolute velocity
-            td = time_diff.clone()
-            td[td < 1e-5] = 1.0
+            td = torch.where(time_diff < 1e-5, torch.ones_like(time_diff), time_diff)
             bbox_pred = torch.cat([bbox_pred[..., :8], bbox_pred[..., 8:] / td[:, 1:2, None]], dim=-1)
         return query_feat, cls_score, bbox_pred
 

@@ -163,3 +163,23 @@ def test_decoder_forward_and_gradients_match_live_reference(batch, with_dn_mask,
         assert rg[k] is not None and mg[k] is not None, k
         scale = float(rg[k].abs().max())
         _close(mg[k], rg[k], f"grad {k} vs live reference", rtol=0.0, atol=grad_tol * max(scale, 1e-6))
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_equals_eager_and_tracks_new_inputs():
+    """The captured decoder forward (racformer_b200/graphs.py) reproduces the eager result bit for bit, also after
+    new inputs are loaded into its static buffers."""
+    from racformer_b200.graphs import GraphedDecoderForward
+    model = _my_model().cuda()
+    d = small_inputs(seed=5, device="cuda")
+    graphed = GraphedDecoderForward(model, d)
+    with torch.no_grad():
+        eager = model(d["query_bbox"], d["query_feat"], d["mlvl_feats"], d["lss_bev"], d["radar_bev"], None, d["img_metas"])
+    out = graphed()
+    assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+    d2 = small_inputs(seed=6, device="cuda")
+    with torch.no_grad():
+        eager2 = model(d2["query_bbox"], d2["query_feat"], d2["mlvl_feats"], d2["lss_bev"], d2["radar_bev"], None, d2["img_metas"])
+    out2 = graphed({k: v for k, v in d2.items() if k != "img_metas"})
+    assert torch.equal(out2[0], eager2[0]) and torch.equal(out2[1], eager2[1])
+    assert not torch.equal(eager[0], eager2[0])
