@@ -128,6 +128,37 @@ int racf_msda_tap_masks(const int64_t* spatial_shapes, const float* loc,
                         int batch, int num_heads, int num_levels, int num_query, int num_point,
                         uint8_t* tap_mask, racf_stream_t stream);
 
+/*
+ * ---- "next" row: fused sampling-point generation, forward / inference only ----------
+ *
+ * racf_msmv_points_forward replaces the PyTorch op chain of RaCFormerSampling.inner_forward
+ * (models/racformer_transformer.py:361-408) plus the projection / view-selection / packing half of sampling_4d
+ * (models/sparsebev_sampling.py:45-120). Device inputs (fp32, contiguous):
+ *   query_ray [B,Q,10]   polar query boxes            offset    [B,Q,G*Pn*D,3]  sampling_offset(query_feat)
+ *   ray_logit [B,Q,D]    ray_points_offset(query_feat) scale_raw [B,Q,G,T,Pn*D,L] scale_weights(query_feat), pre-softmax
+ *   time_diff [B,T]      lidar2img [B,T*N,4,4]         depth_base [D]            linspace(-d_region, d_region, D)
+ * Host inputs: pc_range (6 doubles). Outputs: loc [B*T*G,Q,Pn*D,3] and weights [B*G*T,Q,Pn*D,L] -- exactly the two
+ * tensors sampling_4d hands to msmv_sampling (including the reference's B*T*G vs B*G*T packing).
+ */
+int racf_msmv_points_forward(const float* query_ray, const float* offset, const float* ray_logit,
+                             const float* scale_raw, const float* time_diff, const float* lidar2img,
+                             const float* depth_base, const double* pc_range, float d_region, float image_w,
+                             float image_h, float eps, int batch, int num_query, int num_frames, int num_groups,
+                             int num_points, int depth_num, int num_views, int num_levels,
+                             float* loc, float* weights, racf_stream_t stream);
+
+/*
+ * racf_bev_points_forward replaces BEVSampling.inner_forward's point math (models/racformer_transformer.py:493-529)
+ * plus the queue-major packing of BEVSelfAttention.forward (models/bev_self_attention.py:176-188), num_levels == 1:
+ *   offset [B,Q,M*Pn*D,2], attn_raw [B,Q,M,Pn*D] (pre-softmax) ->
+ *   loc [T*B,Q,M,1,Pn*D,2], attn [T*B,Q,M,1,Pn*D] (softmax over the Pn*D points, repeated over the T frames).
+ */
+int racf_bev_points_forward(const float* query_ray, const float* offset, const float* ray_logit,
+                            const float* attn_raw, const float* time_diff, const float* depth_base,
+                            const double* pc_range, float d_region, int batch, int num_query, int num_frames,
+                            int num_heads, int num_points, int depth_num, float* loc, float* attn,
+                            racf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,6 +253,21 @@ class ScaleAdaptiveSelfAttention(nn.Module):
         return _maybe_checkpoint(self, lambda qb, qf: self.inner_forward(qb, qf, pre_attn_mask), query_bbox, query_feat)
 
 
+def _use_fused_points(module, *tensors):
+    """The fused CUDA point kernels are forward-only: use them when autograd is off and everything lives on a GPU."""
+    return (getattr(module, "fused_points", True) and not torch.is_grad_enabled()
+            and all(t.is_cuda and t.dtype == torch.float32 for t in tensors))
+
+
+def _depth_base(d_region, depth_num, device):
+    key = ("linspace", str(device), float(d_region), int(depth_num))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(-d_region, d_region, depth_num, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def _polar_depth_offsets(module, query_feat, d_region):
     """linspace(-d, d, D) + learned jitter, shared by both samplers (racformer_transformer.py:395-396, 513-514)."""
     D = module.depth_num
@@ -280,6 +295,16 @@ class RaCFormerSampling(nn.Module):
     def inner_forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region):
         B, Q, _ = query_ray.shape
         T, G, Pn, D, pr = self.num_frames, self.num_groups, self.num_points, self.depth_num, self.pc_range
+        if _use_fused_points(self, query_ray, query_feat, meta["lidar2img"]):
+            from . import points   # one kernel instead of the ~150 PyTorch launches below
+            loc, w = points.msmv_points(
+                query_ray.contiguous(), self.sampling_offset(query_feat), self.ray_points_offset(query_feat),
+                self.scale_weights(query_feat), meta["time_diff"], meta["lidar2img"],
+                _depth_base(d_region, D, query_feat.device), pr, d_region, meta["image_w"], meta["image_h"],
+                T, G, Pn, D, self.num_levels)
+            out = ops.msmv(mlvl_feats, loc, w)                                         # [B*T*G,Q,C,P]
+            C = out.shape[2]
+            return out.reshape(B, T, G, Q, C, Pn * D).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
         query_bbox = theta_d2xy_coods(query_ray)
         offset = self.sampling_offset(query_feat).view(B, Q, G * Pn * D, 3)
         pts = make_sample_points(query_bbox, offset, pr).reshape(B, Q, 1, G, Pn * D, 3).expand(B, Q, T, G, Pn * D, 3)
@@ -334,6 +359,12 @@ class BEVSelfAttention(nn.Module):
         T, M, L, P = self.num_bev_queue, self.num_heads, self.num_levels, self.num_points
         loc = sampling_locations.view(B, Q, M, T, L, P, 2).permute(3, 0, 1, 2, 4, 5, 6).reshape(B * T, Q, M, L, P, 2)
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
+        return self.attend(ops, query, value, loc, aw, spatial_shapes)
+
+    def attend(self, ops, query, value, loc, aw, spatial_shapes):
+        """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing."""
+        B, Q, C = query.shape
+        T = self.num_bev_queue
         shapes = _const_long((tuple(int(v) for v in spatial_shapes),), value.device)
         lsi = _const_long((0,), value.device)
         out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
@@ -449,6 +480,13 @@ class BEVSampling(nn.Module):
     def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region):
         B, Q, _ = query_ray.shape
         T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
+        if self.num_levels == 1 and _use_fused_points(self, query_ray, query_feat, value):
+            from . import points
+            loc, aw = points.bev_points(
+                query_ray.contiguous(), self.sampling_offset(query_feat), self.ray_points_offset(query_feat),
+                self.scale_weights(query_feat), meta["time_diff"], _depth_base(d_region, D, query_feat.device), pr,
+                d_region, T, M, Pn, D)
+            return self.attention.attend(ops, query_feat, value, loc, aw, hw)
         query_bbox = theta_d2xy_coods(query_ray)
         offset = self.sampling_offset(query_feat).view(B, Q, M * Pn * D, 2)
         offset = torch.cat([offset, torch.zeros_like(offset[..., 0:1])], dim=-1)
@@ -656,6 +694,12 @@ class RaCFormerTransformer(nn.Module):
     @torch.no_grad()
     def init_weights(self):
         self.decoder.init_weights()
+
+    def set_fused_points(self, enabled):
+        """Toggle the fused CUDA point-generation kernels (inference only; eager PyTorch chain when False)."""
+        for m in self.modules():
+            if isinstance(m, (RaCFormerSampling, BEVSampling)):
+                m.fused_points = enabled
 
     def set_activation_checkpoint(self, enabled):
         for m in self.modules():

@@ -1,0 +1,65 @@
+"""Python binding of the fused sampling-point kernels (racformer_b200/csrc/points.cu). Forward only:
+they are used by the decoder harness when autograd is off; training keeps the PyTorch op chain."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_lib.load()
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check(*tensors):
+    dev = tensors[0].device
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == dev):
+            raise RuntimeError("fused point kernels need contiguous fp32 CUDA tensors on one device")
+
+
+def _pc(pc_range):
+    return (ctypes.c_double * 6)(*[float(v) for v in pc_range])
+
+
+def msmv_points(query_ray, offset, ray_logit, scale_raw, time_diff, lidar2img, depth_base, pc_range, d_region, image_w,
+                image_h, num_frames, num_groups, num_points, depth_num, num_levels, eps=1e-5):
+    """-> loc [B*T*G,Q,Pn*D,3], weights [B*G*T,Q,Pn*D,L]: the two tensors sampling_4d passes to msmv_sampling."""
+    _check(query_ray, offset, ray_logit, scale_raw, time_diff, lidar2img, depth_base)
+    B, Q, _ = query_ray.shape
+    T, G, Pn, D, L = num_frames, num_groups, num_points, depth_num, num_levels
+    N = lidar2img.shape[1] // T
+    P = Pn * D
+    if offset.numel() != B * Q * G * P * 3 or scale_raw.numel() != B * Q * G * T * P * L or ray_logit.numel() != B * Q * D:
+        raise RuntimeError("msmv_points: inconsistent input sizes")
+    loc = torch.empty((B * T * G, Q, P, 3), dtype=torch.float32, device=query_ray.device)
+    weights = torch.empty((B * G * T, Q, P, L), dtype=torch.float32, device=query_ray.device)
+    with torch.cuda.device(query_ray.device):
+        rc = _lib.load().racf_msmv_points_forward(
+            query_ray.data_ptr(), offset.data_ptr(), ray_logit.data_ptr(), scale_raw.data_ptr(), time_diff.data_ptr(),
+            lidar2img.data_ptr(), depth_base.data_ptr(), _pc(pc_range), float(d_region), float(image_w), float(image_h),
+            float(eps), B, Q, T, G, Pn, D, N, L, loc.data_ptr(), weights.data_ptr(), _stream(query_ray.device))
+    _lib.check(rc, "racf_msmv_points_forward")
+    return loc, weights
+
+
+def bev_points(query_ray, offset, ray_logit, attn_raw, time_diff, depth_base, pc_range, d_region, num_frames, num_heads,
+               num_points, depth_num):
+    """-> loc [T*B,Q,M,1,Pn*D,2], attn [T*B,Q,M,1,Pn*D] (queue-major, as BEVSelfAttention hands them to MSDA)."""
+    _check(query_ray, offset, ray_logit, attn_raw, time_diff, depth_base)
+    B, Q, _ = query_ray.shape
+    T, M, Pn, D = num_frames, num_heads, num_points, depth_num
+    P = Pn * D
+    if offset.numel() != B * Q * M * P * 2 or attn_raw.numel() != B * Q * M * P or ray_logit.numel() != B * Q * D:
+        raise RuntimeError("bev_points: inconsistent input sizes")
+    loc = torch.empty((T * B, Q, M, 1, P, 2), dtype=torch.float32, device=query_ray.device)
+    attn = torch.empty((T * B, Q, M, 1, P), dtype=torch.float32, device=query_ray.device)
+    with torch.cuda.device(query_ray.device):
+        rc = _lib.load().racf_bev_points_forward(
+            query_ray.data_ptr(), offset.data_ptr(), ray_logit.data_ptr(), attn_raw.data_ptr(), time_diff.data_ptr(),
+            depth_base.data_ptr(), _pc(pc_range), float(d_region), B, Q, T, M, Pn, D, loc.data_ptr(), attn.data_ptr(),
+            _stream(query_ray.device))
+    _lib.check(rc, "racf_bev_points_forward")
+    return loc, attn

@@ -12,6 +12,7 @@ import bench_workloads  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "decoder_forward_f8"
 wl = bench_workloads.build(name, torch.device("cuda", 0))
+wl.use_graph = False
 for _ in range(3):
     wl.step()
 torch.cuda.synchronize()
@@ -40,5 +41,15 @@ for e in evs:
     d[1] += 1
 total = sum(v[0] for v in agg.values())
 top = sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]
+single = sorted(evs, key=lambda e: -(e.device_time if hasattr(e, "device_time") else e.cuda_time))[:30]
+hist = {"<3us": 0, "3-10us": 0, "10-50us": 0, "50-200us": 0, ">200us": 0}
+hist_ms = dict.fromkeys(hist, 0.0)
+for e in evs:
+    t = e.device_time if hasattr(e, "device_time") else e.cuda_time
+    k = "<3us" if t < 3 else "3-10us" if t < 10 else "10-50us" if t < 50 else "50-200us" if t < 200 else ">200us"
+    hist[k] += 1
+    hist_ms[k] += t / 1e3
 print(json.dumps({"workload": name, "step_ms": step_ms, "gpu_busy_ms": total / 1e3, "num_gpu_kernels": sum(v[1] for v in agg.values()),
+                  "duration_histogram_calls": hist, "duration_histogram_ms": hist_ms,
+                  "largest_single_kernels": [{"name": e.name[:70], "us": (e.device_time if hasattr(e, "device_time") else e.cuda_time)} for e in single],
                   "top": [{"name": k, "ms": v[0] / 1e3, "calls": v[1]} for k, v in top]}, indent=1))
