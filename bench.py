@@ -171,15 +171,18 @@ def main():
 
     # ---- end to end: pinned host inputs -> H2D -> ops -> D2H result, every step --------------------------------
     wl.prepare_host_inputs()
-    for _ in range(2):
+    flush = getattr(wl, "e2e_flush", lambda: None)
+    for _ in range(3):
         wl.e2e_step()
+    flush()
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     s2.record()
     for _ in range(e2e_steps):
         wl.e2e_step()
+    flush()          # the last sample's result has been read back before the clock stops
     e2.record()
     barrier()
     ms2 = parallel.max_over_ranks(s2.elapsed_time(e2), dev)

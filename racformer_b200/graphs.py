@@ -53,3 +53,45 @@ class GraphedDecoderForward:
             self.load(inputs)
         self.graph.replay()
         return self.outputs
+
+
+class PipelinedDecoderForward:
+    """End-to-end serving loop for host-resident inputs: H2D copy of sample s+1 overlaps the decoder forward of sample s.
+
+    `depth` captured graphs, each with its own static input/output buffers, are used round-robin. A copy stream
+    moves pinned host inputs into the next slot while the compute stream replays the current one; results are copied
+    back into pinned host buffers on the compute stream. Per sample: submit() -> ticket, then result(ticket).
+    """
+
+    def __init__(self, model, example, depth=2):
+        self.dev = example["query_bbox"].device
+        self.slots = [GraphedDecoderForward(model, example) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.loaded = [torch.cuda.Event() for _ in range(depth)]     # H2D of the slot finished
+        self.free = [torch.cuda.Event() for _ in range(depth)]       # compute + D2H of the slot finished
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.host_out = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in s.outputs] for s in self.slots]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(self.dev))
+        self.next = 0
+
+    def submit(self, host_inputs):
+        i = self.next
+        self.next = (self.next + 1) % len(self.slots)
+        slot = self.slots[i]
+        compute = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_event(self.free[i])                    # slot's previous sample fully consumed
+        with torch.cuda.stream(self.copy_stream):
+            slot.load(host_inputs, non_blocking=True)
+            self.loaded[i].record(self.copy_stream)
+        compute.wait_event(self.loaded[i])
+        outs = slot()
+        for h, o in zip(self.host_out[i], outs):
+            h.copy_(o, non_blocking=True)
+        self.free[i].record(compute)
+        self.done[i].record(compute)
+        return i
+
+    def result(self, ticket):
+        self.done[ticket].synchronize()
+        return self.host_out[ticket]
