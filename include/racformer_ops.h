@@ -159,6 +159,14 @@ int racf_bev_points_forward(const float* query_ray, const float* offset, const f
                             int num_heads, int num_points, int depth_num, float* loc, float* attn,
                             racf_stream_t stream);
 
+/*
+ * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
+ * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
+ * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.
+ */
+int racf_bench_gather_ceiling(const float* buf, long long num_rows, long long total_rows, int ilp,
+                              float* sink, racf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,34 @@
+"""Measure the gather speed of light on this GPU: random coalesced 512-byte row reads (see csrc/ceiling.cu)."""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from racformer_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+sink = torch.zeros(4, device=dev)
+res = []
+for mb in (32, 64, 134, 735, 2048):
+    n_rows = mb * (1 << 20) // 512
+    buf = torch.randn(n_rows * 128, device=dev)
+    total_rows = int(1.5e9 // 512)     # ~1.5 GB of requests, like one MSMV forward at the f8 shapes
+    for ilp in (2, 4, 8, 16):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            assert lib.racf_bench_gather_ceiling(buf.data_ptr(), n_rows, total_rows, ilp, sink.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            lib.racf_bench_gather_ceiling(buf.data_ptr(), n_rows, total_rows, ilp, sink.data_ptr(), st)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        res.append({"footprint_mb": mb, "ilp": ilp, "ms": ms, "gbs": total_rows * 512 / ms / 1e6})
+    del buf
+print(json.dumps(res, indent=1))
