@@ -93,7 +93,7 @@ class ClockSampler:
 def run_reference_arm(args, rank):
     """The reference's own CPU implementation of the path (PyTorch grid_sample; oracle port) on the host cores."""
     if rank != 0:
-        return
+        return None
     import bench_workloads as workloads
     wl = workloads.build(args.workload, device="cpu", seed=0)
     cores = os.cpu_count() or 1
@@ -114,10 +114,34 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
+
+
+class QuietStdout:
+    """Route everything written to fd 1 (e.g. NCCL's version banner) to stderr until the JSON line is printed, so
+    that stdout carries exactly one line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
 
 
 def main():
+    with QuietStdout():
+        line = _main()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -131,8 +155,7 @@ def main():
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
-        run_reference_arm(args, rank)
-        return
+        return run_reference_arm(args, rank)
 
     import torch.distributed as dist
     import bench_workloads as workloads
@@ -217,9 +240,11 @@ def main():
             "cpu_baseline": cpu_baseline,
             "kernels": wl.kernel_report(hbm_peak),
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

@@ -273,7 +273,8 @@ class DecoderWorkload:
         self.model.init_weights()
         self.model.eval().to(self.device)
         self.inp = make_decoder_inputs(seed=100 + seed, device=self.device)
-        self.launches_per_step = 3 * num_layers
+        # our kernels per step: per iteration 1 MSMV + 2 MSDA, and (inference) 1 + 2 fused point-generation kernels
+        self.launches_per_step = 6 * num_layers
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None
