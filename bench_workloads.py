@@ -263,7 +263,8 @@ class DecoderWorkload:
         if self.on_gpu:
             base = SamplingOps()
             ops = SamplingOps(msmv=lambda *a: self._timed("msmv_fwd", base.msmv, a),
-                              msda=lambda *a: self._timed("msda_fwd", base.msda, a))
+                              msda=lambda *a: self._timed("msda_fwd", base.msda, a),
+                              msmv_grouped=lambda *a: self._timed("msmv_fwd", base.msmv_grouped, a))
         else:   # CPU baseline leg: the oracle's port of the reference's PyTorch ops (never used for the GPU numbers)
             from oracle import reference_port
             ops = SamplingOps(msmv=reference_port.msmv_sampling_torch_channel_last,

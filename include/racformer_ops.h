@@ -35,6 +35,7 @@ extern "C" {
 #define RACF_ERR_BAD_SHAPE     (-3)  /* a dimension is <= 0 or a per-batch extent overflows int32 */
 #define RACF_ERR_TOO_MANY_PTS  (-4)  /* num_point > RACF_MSMV_MAX_POINT (reference: msmv_sampling.cpp:159) */
 #define RACF_ERR_IM2COL_STEP   (-5)  /* batch % min(batch, im2col_step) != 0 (mmcv contract) */
+#define RACF_ERR_UNSUPPORTED   (-6)  /* the requested variant only exists for the fast path (C == 64, L in {2,4,5}) */
 
 #define RACF_MAX_LEVELS        8
 #define RACF_MSMV_MAX_POINT    128
@@ -62,6 +63,17 @@ int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels,
                       const float* loc, const float* weights,
                       int batch, int channels, int num_views, int num_query, int num_point,
                       float* out, racf_stream_t stream);
+
+/*
+ * Forward with the un-packing of sampling_4d's tail fused in (models/sparsebev_sampling.py:128-131): batch is
+ * B*T*G (T = num_frames, G = num_groups, G fastest) and out is [B, Q, G, T*P, C] -- what AdaptiveMixing consumes --
+ * instead of [B*T*G, Q, C, P]. Same arithmetic as racf_msmv_forward; forward only; fast path only
+ * (returns RACF_ERR_UNSUPPORTED otherwise, callers then use racf_msmv_forward + a permute).
+ */
+int racf_msmv_forward_grouped(const float* const* feats, const int* hw, int num_levels,
+                              const float* loc, const float* weights,
+                              int batch, int channels, int num_views, int num_query, int num_point,
+                              int num_frames, int num_groups, float* out, racf_stream_t stream);
 
 /*
  * Multi-scale multi-view sampling, backward (msmv_sampling_backward.cu:29-105,132-223).
@@ -158,6 +170,13 @@ int racf_bev_points_forward(const float* query_ray, const float* offset, const f
                             const double* pc_range, float d_region, int batch, int num_query, int num_frames,
                             int num_heads, int num_points, int depth_num, float* loc, float* attn,
                             racf_stream_t stream);
+
+/*
+ * "next" row: channel-last re-layout of one FPN level,
+ * in [B, T*N, G*C, H, W] -> out [B*T*G, N, H, W, C] (models/racformer_transformer.py:112-124), C == 64.
+ */
+int racf_to_sampling_layout(const float* in, float* out, int batch, int num_frames, int num_views,
+                            int num_groups, int channels, int height, int width, racf_stream_t stream);
 
 /*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over

@@ -17,6 +17,8 @@ SIGNATURES = {
     "racf_status_string": (ctypes.c_char_p, [_i]),
     "racf_msmv_forward": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
                                _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_msmv_forward_grouped": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
+                                       _i, _i, _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_msmv_backward": (_i, [_c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p,
                                 _c_float_p, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                 _c_float_p, _i, ctypes.c_void_p]),
@@ -31,6 +33,7 @@ SIGNATURES = {
                                  + [_i] * 8 + [_c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_bev_points_forward": (_i, [_c_float_p] * 6 + [ctypes.POINTER(ctypes.c_double), ctypes.c_float] + [_i] * 6
                                 + [_c_float_p, _c_float_p, ctypes.c_void_p]),
+    "racf_to_sampling_layout": (_i, [_c_float_p, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
     "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
 }

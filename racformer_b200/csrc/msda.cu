@@ -383,6 +383,7 @@ extern "C" const char* racf_status_string(int status) {
         case RACF_ERR_BAD_SHAPE: return "invalid or too large dimension";
         case RACF_ERR_TOO_MANY_PTS: return "num_point exceed limits";
         case RACF_ERR_IM2COL_STEP: return "batch must be divisible by min(batch, im2col_step)";
+        case RACF_ERR_UNSUPPORTED: return "variant not available for these shapes";
         default: break;
     }
     if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));

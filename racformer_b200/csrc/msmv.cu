@@ -37,6 +37,7 @@ struct MsmvArgs {
     float* grad_loc;       // [B,Q,P,3]
     float* grad_wts;       // [B,Q,P,L]
     int B, N, Q, P, C;
+    int out_T, out_G;   // > 0: forward writes the un-packed layout [B/(T*G), Q, G, T*P, C] instead of [B,Q,C,P]
 };
 
 template <int L>
@@ -166,8 +167,22 @@ __global__ void __launch_bounds__(kMsmvWarps * 32, 2) msmv_fwd_c64_kernel(const 
                 acc[pp].z += __shfl_xor_sync(0xffffffffu, acc[pp].z, 16);
                 acc[pp].w += __shfl_xor_sync(0xffffffffu, acc[pp].w, 16);
             }
-            // out[b,q,c,p]: lane (slot, j) stores channels 4j + 2*slot + {0,1}, points p0..p0+3
             const int p0 = pb + c;
+            if (a.out_T > 0) {
+                // un-packed layout of sampling_4d's tail (sparsebev_sampling.py:128-131): out[bb,q,g,t*P+p,:], one
+                // pixel-sized 256 B row per point; half-warp 0 stores points 0,1 and half-warp 1 points 2,3
+                const int g = b % a.out_G, t = (b / a.out_G) % a.out_T, bb = b / (a.out_G * a.out_T);
+                const int q = (int)(bq - (long long)b * a.Q);
+                float* rowp = a.out + ((((size_t)bb * a.Q + q) * a.out_G + g) * ((size_t)a.out_T * a.P) + (size_t)t * a.P) * 64;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pp = 2 * slot + h;
+                    const float4 val = slot ? (h ? acc[3] : acc[2]) : (h ? acc[1] : acc[0]);
+                    if (p0 + pp < a.P) *reinterpret_cast<float4*>(rowp + (size_t)(p0 + pp) * 64 + 4 * j) = val;
+                }
+                continue;
+            }
+            // out[b,q,c,p]: lane (slot, j) stores channels 4j + 2*slot + {0,1}, points p0..p0+3
             const int c0 = 4 * j + 2 * slot;
             const float4 e0 = slot ? make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z)
                                    : make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
@@ -482,8 +497,10 @@ static int check_msmv_common(const float* const* feats, const int* hw, int L, co
 template <int L>
 static int launch_fast(bool backward, const float* grad_out, const float* const* feats, float* const* grad_feats,
                        const int* hw, const float* loc, const float* wts, int B, int C, int N, int Q, int P,
-                       float* out, float* grad_loc, float* grad_wts, cudaStream_t st) {
+                       float* out, float* grad_loc, float* grad_wts, cudaStream_t st, int out_T = 0, int out_G = 0) {
     MsmvArgs<L> a;
+    a.out_T = out_T;
+    a.out_G = out_G;
     for (int l = 0; l < L; ++l) {
         a.feat[l] = feats[l];
         a.grad_feat[l] = grad_feats ? grad_feats[l] : nullptr;
@@ -556,6 +573,24 @@ extern "C" int racf_msmv_forward(const float* const* feats, const int* hw, int n
     }
     return launch_generic(false, nullptr, feats, nullptr, hw, num_levels, loc, weights, batch, channels, num_views,
                           num_query, num_point, out, nullptr, nullptr, st);
+}
+
+extern "C" int racf_msmv_forward_grouped(const float* const* feats, const int* hw, int num_levels, const float* loc,
+                                         const float* weights, int batch, int channels, int num_views, int num_query,
+                                         int num_point, int num_frames, int num_groups, float* out,
+                                         racf_stream_t stream) {
+    int rc = check_msmv_common(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query, num_point);
+    if (rc != RACF_OK) return rc;
+    if (!out) return RACF_ERR_NULL_POINTER;
+    if (num_frames <= 0 || num_groups <= 0 || batch % (num_frames * num_groups) != 0) return RACF_ERR_BAD_SHAPE;
+    if (!fast_ok(feats, nullptr, num_levels, channels, out)) return RACF_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (num_levels) {
+        case 2: return launch_fast<2>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, num_frames, num_groups);
+        case 4: return launch_fast<4>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, num_frames, num_groups);
+        case 5: return launch_fast<5>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, num_frames, num_groups);
+    }
+    return RACF_ERR_UNSUPPORTED;
 }
 
 extern "C" int racf_msmv_backward(const float* grad_out, const float* const* feats, const int* hw, int num_levels,

@@ -37,13 +37,15 @@ from torch.utils.checkpoint import checkpoint as _torch_checkpoint
 class SamplingOps:
     """msmv(feats_channel_last, loc, w) -> [B',Q,C,P];  msda(value, shapes, lsi, loc, aw, im2col_step) -> [B,Q,M*D]."""
 
-    def __init__(self, msmv=None, msda=None):
+    def __init__(self, msmv=None, msda=None, msmv_grouped=None):
         if msmv is None or msda is None:
             from . import wrapper
             from .multi_scale_deformable_attn_function import MultiScaleDeformableAttnFunction_fp32
+            if msmv is None and msmv_grouped is None:
+                msmv_grouped = wrapper.msmv_forward_grouped     # inference-only variant with the un-packing fused in
             msmv = msmv or wrapper.msmv_sampling
             msda = msda or MultiScaleDeformableAttnFunction_fp32.apply
-        self.msmv, self.msda = msmv, msda
+        self.msmv, self.msda, self.msmv_grouped = msmv, msda, msmv_grouped
 
 
 _CONST_CACHE = {}
@@ -302,6 +304,8 @@ class RaCFormerSampling(nn.Module):
                 self.scale_weights(query_feat), meta["time_diff"], meta["lidar2img"],
                 _depth_base(d_region, D, query_feat.device), pr, d_region, meta["image_w"], meta["image_h"],
                 T, G, Pn, D, self.num_levels)
+            if getattr(ops, "msmv_grouped", None) is not None:
+                return ops.msmv_grouped(mlvl_feats, loc, w, T, G)                      # [B,Q,G,T*P,C] directly
             out = ops.msmv(mlvl_feats, loc, w)                                         # [B*T*G,Q,C,P]
             C = out.shape[2]
             return out.reshape(B, T, G, Q, C, Pn * D).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
@@ -520,6 +524,8 @@ class AdaptiveMixing(nn.Module):
         self.m_parameters = self.eff_in_dim * self.eff_out_dim
         self.s_parameters = self.in_points * self.out_points
         self.activation_checkpoint = True
+        self.fold_bias = True
+        self._folded = None
         self.parameter_generator = nn.Linear(in_dim, n_groups * (self.m_parameters + self.s_parameters))
         self.out_proj = nn.Linear(self.eff_out_dim * self.out_points * n_groups, in_dim)
 
@@ -527,9 +533,22 @@ class AdaptiveMixing(nn.Module):
     def init_weights(self):
         nn.init.zeros_(self.parameter_generator.weight)
 
+    def _generate(self, query):
+        """parameter_generator(query). In inference the bias is folded into the GEMM as an extra K column
+        ([q, 1] @ [W, b]^T): cuBLAS otherwise adds it in a separate pass over the 236 MB output (0.16 ms per layer on
+        B200, profiles/r01_decoder_forward_kernel_breakdown_fused.json). Same sum, rounded inside the accumulator."""
+        lin = self.parameter_generator
+        if torch.is_grad_enabled() or not query.is_cuda or lin.bias is None or not self.fold_bias:
+            return lin(query)
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+        if self._folded is None or self._folded[0] != key:
+            self._folded = (key, torch.cat([lin.weight.detach(), lin.bias.detach()[:, None]], dim=1).contiguous())
+        ones = torch.ones_like(query[..., :1])
+        return F.linear(torch.cat([query, ones], dim=-1), self._folded[1])
+
     def inner_forward(self, x, query):
         B, Q, G, P, C = x.shape
-        params = self.parameter_generator(query).reshape(B * Q, G, -1)
+        params = self._generate(query).reshape(B * Q, G, -1)
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)
         s = s.reshape(B * Q, G, self.out_points, self.in_points)
@@ -622,6 +641,10 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
     """[B, T*N, G*C, H, W] FPN level -> channel-last sampling layout [B*T*G, N, H, W, C] (racformer_transformer.py:112-124)."""
     B, TN, GC, H, W = feat.shape
     N, T, G, C = num_cams, TN // num_cams, num_groups, GC // num_groups
+    if (C == 64 and feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous()
+            and not (torch.is_grad_enabled() and feat.requires_grad)):
+        from . import points   # tiled-transpose kernel (SURVEY 8f-3); the PyTorch permute below is the autograd path
+        return points.to_sampling_layout(feat, num_cams, num_groups)
     return feat.reshape(B, T, N, G, C, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, C).contiguous()
 
 

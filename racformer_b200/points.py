@@ -63,3 +63,16 @@ def bev_points(query_ray, offset, ray_logit, attn_raw, time_diff, depth_base, pc
             _stream(query_ray.device))
     _lib.check(rc, "racf_bev_points_forward")
     return loc, attn
+
+
+def to_sampling_layout(feat, num_cams, num_groups=4):
+    """[B, T*N, G*C, H, W] -> [B*T*G, N, H, W, C] with the tiled-transpose kernel (C == 64, fp32 CUDA, no autograd)."""
+    _check(feat)
+    B, TN, GC, H, W = feat.shape
+    T, C = TN // num_cams, GC // num_groups
+    out = torch.empty((B * T * num_groups, num_cams, H, W, C), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        rc = _lib.load().racf_to_sampling_layout(feat.data_ptr(), out.data_ptr(), B, T, num_cams, num_groups, C, H, W,
+                                                 _stream(feat.device))
+    _lib.check(rc, "racf_to_sampling_layout")
+    return out

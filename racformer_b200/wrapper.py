@@ -91,6 +91,28 @@ def msmv_forward(feats, sampling_loc, attn_weight):
     return out
 
 
+def msmv_forward_grouped(feats, sampling_loc, attn_weight, num_frames, num_groups):
+    """Forward with sampling_4d's un-packing fused in: -> [B, Q, G, T*P, C] (B' = B*T*G). Inference helper, no autograd.
+    Falls back to msmv_forward + permute when the fused variant does not exist for the shapes."""
+    feats = list(feats)
+    Bp, N, C, Q, P = _check_inputs(feats, sampling_loc, attn_weight)
+    T, G = int(num_frames), int(num_groups)
+    _require(Bp % (T * G) == 0, "batch must be B * num_frames * num_groups")
+    B = Bp // (T * G)
+    out = torch.empty((B, Q, G, T * P, C), dtype=torch.float32, device=feats[0].device)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(feats[0].device):
+        rc = _lib.load().racf_msmv_forward_grouped(
+            _ptr_array(feats), _hw_array(feats), len(feats), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+            Bp, C, N, Q, P, T, G, out.data_ptr(), _stream(feats[0].device))
+    if rc == -6:   # RACF_ERR_UNSUPPORTED: generic shapes
+        plain = msmv_forward(feats, sampling_loc, attn_weight)
+        return plain.reshape(B, T, G, Q, C, P).permute(0, 3, 2, 1, 5, 4).flatten(3, 4).contiguous()
+    _lib.check(rc, "racf_msmv_forward_grouped")
+    return out
+
+
 def msmv_backward(grad_output, feats, sampling_loc, attn_weight):
     """-> [grad_feat_0, ..., grad_feat_{L-1}, grad_sampling_loc, grad_attn_weight] (msmv_sampling.cpp:356-358)."""
     feats = list(feats)

@@ -30,7 +30,13 @@ class Spy(SamplingOps):
             self.msda_args.append((loc.clone(), aw.clone()))
             return real_msda(value, shapes, lsi, loc, aw, step)
 
-        self.msmv, self.msda = msmv, msda
+        real_grouped = self.msmv_grouped
+
+        def grouped(feats, loc, w, T, G):
+            self.msmv_args.append((loc.clone(), w.clone()))
+            return real_grouped(feats, loc, w, T, G)
+
+        self.msmv, self.msda, self.msmv_grouped = msmv, msda, grouped
 
 
 def _run(cfg, inputs, fused, seed=3):
@@ -103,3 +109,34 @@ def test_fused_points_f8_shapes():
     g = torch.Generator().manual_seed(1)
     d["query_bbox"][..., 8:10] = (torch.randn(1, 900, 2, generator=g) * 0.5).cuda()
     _compare(cfg, d, num_views=6)
+
+
+def test_grouped_output_variant_is_bit_identical_to_permuted_reference_layout():
+    """racf_msmv_forward_grouped = racf_msmv_forward + sampling_4d's un-packing (sparsebev_sampling.py:128-131)."""
+    from racformer_b200 import wrapper
+    from tests.helpers import make_msmv_inputs
+    B, T, G, Q, P, C = 2, 3, 4, 50, 12, 64
+    feats, loc, w, _ = make_msmv_inputs(3, Bp=B * T * G, N=6, C=C, Q=Q, P=P, shapes=[(16, 44), (8, 22), (4, 11), (2, 6)],
+                                        lo=-0.1, hi=1.1, device="cuda")
+    plain = wrapper.msmv_forward(feats, loc, w)
+    want = plain.reshape(B, T, G, Q, C, P).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
+    got = wrapper.msmv_forward_grouped(feats, loc, w, T, G)
+    assert got.shape == (B, Q, G, T * P, C) and torch.equal(got, want)
+    # ragged point count and a level count without a fast kernel (falls back to forward + permute)
+    feats, loc, w, _ = make_msmv_inputs(4, Bp=T * G, N=3, C=C, Q=7, P=5, shapes=[(8, 22), (4, 11), (2, 6)], device="cuda")
+    plain = wrapper.msmv_forward(feats, loc, w)
+    want = plain.reshape(1, T, G, 7, C, 5).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
+    assert torch.equal(wrapper.msmv_forward_grouped(feats, loc, w, T, G), want)
+    feats, loc, w, _ = make_msmv_inputs(5, Bp=T * G, N=3, C=C, Q=7, P=6, shapes=[(8, 22), (4, 11)], device="cuda")
+    plain = wrapper.msmv_forward(feats, loc, w)
+    want = plain.reshape(1, T, G, 7, C, 6).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
+    assert torch.equal(wrapper.msmv_forward_grouped(feats, loc, w, T, G), want)
+
+
+def test_channel_last_relayout_kernel_equals_permute():
+    """racf_to_sampling_layout = reshape/permute/contiguous of racformer_transformer.py:112-124, bit for bit."""
+    from racformer_b200 import points
+    for (B, T, N, G, H, W) in ((1, 8, 6, 4, 8, 22), (2, 2, 3, 4, 5, 7), (1, 1, 6, 4, 64, 176)):
+        feat = torch.randn(B, T * N, G * 64, H, W, device="cuda")
+        want = feat.reshape(B, T, N, G, 64, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, 64).contiguous()
+        assert torch.equal(points.to_sampling_layout(feat, N, G), want)
