@@ -303,3 +303,77 @@ def test_msda_errors():
     with pytest.raises(RuntimeError, match="contiguous"):
         strided = torch.zeros(6, 16, 1, 128, device=DEV)[..., ::2]
         msda.ext_module.ms_deform_attn_forward(strided, sp, lsi, loc, aw, im2col_step=64)
+
+
+# ------------------------------------------------------------------------------------------------ guard bands
+def _guarded(shape, pad=1024, fill=float("nan")):
+    """A tensor living inside a larger sentinel-filled allocation (compute-sanitizer is closed on this pool)."""
+    n = 1
+    for s in shape:
+        n *= s
+    big = torch.full((n + 2 * pad,), fill, device=DEV)
+    return big, big[pad:pad + n].view(shape)
+
+
+def test_no_out_of_bounds_access_guard_bands():
+    """Boundary-heavy coordinates (pixel -1, -0.5, 0, W-1, W-0.5, W, corners of the first/last view and batch element):
+    forward must never read the NaN guard bands around the feature maps (outputs stay finite and equal to the
+    unguarded run) and backward must never write outside the gradient buffers (sentinels intact)."""
+    import ctypes
+    from racformer_b200 import _lib, wrapper
+    shapes = [(8, 12), (4, 6), (2, 3), (1, 2)]
+    Bp, N, C, Q, P = 2, 3, 64, 16, 12
+    feats, loc, w, g = make_msmv_inputs(17, Bp=Bp, N=N, C=C, Q=Q, P=P, shapes=shapes, lo=-0.2, hi=1.2)
+    h0, w0 = shapes[0]
+    edge_x = torch.tensor([-1.0, -0.5, 0.0, w0 - 1.0, w0 - 0.5, float(w0), -1e-7, w0 - 1 + 1e-7]) / (w0 - 1)
+    edge_y = torch.tensor([-1.0, -0.5, 0.0, h0 - 1.0, h0 - 0.5, float(h0), -1e-7, h0 - 1 + 1e-7]) / (h0 - 1)
+    for b in (0, Bp - 1):
+        for k in range(8):
+            loc[b, k, :, 0] = edge_x[k]
+            loc[b, k, :, 1] = edge_y[(k + torch.arange(P)) % 8]
+            loc[b, k, :, 2] = (0.0 if b == 0 else 1.0)          # first view of the first element / last of the last
+    guards, gfeats = zip(*[_guarded(f.shape) for f in feats])
+    for gf, f in zip(gfeats, feats):
+        gf.copy_(f)
+    loc_d, w_d, g_d = loc.to(DEV), w.to(DEV), g.to(DEV)
+    out_guarded = wrapper.msmv_forward(list(gfeats), loc_d, w_d)
+    out_plain = wrapper.msmv_forward([f.to(DEV) for f in feats], loc_d, w_d)
+    assert torch.isfinite(out_guarded).all(), "forward read a guard band"
+    assert torch.equal(out_guarded, out_plain)
+    # backward through the C ABI with caller-owned, guarded gradient buffers
+    gg_guards, gg = zip(*[_guarded(f.shape, fill=12345.0) for f in feats])
+    for t in gg:
+        t.zero_()
+    gl_guard, gl = _guarded(loc.shape, fill=12345.0)
+    gw_guard, gw = _guarded(w.shape, fill=12345.0)
+    lib = _lib.load()
+    ptrs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in gfeats])
+    gptrs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in gg])
+    hw = (ctypes.c_int * 8)(*[d for s in shapes for d in s])
+    rc = lib.racf_msmv_backward(g_d.data_ptr(), ptrs, hw, 4, loc_d.data_ptr(), w_d.data_ptr(), Bp, C, N, Q, P, gptrs,
+                                gl.data_ptr(), gw.data_ptr(), 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    pad = 1024
+    for big in list(gg_guards) + [gl_guard, gw_guard]:
+        assert bool((big[:pad] == 12345.0).all()) and bool((big[-pad:] == 12345.0).all()), "backward wrote out of bounds"
+    ref = wrapper.msmv_backward(g_d, [f.to(DEV) for f in feats], loc_d, w_d)
+    for a, b in zip(list(gg) + [gl, gw], ref):
+        assert_close(a, b, BWD_RTOL, BWD_ATOL * _scale(b), "guarded backward vs plain backward")
+    # MSDA: same idea on the value map
+    value, sp, lsi, mloc, aw, mg = make_msda_inputs(3, B=2, M=4, D=64, Q=16, P=20, shapes=[(6, 5)], lo=-0.2, hi=1.2)
+    mloc[0, 0, 0, 0, :6, 0] = torch.tensor([-0.5, 0.0, 0.5, 4.5, 5.0, 5.5]) / 5
+    mloc[0, 0, 0, 0, :6, 1] = torch.tensor([-0.5, 0.0, 0.5, 5.5, 6.0, 6.5]) / 6
+    mloc[-1, -1, -1, 0, :6] = mloc[0, 0, 0, 0, :6]
+    _, msda = _ops()
+    vguard, vg = _guarded(value.shape)
+    vg.copy_(value)
+    args = [sp.to(DEV), lsi.to(DEV), mloc.to(DEV), aw.to(DEV)]
+    mo = msda.ext_module.ms_deform_attn_forward(vg, *args, im2col_step=64)
+    assert torch.isfinite(mo).all() and torch.equal(mo, msda.ext_module.ms_deform_attn_forward(value.to(DEV), *args, im2col_step=64))
+    gvguard, gv = _guarded(value.shape, fill=12345.0)
+    gv.zero_()
+    gl2, ga2 = torch.empty_like(args[2]), torch.empty_like(args[3])
+    msda.ext_module.ms_deform_attn_backward(vg, *args, mg.to(DEV), gv, gl2, ga2, im2col_step=64)
+    torch.cuda.synchronize()
+    assert bool((gvguard[:pad] == 12345.0).all()) and bool((gvguard[-pad:] == 12345.0).all())
