@@ -16,7 +16,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libracformer_ops.so")
+LIB_PATH = os.environ.get("RACF_LIB_PATH") or os.path.join(LIB_DIR, "libracformer_ops.so")   # override: tuning experiments
 STAMP = LIB_PATH + ".srchash"
 
 SOURCES = ["msmv.cu", "msda.cu", "points.cu", "layout.cu", "ceiling.cu"]
@@ -42,7 +42,7 @@ def source_hash():
     for f in files:
         with open(f, "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("RACF_NVCC_DEFINES", "")).encode())
     return h.hexdigest()
 
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("RACF_NVCC_DEFINES", "").split() + ["-I", INCLUDE, "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]

@@ -15,13 +15,18 @@
 //     one lane per tap and staged in shared memory; every lane then reads it back as a broadcast.
 //   * backward scatters the feature gradient with red.global.add.v4.f32: one 512-byte vector
 //     reduction per row per warp instead of 128 scalar atomics.
+#include <cstdlib>
+
 #include "racf_common.cuh"
 #include "racformer_ops.h"
 
 namespace racf {
 
 constexpr int kMsmvChunk = 4;   // sample points handled per inner round (also the float4 width along P)
-constexpr int kMsmvWarps = 8;   // warps (queries) per CTA on the fast path
+#ifndef RACF_MSMV_WARPS
+#define RACF_MSMV_WARPS 8
+#endif
+constexpr int kMsmvWarps = RACF_MSMV_WARPS;   // warps (queries) per CTA on the fast path
 constexpr int kLanesPerPixel = 16;  // C == 64 -> 16 float4 lanes
 
 template <int L>
@@ -62,8 +67,11 @@ struct PointRegs {
     float4 bot[L];
 };
 
+#ifndef RACF_FWD_MIN_BLOCKS
+#define RACF_FWD_MIN_BLOCKS 2   // 128 registers: room for two point buffers (16 x 128-bit loads in flight per lane)
+#endif
 template <int L>
-__global__ void __launch_bounds__(kMsmvWarps * 32, 2) msmv_fwd_c64_kernel(const MsmvArgs<L> a) {
+__global__ void __launch_bounds__(kMsmvWarps * 32, RACF_FWD_MIN_BLOCKS) msmv_fwd_c64_kernel(const MsmvArgs<L> a) {
     constexpr int G = kLanesPerPixel;
     constexpr int PB = (L <= 4) ? 16 : 12;      // points per staged batch (multiple of kMsmvChunk)
     constexpr int NT = PB * L;                  // taps per batch (<= 64)
@@ -201,6 +209,198 @@ __global__ void __launch_bounds__(kMsmvWarps * 32, 2) msmv_fwd_c64_kernel(const 
                     }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path, forward, persistent variant with software L2 prefetch (used when a query fits one staged batch).
+//
+// The gather is limited by bytes in flight per SM (ncu r01b; every occupancy/register trade lands on the same
+// ~130 us plateau, profiles/r01_msmv_fwd_variants.txt). Each warp walks its queries in a 3-stage pipeline, so the
+// loc/weight loads and the tap-record computation of the following queries hide behind the gather of the current
+// one (133 -> 125 us). The optional prefetch.global.L2 of the next query's rows was measured too and is OFF: it
+// costs L2 request bandwidth, which is the binding resource (145-168 us with 1-4 levels prefetched).
+//   iteration i:  (a) turn the loc/weights loaded during iteration i-1 into the tap records of query i+1 and issue
+//                     prefetch.global.L2 for their cell rows on the DRAM-sized levels,
+//                 (b) load loc/weights of query i+2 into registers,
+//                 (c) gather + blend query i, whose rows were prefetched one iteration ago.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int L>
+__global__ void __launch_bounds__(kMsmvWarps * 32, 2) msmv_fwd_c64_pf_kernel(const MsmvArgs<L> a, int prefetch_levels) {
+    constexpr int G = kLanesPerPixel;
+    constexpr int PB = (L <= 4) ? 16 : 12;
+    constexpr int NT = PB * L;
+    constexpr int NTP = NT + L;
+    constexpr int TPL = (NT + 31) / 32;          // taps owned by a lane (<= 2)
+    __shared__ float2 s_w[kMsmvWarps][2][NTP][2];
+    __shared__ int2 s_om[kMsmvWarps][2][NTP];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane >> 4, j = lane & 15;
+    const long long nq = (long long)a.B * a.Q;
+    const long long stride = (long long)gridDim.x * kMsmvWarps;
+    const long long q0 = (long long)blockIdx.x * kMsmvWarps + warp;
+    if (q0 >= nq) return;
+
+    const float4* lbase[L];
+    int row[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        lbase[l] = reinterpret_cast<const float4*>(a.feat[l]) + slot * G + j;
+        row[l] = a.W[l] * G;
+    }
+    const bool vec_store = (a.P % 4) == 0;
+    if (lane < L) {
+#pragma unroll
+        for (int bsel = 0; bsel < 2; ++bsel) {
+            s_w[warp][bsel][NT + lane][0] = make_float2(0.f, 0.f);
+            s_w[warp][bsel][NT + lane][1] = make_float2(0.f, 0.f);
+            s_om[warp][bsel][NT + lane] = make_int2(0, 0);
+        }
+    }
+
+    float lx[TPL], ly[TPL], lz[TPL], sw[TPL];
+    auto load_locw = [&](long long q) {
+#pragma unroll
+        for (int k = 0; k < TPL; ++k) {
+            const int t = lane + 32 * k, pp = t / L, l = t % L;
+            lx[k] = ly[k] = lz[k] = sw[k] = 0.f;
+            if (q < nq && t < NT && pp < a.P) {
+                const float* lp = a.loc + (q * a.P + pp) * 3;
+                lx[k] = __ldg(lp); ly[k] = __ldg(lp + 1); lz[k] = __ldg(lp + 2);
+                sw[k] = __ldg(a.wts + (q * a.P + pp) * L + l);
+            }
+        }
+    };
+    auto stage = [&](long long q, int buf) {
+        const int b = (int)(q / a.Q);
+#pragma unroll
+        for (int k = 0; k < TPL; ++k) {
+            const int t = lane + 32 * k;
+            if (t >= NT) continue;
+            const int pp = t / L, l = t % L;
+            float2 w0 = make_float2(0.f, 0.f), w1 = w0;
+            int2 om = make_int2(0, 0);
+            if (pp < a.P) {
+                int H, W;
+                level_dims<L>(a, l, H, W);
+                const int v = msmv_view(lz[k], a.N);
+                const TapGeom g = tap_geometry(msmv_pixel(ly[k], H), msmv_pixel(lx[k], W), H, W);
+                if (g.mask != 0u && v >= 0 && v < a.N) {
+                    const float hh = 1.f - g.lh, hw = 1.f - g.lw, s = sw[k];
+                    w0 = make_float2(hh * hw * s, g.lh * hw * s);
+                    w1 = make_float2(hh * g.lw * s, g.lh * g.lw * s);
+                    om.x = ((((b * a.N + v) * H) + g.h_low) * W + g.w_low) * G;
+                    om.y = (int)g.mask;
+                    if (l < prefetch_levels) {
+                        const float* f = a.feat[0];
+#pragma unroll
+                        for (int kk = 1; kk < L; ++kk)
+                            if (kk == l) f = a.feat[kk];
+                        const char* top = reinterpret_cast<const char*>(f) + (long long)om.x * 16;
+                        const char* bot = top + (long long)W * G * 16;
+                        if (g.mask & kTL) { prefetch_l2(top); prefetch_l2(top + 128); }
+                        if (g.mask & kTR) { prefetch_l2(top + 256); prefetch_l2(top + 384); }
+                        if (g.mask & kBL) { prefetch_l2(bot); prefetch_l2(bot + 128); }
+                        if (g.mask & kBR) { prefetch_l2(bot + 256); prefetch_l2(bot + 384); }
+                    }
+                }
+            }
+            s_w[warp][buf][t][0] = w0;
+            s_w[warp][buf][t][1] = w1;
+            s_om[warp][buf][t] = om;
+        }
+    };
+
+    // prologue: query 0 staged directly, loc/weights of query 1 in registers
+    load_locw(q0);
+    stage(q0, 0);
+    load_locw(q0 + stride);
+    int cur = 0;
+    for (long long q = q0; q < nq; q += stride, cur ^= 1) {
+        if (q + stride < nq) stage(q + stride, cur ^ 1);
+        load_locw(q + 2 * stride);
+        __syncwarp();
+
+        auto issue = [&](PointRegs<L>& r, int pt) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int2 om = s_om[warp][cur][pt * L + l];
+                const unsigned m = (unsigned)om.y >> slot;
+                const float4* p = lbase[l] + om.x;
+                r.top[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r.bot[l] = r.top[l];
+                if (m & 1u) r.top[l] = ldg128(p);
+                if (m & 4u) r.bot[l] = ldg128(p + row[l]);
+            }
+        };
+        auto consume = [&](const PointRegs<L>& r, int pt, float4& acc) {
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const float2 w = s_w[warp][cur][pt * L + l][slot];
+                acc.x = fmaf(w.y, r.bot[l].x, fmaf(w.x, r.top[l].x, acc.x));
+                acc.y = fmaf(w.y, r.bot[l].y, fmaf(w.x, r.top[l].y, acc.y));
+                acc.z = fmaf(w.y, r.bot[l].z, fmaf(w.x, r.top[l].z, acc.z));
+                acc.w = fmaf(w.y, r.bot[l].w, fmaf(w.x, r.top[l].w, acc.w));
+            }
+        };
+
+        const int b = (int)(q / a.Q);
+        float* out_q = a.out + q * 64 * a.P;
+        PointRegs<L> ra, rb;
+        issue(ra, 0);
+        for (int c = 0; c < a.P; c += kMsmvChunk) {
+            float4 acc[kMsmvChunk];
+            issue(rb, c + 1);
+            consume(ra, c + 0, acc[0]);
+            issue(ra, c + 2);
+            consume(rb, c + 1, acc[1]);
+            issue(rb, c + 3);
+            consume(ra, c + 2, acc[2]);
+            issue(ra, c + 4);
+            consume(rb, c + 3, acc[3]);
+#pragma unroll
+            for (int pp = 0; pp < kMsmvChunk; ++pp) {
+                acc[pp].x += __shfl_xor_sync(0xffffffffu, acc[pp].x, 16);
+                acc[pp].y += __shfl_xor_sync(0xffffffffu, acc[pp].y, 16);
+                acc[pp].z += __shfl_xor_sync(0xffffffffu, acc[pp].z, 16);
+                acc[pp].w += __shfl_xor_sync(0xffffffffu, acc[pp].w, 16);
+            }
+            const int p0 = c;
+            if (a.out_T > 0) {
+                const int g = b % a.out_G, t = (b / a.out_G) % a.out_T, bb = b / (a.out_G * a.out_T);
+                const int qi = (int)(q - (long long)b * a.Q);
+                float* rowp = a.out + ((((size_t)bb * a.Q + qi) * a.out_G + g) * ((size_t)a.out_T * a.P) + (size_t)t * a.P) * 64;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pp = 2 * slot + h;
+                    const float4 val = slot ? (h ? acc[3] : acc[2]) : (h ? acc[1] : acc[0]);
+                    if (p0 + pp < a.P) *reinterpret_cast<float4*>(rowp + (size_t)(p0 + pp) * 64 + 4 * j) = val;
+                }
+                continue;
+            }
+            const int c0 = 4 * j + 2 * slot;
+            const float4 e0 = slot ? make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z)
+                                   : make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+            const float4 e1 = slot ? make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w)
+                                   : make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+            if (vec_store) {
+                *reinterpret_cast<float4*>(out_q + (size_t)c0 * a.P + p0) = e0;
+                *reinterpret_cast<float4*>(out_q + (size_t)(c0 + 1) * a.P + p0) = e1;
+            } else {
+                const float v0[4] = {e0.x, e0.y, e0.z, e0.w}, v1[4] = {e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                for (int pp = 0; pp < kMsmvChunk; ++pp)
+                    if (p0 + pp < a.P) {
+                        out_q[(size_t)c0 * a.P + p0 + pp] = v0[pp];
+                        out_q[(size_t)(c0 + 1) * a.P + p0 + pp] = v1[pp];
+                    }
+            }
+        }
+        __syncwarp();   // every lane is done with buffer `cur` before the next iteration restages it
     }
 }
 
@@ -494,6 +694,16 @@ static int check_msmv_common(const float* const* feats, const int* hw, int L, co
     return RACF_OK;
 }
 
+// Forward variant selector (tuning knob, read once): RACF_MSMV_FWD_MODE = 0 one-query-per-warp kernel,
+// -1 persistent kernel without prefetch, k > 0 persistent kernel prefetching the first k levels into L2.
+static int msmv_fwd_mode() {
+    static int mode = [] {
+        const char* e = getenv("RACF_MSMV_FWD_MODE");
+        return e ? atoi(e) : -1;   // measured best on B200 (profiles/r01_msmv_fwd_variants.txt)
+    }();
+    return mode;
+}
+
 template <int L>
 static int launch_fast(bool backward, const float* grad_out, const float* const* feats, float* const* grad_feats,
                        const int* hw, const float* loc, const float* wts, int B, int C, int N, int Q, int P,
@@ -511,10 +721,21 @@ static int launch_fast(bool backward, const float* grad_out, const float* const*
     a.B = B; a.N = N; a.Q = Q; a.P = P; a.C = C;
     const long long nq = (long long)B * Q;
     const unsigned grid = (unsigned)((nq + kMsmvWarps - 1) / kMsmvWarps);
-    if (backward)
+    if (backward) {
         msmv_bwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
-    else
-        msmv_fwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
+    } else {
+        constexpr int PB = (L <= 4) ? 16 : 12;
+        bool fits32 = true;   // the persistent kernel indexes whole levels (all batch elements) with 32-bit float4 offsets
+        for (int l = 0; l < L; ++l)
+            if ((long long)B * N * hw[2 * l] * hw[2 * l + 1] * 16 >= (1LL << 31)) fits32 = false;
+        const int mode = msmv_fwd_mode();
+        if (mode != 0 && P <= PB && fits32) {
+            const unsigned pgrid = grid < 148u * 2u ? grid : 148u * 2u;   // persistent: 2 CTAs per SM
+            msmv_fwd_c64_pf_kernel<L><<<pgrid, kMsmvWarps * 32, 0, st>>>(a, mode < 0 ? 0 : (mode > L ? L : mode));
+        } else {
+            msmv_fwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
+        }
+    }
     return (int)cudaGetLastError();
 }
 
