@@ -179,6 +179,23 @@ int racf_to_sampling_layout(const float* in, float* out, int batch, int num_fram
                             int num_groups, int channels, int height, int width, racf_stream_t stream);
 
 /*
+ * "next" row: BEVPoolv2, the reference's other in-tree native op
+ * (models/csrc/bev_pool_v2/src/bev_pool.cpp:30-104 -> bev_pool_cuda.cu:125-140). All pointers are device pointers.
+ *   depth [b,n,d,h,w] fp32, feat [b,n,h,w,c] fp32, ranks_* int32 [n_points], interval_* int32 [n_intervals].
+ * forward : out[ranks_bev[s], :] = sum over the interval of feat[ranks_feat[i], :] * depth[ranks_depth[i]];
+ *           cells without an interval are not touched (the caller zero-fills `out`, bev_pool.py:30).
+ * backward: intervals are runs of equal ranks_feat (bev_pool.py:50-60); depth_grad / feat_grad entries that belong
+ *           to no point are not touched (the caller zero-fills them, bev_pool.py:70-71).
+ */
+int racf_bev_pool_v2_forward(const float* depth, const float* feat, const int* ranks_depth, const int* ranks_feat,
+                             const int* ranks_bev, const int* interval_starts, const int* interval_lengths,
+                             int n_intervals, int channels, float* out, racf_stream_t stream);
+int racf_bev_pool_v2_backward(const float* out_grad, const float* depth, const float* feat, const int* ranks_depth,
+                              const int* ranks_feat, const int* ranks_bev, const int* interval_starts,
+                              const int* interval_lengths, int n_intervals, int channels,
+                              float* depth_grad, float* feat_grad, racf_stream_t stream);
+
+/*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
  * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
  * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.

@@ -103,3 +103,35 @@ def msda_backward(value, spatial_shapes, level_start_index, loc, aw, grad_out):
                                            D, L, Q, P, _p(gv), _p(gl), _p(ga))
     assert rc == 0, rc
     return gv, gl, ga
+
+
+def _i32(t):
+    return t.detach().to("cpu", torch.int32).contiguous()
+
+
+def bev_pool_v2_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, bev_feat_shape, interval_starts,
+                        interval_lengths):
+    """-> out [B,Z,Y,X,C] (zero where no point falls); reference order of summation."""
+    depth, feat = _f32(depth), _f32(feat)
+    rd, rf, rb, st, ln = (_i32(t) for t in (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths))
+    out = torch.zeros(tuple(bev_feat_shape))
+    lib = _load()
+    lib.racf_oracle_bev_pool_v2_forward.restype = ctypes.c_int
+    rc = lib.racf_oracle_bev_pool_v2_forward(_p(depth), _p(feat), _p(rd), _p(rf), _p(rb), _p(st), _p(ln), st.numel(),
+                                             feat.shape[-1], _p(out))
+    assert rc == 0
+    return out
+
+
+def bev_pool_v2_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts_bp,
+                         interval_lengths_bp):
+    """Intervals must be runs of equal ranks_feat (see racformer_b200.bev_pool.backward_intervals)."""
+    out_grad, depth, feat = _f32(out_grad), _f32(depth), _f32(feat)
+    rd, rf, rb, st, ln = (_i32(t) for t in (ranks_depth, ranks_feat, ranks_bev, interval_starts_bp, interval_lengths_bp))
+    dg, fg = torch.zeros_like(depth), torch.zeros_like(feat)
+    lib = _load()
+    lib.racf_oracle_bev_pool_v2_backward.restype = ctypes.c_int
+    rc = lib.racf_oracle_bev_pool_v2_backward(_p(out_grad), _p(depth), _p(feat), _p(rd), _p(rf), _p(rb), _p(st), _p(ln),
+                                              st.numel(), feat.shape[-1], _p(dg), _p(fg))
+    assert rc == 0
+    return dg, fg

@@ -34,6 +34,8 @@ SIGNATURES = {
     "racf_bev_points_forward": (_i, [_c_float_p] * 6 + [ctypes.POINTER(ctypes.c_double), ctypes.c_float] + [_i] * 6
                                 + [_c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_to_sampling_layout": (_i, [_c_float_p, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
+    "racf_bev_pool_v2_forward": (_i, [_c_float_p] * 7 + [_i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_bev_pool_v2_backward": (_i, [_c_float_p] * 8 + [_i, _i, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
 }

@@ -84,14 +84,29 @@ def test_msmv_golden_fixture(case):
     (3, 64, 5, -0.1, 1.1),      # level count without a fast kernel -> generic path
     (4, 32, 6, -0.1, 1.1),      # generic path (C != 64)
     (4, 64, 12, -5.0, -2.0),    # nothing valid at all: zeros everywhere
+    (4, 64, 128, -0.1, 1.1),    # maximum point count (msmv_sampling.cpp:159), several staged batches per query
+    (4, 64, 16, -0.1, 1.1),     # exactly one staged batch incl. the run-ahead pad point
+    (4, 64, 20, -0.1, 1.1),     # more than one batch -> non-persistent kernel
+    (5, 64, 12, -0.1, 1.1),     # c23456 with the RaCFormer point count (12-point batches)
+    (1, 64, 3, -0.1, 1.1),      # single level (generic path)
+    (8, 4, 2, -0.1, 1.1),       # maximum level count, tiny channel count
+    (4, 1, 1, 0.0, 1.0),        # degenerate C = 1, P = 1
 ])
 def test_msmv_seeded_vs_oracle(levels, C, P, lo, hi):
-    shapes = [(16, 44), (8, 22), (4, 11), (2, 6), (1, 3)][:levels]
+    shapes = [(16, 44), (8, 22), (4, 11), (2, 6), (1, 3), (3, 2), (2, 2), (1, 1)][:levels]
     feats, loc, w, g = make_msmv_inputs(11 + levels + P, Bp=3, N=6, C=C, Q=37, P=P, shapes=shapes, lo=lo, hi=hi)
     out, grads = _check_msmv_against_oracle(feats, loc, w, g, f"L{levels} C{C} P{P} [{lo},{hi}]")
     if hi < 0:
         assert float(out.abs().max()) == 0.0
         assert all(float(t.abs().max()) == 0.0 for t in grads)
+
+
+@pytest.mark.parametrize("Bp,N,Q", [(1, 2, 1), (1, 2, 9), (7, 2, 1), (2, 6, 257)])
+def test_msmv_small_and_ragged_batches(Bp, N, Q):
+    """Single query / single batch element / fewer queries than a CTA holds / a query count that is not a multiple of it."""
+    feats, loc, w, g = make_msmv_inputs(Bp * 31 + Q, Bp=Bp, N=N, C=64, Q=Q, P=12, shapes=[(8, 22), (4, 11), (2, 6), (1, 3)],
+                                        lo=-0.1, hi=1.1)
+    _check_msmv_against_oracle(feats, loc, w, g, f"Bp{Bp} N{N} Q{Q}")
 
 
 def test_msmv_special_coordinates_and_views():
@@ -250,6 +265,9 @@ def test_msda_golden_fixture(case):
     ([(12, 7)], 2, 64, 40, -0.1, 1.1),                 # more than 32 taps per (b,q,m): two staging rounds
     ([(16, 20), (8, 10)], 8, 32, 4, -0.1, 1.1),        # generic path
     ([(9, 9)], 3, 16, 5, -2.0, -1.0),                  # nothing valid
+    ([(5, 3)], 1, 64, 1, -0.1, 1.1),                   # one head, one point
+    ([(7, 9), (4, 4)], 3, 64, 16, -0.1, 1.1),          # exactly 32 taps per row
+    ([(7, 9), (4, 4)], 3, 7, 3, -0.1, 1.1),            # odd head_dim (generic path)
 ])
 def test_msda_seeded_vs_oracle(shapes, M, D, P, lo, hi):
     value, sp, lsi, loc, aw, g = make_msda_inputs(23 + P, B=4, M=M, D=D, Q=33, P=P, shapes=shapes, lo=lo, hi=hi)
