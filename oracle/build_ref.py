@@ -37,6 +37,36 @@ def build(verbose=False):
     return SO if os.path.exists(SO) else None
 
 
+POOL_SO = os.path.join(OUT, "bev_pool_v2_ext.so")
+POOL_SRC = os.path.join(REF, "models", "csrc", "bev_pool_v2", "src")
+
+
+def build_bev_pool(verbose=False):
+    """The reference's BEVPoolv2 extension (models/csrc/bev_pool_v2/src/{bev_pool.cpp,bev_pool_cuda.cu}), unmodified."""
+    if os.path.exists(POOL_SO):
+        return POOL_SO
+    if not os.path.isdir(POOL_SRC):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "4")
+    from torch.utils import cpp_extension
+    cpp_extension.load(name="bev_pool_v2_ext",
+                       sources=[os.path.join(POOL_SRC, f) for f in ("bev_pool.cpp", "bev_pool_cuda.cu")],
+                       build_directory=OUT, is_python_module=False, verbose=verbose)
+    return POOL_SO if os.path.exists(POOL_SO) else None
+
+
+def load_prebuilt_bev_pool():
+    if not os.path.exists(POOL_SO):
+        return None
+    import torch  # noqa: F401
+    spec = importlib.util.spec_from_file_location("bev_pool_v2_ext", POOL_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_prebuilt():
     """Import oracle/_ref/_msmv_sampling_cuda.so if it exists (needs torch + a CUDA device to be useful)."""
     if not os.path.exists(SO):
@@ -50,3 +80,4 @@ def load_prebuilt():
 
 if __name__ == "__main__":
     print(build(verbose="--verbose" in sys.argv))
+    print(build_bev_pool(verbose="--verbose" in sys.argv))

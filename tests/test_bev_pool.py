@@ -134,3 +134,30 @@ def test_cuda_rejects_bad_inputs():
         bev_pool.bev_pool_v2_forward(depth, feat, out, rd.long(), rf, rb, lengths, starts)
     with pytest.raises(RuntimeError, match="float32 CUDA"):
         bev_pool.bev_pool_v2_forward(depth.cpu(), feat, out, rd, rf, rb, lengths, starts)
+
+
+@pytest.mark.gpu
+def test_cuda_vs_reference_extension():
+    """The reference's own bev_pool_v2_ext (oracle/_ref, built by oracle/build_ref.py) on LSS-shaped inputs."""
+    from oracle import build_ref
+    ext = build_ref.load_prebuilt_bev_pool()
+    if ext is None:
+        pytest.skip("oracle/_ref/bev_pool_v2_ext.so not built")
+    from racformer_b200 import bev_pool
+    case = make_lss_case(11, 1, 6, 96, 16, 44, 256, (128, 128), device="cuda")
+    out = torch.zeros(case["shape"], device="cuda")
+    ref = torch.zeros(case["shape"], device="cuda")
+    args = (case["ranks_depth"], case["ranks_feat"], case["ranks_bev"], case["lengths"], case["starts"])
+    bev_pool.bev_pool_v2_forward(case["depth"], case["feat"], out, *args)
+    ext.bev_pool_v2_forward(case["depth"], case["feat"], ref, *args)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), "forward must be bit-identical to the reference kernel"
+    og = torch.randn(case["shape"], device="cuda")
+    rd, rf, rb, st, ln = (t.cuda() for t in _bp_intervals(case["ranks_depth"].cpu(), case["ranks_feat"].cpu(), case["ranks_bev"].cpu()))
+    dg, fg = torch.zeros_like(case["depth"]), torch.zeros_like(case["feat"])
+    rdg, rfg = torch.zeros_like(case["depth"]), torch.zeros_like(case["feat"])
+    bev_pool.bev_pool_v2_backward(og, dg, fg, case["depth"], case["feat"], rd, rf, rb, ln, st)
+    ext.bev_pool_v2_backward(og, rdg, rfg, case["depth"], case["feat"], rd, rf, rb, ln, st)
+    torch.cuda.synchronize()
+    assert torch.equal(fg, rfg)
+    assert float((dg - rdg).abs().max()) <= 1e-5 * float(rdg.abs().max())
