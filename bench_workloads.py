@@ -247,7 +247,7 @@ class DecoderWorkload:
                                     "reference's PyTorch CPU path (grid_sample ops, reference schedule without hoisting), "
                                     "full f8 shapes, all host threads")
 
-    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True):
+    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True, num_cams=6):
         from racformer_b200.decoder import RaCFormerTransformer, SamplingOps
         self.use_graph = graph and torch.device(device).type == "cuda"
         self._graphed = None
@@ -257,7 +257,8 @@ class DecoderWorkload:
         self.on_gpu = self.device.type == "cuda"
         self.cfg = dict(embed_dims=256, num_frames=8, num_points=4, num_points_bev=4, num_layers=num_layers, num_levels=4,
                         num_classes=10, code_size=10, img_depth_num=3, bev_depth_num=5, pc_range=PC_RANGE, num_ray=150,
-                        d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=6)
+                        d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=num_cams)
+        self.num_cams = num_cams
         self.timers = {}
         self._time_kernels = False
         if self.on_gpu:
@@ -273,7 +274,7 @@ class DecoderWorkload:
         self.model = RaCFormerTransformer(**self.cfg, ops=ops, hoist_invariants=hoist if self.on_gpu else False)
         self.model.init_weights()
         self.model.eval().to(self.device)
-        self.inp = make_decoder_inputs(seed=100 + seed, device=self.device)
+        self.inp = make_decoder_inputs(seed=100 + seed, device=self.device, num_cams=num_cams)
         # our kernels per step: per iteration 1 MSMV + 2 MSDA, and (inference) 1 + 2 fused point-generation kernels
         self.launches_per_step = 6 * num_layers
         self.h2d_bytes_per_step = 0
@@ -282,7 +283,7 @@ class DecoderWorkload:
 
     def config(self):
         return {"workload": self.name, "shapes": "racformer_r50_nuimg_704x256_f8", "batch_per_gpu": 1, "num_query": 900,
-                "frames": 8, "cams": 6, "fpn_levels": 4, "embed_dims": 256, "decoder_layers": self.layers,
+                "frames": 8, "cams": self.num_cams, "fpn_levels": 4, "embed_dims": 256, "decoder_layers": self.layers,
                 "msmv_points": 12, "msda_points": 20, "bev": [128, 128], "weights": "random init (seed 0)",
                 "hoist_invariants": self.hoist, "includes_channel_last_relayout": True, "cuda_graph": self.use_graph,
                 "conv_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
@@ -434,15 +435,15 @@ class DecoderTrainWorkload(DecoderWorkload):
     projection of the outputs (Hungarian assignment / losses are outside the path)."""
     metric = "decoder training samples/s (RaCFormer R50 704x256 f8 decoder fwd+bwd+allreduce+AdamW, batch 2/GPU)"
 
-    def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320):
+    def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320, num_cams=6):
         from racformer_b200.parallel import GradientAllReducer
         from racformer_b200.synthetic import make_decoder_inputs
-        super().__init__(device, seed=seed, name=name, graph=False)
+        super().__init__(device, seed=seed, name=name, graph=False, num_cams=num_cams)
         self.samples_per_step = batch
         self.batch, self.dn = batch, dn_queries
         self.model.train()
         q = 900 + dn_queries
-        self.inp = make_decoder_inputs(seed=100 + seed, batch=batch, num_query=900, device=self.device)
+        self.inp = make_decoder_inputs(seed=100 + seed, batch=batch, num_query=900, device=self.device, num_cams=num_cams)
         g = torch.Generator().manual_seed(7 + seed)
         dn_bbox = torch.rand(batch, dn_queries, 10, generator=g).to(self.device) * 0.8 + 0.1
         dn_bbox[..., 8:] = 0
@@ -512,6 +513,10 @@ class DecoderTrainWorkload(DecoderWorkload):
 def build(name, device, seed=0):
     if name == "decoder_train_f8":
         return DecoderTrainWorkload(device, seed=seed)
+    if name == "decoder_forward_f8_3cam":      # racformer_r50_nuimg_704x256_f8_3cam_3rad (config 5), forward
+        return DecoderWorkload(device, seed=seed, name=name, num_cams=3)
+    if name == "decoder_train_f8_3cam":        # config 5: decoder fwd+bwd with 3 cameras
+        return DecoderTrainWorkload(device, seed=seed, name=name, num_cams=3)
     if name == "decoder_forward_f8":
         return DecoderWorkload(device, seed=seed)
     if name == "decoder_forward_f8_nohoist":
