@@ -158,6 +158,12 @@ def _main():
         return run_reference_arm(args, rank)
 
     import torch.distributed as dist
+    try:   # make sure the in-tree library matches the sources (no-op when it is current; needs nvcc otherwise)
+        from racformer_b200 import build as _lib_build
+        if env_int("LOCAL_RANK", 0) == 0:
+            _lib_build.build()
+    except Exception as exc:  # the prebuilt .so travels with the snapshot; loading fails loudly below if it is absent
+        print(f"bench.py: library rebuild skipped ({exc})", file=sys.stderr)
     import bench_workloads as workloads
     from racformer_b200 import parallel
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the ops)"

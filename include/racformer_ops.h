@@ -203,6 +203,9 @@ int racf_bev_pool_v2_backward(const float* out_grad, const float* depth, const f
 int racf_bench_gather_ceiling(const float* buf, long long num_rows, long long total_rows, int ilp,
                               float* sink, racf_stream_t stream);
 
+/* Measurement aid: the same for the scatter -- red.global.add.v4.f32 on random 512-byte rows of buf. */
+int racf_bench_scatter_ceiling(float* buf, long long num_rows, long long total_rows, racf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

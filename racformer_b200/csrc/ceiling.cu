@@ -34,7 +34,28 @@ __global__ void __launch_bounds__(256) gather_ceiling_kernel(const float4* __res
     if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;   // keep the loads alive
 }
 
+// Same request shape for the scatter: every warp issues red.global.add.v4.f32 on random 512-byte rows.
+__global__ void __launch_bounds__(256) scatter_ceiling_kernel(float* __restrict__ buf, uint32_t num_rows, int rows_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (int i = 0; i < rows_per_warp; ++i) {
+        const uint32_t row = mix(warp * 9781u + (uint32_t)i * 2654435761u) % num_rows;
+        float* p = buf + ((size_t)row * 32 + lane) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(p), "f"(1.0f) : "memory");
+    }
+}
+
 }  // namespace racf
+
+extern "C" int racf_bench_scatter_ceiling(float* buf, long long num_rows, long long total_rows, racf_stream_t stream) {
+    if (!buf) return RACF_ERR_NULL_POINTER;
+    if (num_rows <= 0 || num_rows >= (1LL << 32) || total_rows <= 0) return RACF_ERR_BAD_SHAPE;
+    const int rows_per_warp = 64;
+    const long long warps = (total_rows + rows_per_warp - 1) / rows_per_warp;
+    racf::scatter_ceiling_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        buf, (uint32_t)num_rows, rows_per_warp);
+    return (int)cudaGetLastError();
+}
 
 // Reads total_rows x 512 B at random 512-byte rows of buf[0 : num_rows*512 B]. ilp in {1,2,4,8,16}.
 extern "C" int racf_bench_gather_ceiling(const float* buf, long long num_rows, long long total_rows, int ilp,

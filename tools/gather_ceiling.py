@@ -30,5 +30,25 @@ for mb in (32, 64, 134, 735, 2048):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
         res.append({"footprint_mb": mb, "ilp": ilp, "ms": ms, "gbs": total_rows * 512 / ms / 1e6})
+    # scatter: vector reductions on random rows; (a) warm = buffer resident / dirty in L2 where it fits,
+    # (b) after a memset of the buffer (what the backward pass sees: zero-fill, then read-modify-write)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    total_rows = int(1.4e9 // 512)
+    for mode in ("warm", "after_memset"):
+        for _ in range(2):
+            lib.racf_bench_scatter_ceiling(buf.data_ptr(), n_rows, total_rows, st)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            if mode == "after_memset":
+                buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.racf_bench_scatter_ceiling(buf.data_ptr(), n_rows, total_rows, st)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = sorted(ts)[len(ts) // 2]
+        res.append({"footprint_mb": mb, "scatter": mode, "ms": ms, "gbs": total_rows * 512 / ms / 1e6})
     del buf
 print(json.dumps(res, indent=1))
