@@ -9,8 +9,6 @@ reference's PyTorch (grid_sample) path, which racformer_b200/ itself must never 
                         layers in between left out.
   decoder_sampling_f8_train   same with backward (config 4 sampling work, B=2 per GPU, Q=1220).
 """
-import math
-
 import torch
 
 F8_SHAPES = [(64, 176), (32, 88), (16, 44), (8, 22)]

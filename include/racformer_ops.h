@@ -4,7 +4,8 @@
  * The drop-in boundary for RaCFormer's sampling hot path. Every entry point
  * takes plain device pointers, integer sizes and a CUDA stream; the library
  * never allocates or frees device memory, never synchronises, keeps no
- * global state and returns an int status instead of printing.
+ * mutable global state (one tuning knob, RACF_MSMV_FWD_MODE, is read from the
+ * environment once) and returns an int status instead of printing.
  *
  * Reference interfaces replaced (paths relative to the RaCFormer tree):
  *   racf_msmv_forward   <- ms_deformable_im2col_cuda_c{45,2345,23456}

@@ -395,3 +395,26 @@ def test_no_out_of_bounds_access_guard_bands():
     msda.ext_module.ms_deform_attn_backward(vg, *args, mg.to(DEV), gv, gl2, ga2, im2col_step=64)
     torch.cuda.synchronize()
     assert bool((gvguard[:pad] == 12345.0).all()) and bool((gvguard[-pad:] == 12345.0).all())
+
+
+def test_ops_on_a_non_current_device():
+    """Tensors on cuda:1 while cuda:0 is current: the wrappers must launch under a device guard on that device's stream."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    wrapper, msda = _ops()
+    co = _oracle()
+    assert torch.cuda.current_device() == 0
+    feats, loc, w, g = make_msmv_inputs(2, Bp=2, N=3, C=64, Q=9, P=12, shapes=[(8, 22), (4, 11), (2, 6), (1, 3)], lo=-0.1, hi=1.1)
+    d1 = "cuda:1"
+    f1 = [f.to(d1).requires_grad_() for f in feats]
+    loc1, w1 = loc.to(d1).requires_grad_(), w.to(d1).requires_grad_()
+    out = wrapper.msmv_sampling(f1, loc1, w1)
+    out.backward(g.to(d1))
+    assert out.device == torch.device(d1) and torch.cuda.current_device() == 0
+    assert_close(out, co.msmv_forward(feats, loc, w), FWD_RTOL, FWD_ATOL_EXACT * max(_scale(f) for f in feats), "cuda:1 forward")
+    rgf, rgl, rgw = co.msmv_backward(g, feats, loc, w)
+    assert_close(loc1.grad, rgl, BWD_RTOL, BWD_ATOL * _scale(rgl), "cuda:1 grad_loc")
+    assert_close(f1[0].grad, rgf[0], BWD_RTOL, BWD_ATOL * _scale(rgf[0]), "cuda:1 grad_feat0")
+    value, sp, lsi, mloc, aw, mg = make_msda_inputs(4, B=2, M=4, D=64, Q=9, P=20, shapes=[(16, 16)])
+    mo = msda.MultiScaleDeformableAttnFunction_fp32.apply(value.to(d1), sp.to(d1), lsi.to(d1), mloc.to(d1), aw.to(d1), 64)
+    assert_close(mo, co.msda_forward(value, sp, lsi, mloc, aw), FWD_RTOL, FWD_ATOL_EXACT * _scale(value), "cuda:1 msda forward")
