@@ -245,7 +245,8 @@ class DecoderWorkload:
                                     "reference's PyTorch CPU path (grid_sample ops, reference schedule without hoisting), "
                                     "full f8 shapes, all host threads")
 
-    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True, num_cams=6):
+    def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True, num_cams=6,
+                 mixing_precision="fp32"):
         from racformer_b200.decoder import RaCFormerTransformer, SamplingOps
         self.use_graph = graph and torch.device(device).type == "cuda"
         self._graphed = None
@@ -272,6 +273,8 @@ class DecoderWorkload:
         self.model = RaCFormerTransformer(**self.cfg, ops=ops, hoist_invariants=hoist if self.on_gpu else False)
         self.model.init_weights()
         self.model.eval().to(self.device)
+        self.mixing_precision = mixing_precision
+        self.model.set_mixing_precision(mixing_precision)
         self.inp = make_decoder_inputs(seed=100 + seed, device=self.device, num_cams=num_cams)
         # our kernels per step: per iteration 1 MSMV + 2 MSDA, and (inference) 1 + 2 fused point-generation kernels
         self.launches_per_step = 6 * num_layers
@@ -284,6 +287,7 @@ class DecoderWorkload:
                 "frames": 8, "cams": self.num_cams, "fpn_levels": 4, "embed_dims": 256, "decoder_layers": self.layers,
                 "msmv_points": 12, "msda_points": 20, "bev": [128, 128], "weights": "random init (seed 0)",
                 "hoist_invariants": self.hoist, "includes_channel_last_relayout": True, "cuda_graph": self.use_graph,
+                "mixing_gemm_precision": self.mixing_precision,
                 "conv_tf32": bool(torch.backends.cudnn.allow_tf32), "matmul_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
                 "sharding": "one sample per GPU, no data-path collective",
                 "l2_policy": "inputs larger than L2 (735 MB pyramid + 2x134 MB BEV maps vs 126 MB L2); no flush"}
@@ -519,6 +523,8 @@ def build(name, device, seed=0):
         return DecoderWorkload(device, seed=seed)
     if name == "decoder_forward_f8_nohoist":
         return DecoderWorkload(device, seed=seed, name=name, hoist=False, graph=False)
+    if name == "decoder_forward_f8_tf32x3":    # OPT-IN variant: AdaptiveMixing GEMMs as operand-split TF32 (not fp32 SGEMM)
+        return DecoderWorkload(device, seed=seed, name=name, mixing_precision="tf32x3")
     if name == "decoder_forward_f8_eager":
         return DecoderWorkload(device, seed=seed, name=name, graph=False)
     if name == "decoder_sampling_f8":

@@ -513,6 +513,63 @@ class BEVSampling(nn.Module):
         return _maybe_checkpoint(self, fn, query_ray, query_feat, bev_feats)
 
 
+def _tf32_round(x):
+    """Round-to-nearest-even to TF32's 10 explicit mantissa bits, kept in fp32 storage."""
+    i = x.view(torch.int32)
+    return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+
+
+def _tf32_split(x):
+    """x ~= hi + lo with hi, lo exactly representable in TF32 (|x - hi - lo| <= 2^-22 |x|)."""
+    hi = _tf32_round(x)
+    return hi, _tf32_round(x - hi)
+
+
+class _SplitTF32Linear:
+    """OPT-IN (inference): y = x @ W^T + b on TF32 tensor cores at near-fp32 accuracy.
+
+    Operand splitting: x = xh + xl, W = Wh + Wl, y ~= xh Wh^T + xh Wl^T + xl Wh^T, evaluated as ONE TF32 GEMM over the
+    K-concatenated operands [xh, xh, xl] x [Wh, Wl, Wh]; every product of two TF32 numbers is exact in fp32. Long
+    reductions are cut into `chunk`-sized pieces that are summed in fp32 outside the tensor cores, because their
+    internal accumulation truncates (K = 32768 in one go gave 3e-4 error, profiles/r01_tf32x3_experiment.json).
+    Measured on B200: 2.6e-6 mean relative error vs an fp64 product (fp32 SGEMM: 2.5e-7; plain TF32: 2.9e-4) at
+    4.5x the SGEMM speed. Not the default: the reference computes these layers with fp32 SGEMM.
+    """
+
+    def __init__(self, linear, chunk=512):
+        self.linear, self.chunk, self._key, self._w3 = linear, chunk, None, None
+
+    def _weights(self):
+        lin = self.linear
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+        if self._key != key:
+            w = torch.cat([lin.weight.detach(), lin.bias.detach()[:, None]], dim=1)          # bias as one more K column
+            k = w.shape[1]
+            nchunk = (k + self.chunk - 1) // self.chunk
+            kpad = ((k + nchunk * 4 - 1) // (nchunk * 4)) * nchunk * 4
+            w = F.pad(w, (0, kpad - k))
+            wh, wl = _tf32_split(w.reshape(w.shape[0], nchunk, kpad // nchunk))
+            self._w3 = torch.cat([wh, wl, wh], dim=2).permute(1, 2, 0).contiguous()          # [chunks, 3*kc, out]
+            self._key, self._kpad, self._nchunk = key, kpad, nchunk
+        return self._w3
+
+    def __call__(self, x):
+        w3 = self._weights()
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = F.pad(torch.cat([x2, torch.ones_like(x2[:, :1])], dim=1), (0, self._kpad - x2.shape[1] - 1))
+        xh, xl = _tf32_split(x2.reshape(x2.shape[0], self._nchunk, -1))
+        x3 = torch.cat([xh, xh, xl], dim=2).permute(1, 0, 2)                                 # [chunks, rows, 3*kc]
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            y = torch.bmm(x3, w3)                                                            # [chunks, rows, out]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        y = y.sum(0) if self._nchunk > 1 else y[0]
+        return y.reshape(*lead, -1)
+
+
 class AdaptiveMixing(nn.Module):
     """racformer_transformer.py:549-616 (AdaMixer): query-generated channel and point mixing of the sampled features."""
 
@@ -526,6 +583,8 @@ class AdaptiveMixing(nn.Module):
         self.activation_checkpoint = True
         self.fold_bias = True
         self._folded = None
+        self.gemm_precision = "fp32"        # "tf32x3": opt-in operand-split TF32 tensor-core GEMMs (inference)
+        self._split_gen = self._split_out = None
         self.parameter_generator = nn.Linear(in_dim, n_groups * (self.m_parameters + self.s_parameters))
         self.out_proj = nn.Linear(self.eff_out_dim * self.out_points * n_groups, in_dim)
 
@@ -540,6 +599,10 @@ class AdaptiveMixing(nn.Module):
         lin = self.parameter_generator
         if torch.is_grad_enabled() or not query.is_cuda or lin.bias is None or not self.fold_bias:
             return lin(query)
+        if self.gemm_precision == "tf32x3":
+            if self._split_gen is None:
+                self._split_gen = _SplitTF32Linear(lin)
+            return self._split_gen(query)
         key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
         if self._folded is None or self._folded[0] != key:
             self._folded = (key, torch.cat([lin.weight.detach(), lin.bias.detach()[:, None]], dim=1).contiguous())
@@ -556,7 +619,12 @@ class AdaptiveMixing(nn.Module):
         out = F.relu(F.layer_norm(out, [out.size(-2), out.size(-1)]))
         out = torch.matmul(s, out)
         out = F.relu(F.layer_norm(out, [out.size(-2), out.size(-1)]))
-        return query + self.out_proj(out.reshape(B, Q, -1))
+        out = out.reshape(B, Q, -1)
+        if self.gemm_precision == "tf32x3" and not torch.is_grad_enabled() and out.is_cuda:
+            if self._split_out is None:
+                self._split_out = _SplitTF32Linear(self.out_proj)
+            return query + self._split_out(out)
+        return query + self.out_proj(out)
 
     def forward(self, x, query):
         return _maybe_checkpoint(self, self.inner_forward, x, query)
@@ -723,6 +791,13 @@ class RaCFormerTransformer(nn.Module):
         for m in self.modules():
             if isinstance(m, (RaCFormerSampling, BEVSampling)):
                 m.fused_points = enabled
+
+    def set_mixing_precision(self, precision):
+        """"fp32" (default, SGEMM like the reference) or "tf32x3" (opt-in, see _SplitTF32Linear)."""
+        assert precision in ("fp32", "tf32x3")
+        for m in self.modules():
+            if isinstance(m, AdaptiveMixing):
+                m.gemm_precision = precision
 
     def set_activation_checkpoint(self, enabled):
         for m in self.modules():

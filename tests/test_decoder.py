@@ -207,3 +207,25 @@ def test_pipelined_serving_loop_returns_each_samples_result():
         with torch.no_grad():
             e_cls, e_box = model(s["query_bbox"], s["query_feat"], s["mlvl_feats"], s["lss_bev"], s["radar_bev"], None, s["img_metas"])
         assert torch.equal(cls, e_cls.cpu()) and torch.equal(box, e_box.cpu())
+
+
+@pytest.mark.gpu
+def test_optin_split_tf32_mixing_stays_at_fp32_noise_level():
+    """Opt-in `set_mixing_precision("tf32x3")`: the decoder output moves by no more than the fp32 reordering noise that
+    already separates two fp32 implementations (DEC_RTOL/DEC_ATOL of the CPU comparison with the reference)."""
+    d, feats, metas = _fixture_inputs("cuda")
+    args = (d["query_bbox"].cuda(), d["query_feat"].cuda(), feats, d["lss_bev"].cuda(), d["radar_bev"].cuda(), None, metas)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        model = _my_model().cuda()
+        with torch.no_grad():
+            ref = model(*args)
+            model.set_mixing_precision("tf32x3")
+            got = model(*args)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert not torch.equal(ref[0], got[0])            # the other code path really ran
+    _close(got[0], ref[0], "cls tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
+    _close(got[1], ref[1], "box tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
+    assert torch.backends.cuda.matmul.allow_tf32 is False   # the global flag is restored
