@@ -189,13 +189,16 @@ def _main():
         wl.step()
     stop.record()
     barrier()
-    # per-kernel CUDA-event timing (roofline): an eager pass of the same steps with events around our launches
+    total_ms = parallel.max_over_ranks(start.elapsed_time(stop), dev)   # device time, max over ranks
+    value = world * args.steps * wl.samples_per_step / (total_ms * 1e-3)
+    # per-kernel CUDA-event timing for the roofline: from event nodes inside the captured graph (they now hold the last
+    # step of the timed region); workloads that do not run as a graph time their launches in an eager pass instead
+    roof = wl.roofline(hbm_peak, peak_src) if getattr(wl, "graph_events", None) else None
     for _ in range(min(args.steps, 20)):
         wl.step(time_kernels=True)
     barrier()
-    total_ms = parallel.max_over_ranks(start.elapsed_time(stop), dev)   # device time, max over ranks
-    value = world * args.steps * wl.samples_per_step / (total_ms * 1e-3)
-    roof = wl.roofline(hbm_peak, peak_src)
+    roof = roof or wl.roofline(hbm_peak, peak_src)
+    kernels = wl.kernel_report(hbm_peak)
     launches = wl.launches_per_step * args.steps
 
     # ---- end to end: pinned host inputs -> H2D -> ops -> D2H result, every step --------------------------------
@@ -244,7 +247,7 @@ def _main():
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu_baseline,
-            "kernels": wl.kernel_report(hbm_peak),
+            "kernels": kernels,
         }
     else:
         line = None

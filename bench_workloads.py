@@ -259,6 +259,8 @@ class DecoderWorkload:
                         d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=num_cams)
         self.num_cams = num_cams
         self.timers = {}
+        self.graph_events = {}
+        self._collect_graph_events = False
         self._time_kernels = False
         if self.on_gpu:
             base = SamplingOps()
@@ -293,6 +295,18 @@ class DecoderWorkload:
                 "l2_policy": "inputs larger than L2 (735 MB pyramid + 2x134 MB BEV maps vs 126 MB L2); no flush"}
 
     def _timed(self, key, fn, args):
+        if self._collect_graph_events and key == "msmv_fwd" and torch.cuda.is_current_stream_capturing():
+            # external events become event-record nodes of the captured graph: every replay re-records them, so after
+            # the timed region they hold the kernel times of its last step
+            a = torch.cuda.Event(enable_timing=True, external=True)
+            b = torch.cuda.Event(enable_timing=True, external=True)
+            a.record()
+            out = fn(*args)
+            b.record()
+            self.graph_events.setdefault(key, []).append((a, b))
+            if self._captured is None:
+                self._captured = (args[1].detach().clone(), [tuple(f.shape[2:4]) for f in args[0]], args[0][0].shape[1])
+            return out
         if not self._time_kernels:
             return fn(*args)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,7 +330,9 @@ class DecoderWorkload:
         if self.use_graph and not time_kernels:
             if self._graphed is None:
                 from racformer_b200.graphs import GraphedDecoderForward
+                self._collect_graph_events = True
                 self._graphed = GraphedDecoderForward(self.model, self.inp)   # its static buffers = the resident inputs
+                self._collect_graph_events = False
             return self._graphed()
         self._time_kernels = time_kernels
         out = self._forward(self.inp)
@@ -336,7 +352,19 @@ class DecoderWorkload:
             algo["msmv_fwd"] = msmv_bytes(mask, C=64, L=len(hw), feat_bytes=feat_bytes)[0]
             rep["msmv_valid_corner_fraction"] = float(((mask.int() >> 1) & 1).float().mean() + ((mask.int() >> 2) & 1).float().mean()
                                                       + ((mask.int() >> 3) & 1).float().mean() + ((mask.int() >> 4) & 1).float().mean()) / 4
-        for key, pairs in self.timers.items():
+        sources = dict(self.timers)
+        timing = "CUDA events around each launch in an eager pass after the timed region"
+        if self.graph_events:
+            try:   # MSMV kernel times of the LAST replay of the timed region, from event nodes inside the captured graph
+                for pairs in self.graph_events.values():
+                    pairs[0][0].elapsed_time(pairs[0][1])
+                sources.update(self.graph_events)
+                timing = ("msmv_fwd: event-record nodes inside the CUDA graph (the 6 launches of the last step of the "
+                          "timed region); other kernels: eager pass after the timed region")
+            except Exception:
+                pass
+        rep["kernel_timing"] = timing
+        for key, pairs in sources.items():
             ms = [a.elapsed_time(b) for a, b in pairs]
             avg = sum(ms) / len(ms)
             rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / max(1, len(ms) // (
@@ -361,8 +389,7 @@ class DecoderWorkload:
                 "achieved": k.get("gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": k.get("frac_of_hbm_peak"),
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_us": k["avg_us"],
                 "algorithmic_bytes_per_launch": k.get("algorithmic_bytes"),
-                "timing": "CUDA events around each launch in an eager pass of the same workload right after the timed "
-                          "region (events cannot bracket kernels inside a graph replay)",
+                "timing": rep.get("kernel_timing"),
                 "note": "algorithmic bytes count every valid corner read of every tap (SURVEY 8d) of the decoder's actual "
                         "sampling locations (first iteration); repeated pixels and coarse levels hit the 126 MB L2 so "
                         "achieved may exceed the HBM copy peak; `traffic` = DRAM bytes/launch from ncu at the op-benchmark "
