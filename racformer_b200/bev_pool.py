@@ -57,9 +57,11 @@ def bev_pool_v2_backward(out_grad, depth_grad, feat_grad, depth, feat, ranks_dep
     _lib.check(rc, "racf_bev_pool_v2_backward")
 
 
-def backward_intervals(ranks_depth, ranks_feat, ranks_bev):
-    """bev_pool.py:50-60: re-sort the points by ranks_feat and cut them into runs of equal ranks_feat."""
-    order = ranks_feat.argsort()
+def backward_intervals(ranks_depth, ranks_feat, ranks_bev, stable=False):
+    """bev_pool.py:50-60: re-sort the points by ranks_feat and cut them into runs of equal ranks_feat.
+    `stable=True` fixes the order inside a run (the reference's argsort is not stable, so its fp32 sums are only
+    reproducible up to reordering)."""
+    order = torch.argsort(ranks_feat.long(), stable=True) if stable else ranks_feat.argsort()
     ranks_feat, ranks_depth, ranks_bev = ranks_feat[order], ranks_depth[order], ranks_bev[order]
     kept = torch.ones(ranks_bev.shape[0], device=ranks_bev.device, dtype=torch.bool)
     kept[1:] = ranks_feat[1:] != ranks_feat[:-1]

@@ -73,3 +73,31 @@ def fill_parameters_by_name(module, seed=0):
         if "sampling_offset.bias" in name:      # spread the sample points like the reference's init does
             val = torch.rand(p.shape, generator=g) - 0.5
         p.copy_(val.to(p.dtype))
+
+
+def make_lss_pool_case(seed, B, N, D, H, W, C, bev=(128, 128), device="cpu"):
+    """Random frustum-to-BEV assignment shaped like voxel_pooling_prepare_v2 (models/necks/view_transformer_racformer.py:
+    202-260) for BEVPoolv2: every (b,n,d,h,w) point gets a random BEV cell or falls outside the grid (~23 %); kept points
+    are sorted by cell and cut into intervals."""
+    g = torch.Generator().manual_seed(seed)
+    n_pts = B * N * D * H * W
+    depth = torch.rand(B, N, D, H, W, generator=g)
+    feat = torch.randn(B, N, H, W, C, generator=g)
+    ranks_depth = torch.arange(n_pts, dtype=torch.int32)
+    ranks_feat = torch.arange(n_pts // D, dtype=torch.int32).reshape(B, N, 1, H, W).expand(B, N, D, H, W).flatten()
+    cell = torch.randint(0, int(bev[0] * bev[1] * 1.3), (n_pts,), generator=g)
+    batch = torch.arange(B).reshape(B, 1).expand(B, n_pts // B).flatten()
+    kept = cell < bev[0] * bev[1]
+    ranks_bev = (batch * bev[0] * bev[1] + cell)[kept].int()
+    ranks_depth, ranks_feat = ranks_depth[kept], ranks_feat[kept].contiguous()
+    order = torch.argsort(ranks_bev.long(), stable=True)
+    ranks_bev, ranks_depth, ranks_feat = ranks_bev[order], ranks_depth[order], ranks_feat[order]
+    keep = torch.ones(ranks_bev.shape[0], dtype=torch.bool)
+    keep[1:] = ranks_bev[1:] != ranks_bev[:-1]
+    starts = torch.where(keep)[0].int()
+    lengths = torch.zeros_like(starts)
+    lengths[:-1] = starts[1:] - starts[:-1]
+    lengths[-1] = ranks_bev.shape[0] - starts[-1]
+    mv = lambda t: t.to(device)
+    return dict(depth=mv(depth), feat=mv(feat), ranks_depth=mv(ranks_depth), ranks_feat=mv(ranks_feat),
+                ranks_bev=mv(ranks_bev), starts=mv(starts), lengths=mv(lengths), shape=(B, 1, bev[1], bev[0], C))

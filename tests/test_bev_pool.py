@@ -44,32 +44,7 @@ def test_oracle_reproduces_reference_known_answer():
     assert torch.allclose(dg, KAT_GRAD_DEPTH) and torch.allclose(fg, KAT_GRAD_FEAT)
 
 
-def make_lss_case(seed, B, N, D, H, W, C, bev=(128, 128), device="cpu"):
-    """Random frustum-to-BEV assignment shaped like voxel_pooling_prepare_v2 (view_transformer_racformer.py:202-260):
-    every (b,n,d,h,w) point gets a random BEV cell or falls outside; kept points are sorted by cell."""
-    g = torch.Generator().manual_seed(seed)
-    n_pts = B * N * D * H * W
-    depth = torch.rand(B, N, D, H, W, generator=g)
-    feat = torch.randn(B, N, H, W, C, generator=g)
-    ranks_depth = torch.arange(n_pts, dtype=torch.int32)
-    ranks_feat = torch.arange(n_pts // D, dtype=torch.int32).reshape(B, N, 1, H, W).expand(B, N, D, H, W).flatten()
-    cell = torch.randint(0, int(bev[0] * bev[1] * 1.3), (n_pts,), generator=g)      # ~23 % outside the grid
-    batch = torch.arange(B).reshape(B, 1).expand(B, n_pts // B).flatten()
-    kept = cell < bev[0] * bev[1]
-    ranks_bev = (batch * bev[0] * bev[1] + cell)[kept].int()
-    ranks_depth, ranks_feat = ranks_depth[kept], ranks_feat[kept].contiguous()
-    order = torch.argsort(ranks_bev.long(), stable=True)
-    ranks_bev, ranks_depth, ranks_feat = ranks_bev[order], ranks_depth[order], ranks_feat[order]
-    keep = torch.ones(ranks_bev.shape[0], dtype=torch.bool)
-    keep[1:] = ranks_bev[1:] != ranks_bev[:-1]
-    starts = torch.where(keep)[0].int()
-    lengths = torch.zeros_like(starts)
-    lengths[:-1] = starts[1:] - starts[:-1]
-    lengths[-1] = ranks_bev.shape[0] - starts[-1]
-    shape = (B, 1, bev[1], bev[0], C)
-    mv = lambda t: t.to(device)
-    return dict(depth=mv(depth), feat=mv(feat), ranks_depth=mv(ranks_depth), ranks_feat=mv(ranks_feat),
-                ranks_bev=mv(ranks_bev), starts=mv(starts), lengths=mv(lengths), shape=shape)
+from racformer_b200.synthetic import make_lss_pool_case as make_lss_case  # noqa: E402
 
 
 @pytest.mark.gpu

@@ -88,28 +88,17 @@ def main():
     }
     # BEVPoolv2 at the LSS shapes of the f8 config: 6 cams x 96 depth bins x 16x44, C = 256, 128x128 BEV
     from racformer_b200 import bev_pool
-    from tests.test_bev_pool import _bp_intervals, make_lss_case
-    pc = make_lss_case(0, 1, 6, 96, 16, 44, 256, (128, 128), device="cuda")
+    from racformer_b200.synthetic import make_lss_pool_case
+    pc = make_lss_pool_case(0, 1, 6, 96, 16, 44, 256, (128, 128), device="cuda")
     p_out = torch.zeros(pc["shape"], device="cuda")
     p_og = torch.randn(pc["shape"], device="cuda")
-    prd, prf, prb, pst, pln = (t.cuda() for t in _bp_intervals(pc["ranks_depth"].cpu(), pc["ranks_feat"].cpu(), pc["ranks_bev"].cpu()))
+    prd, prf, prb, pst, pln = bev_pool.backward_intervals(pc["ranks_depth"], pc["ranks_feat"], pc["ranks_bev"], stable=True)
     p_dg, p_fg = torch.zeros_like(pc["depth"]), torch.zeros_like(pc["feat"])
     ops["bev_pool_fwd"] = lambda: bev_pool.bev_pool_v2_forward(pc["depth"], pc["feat"], p_out, pc["ranks_depth"], pc["ranks_feat"],
                                                                pc["ranks_bev"], pc["lengths"], pc["starts"])
     ops["bev_pool_bwd"] = lambda: bev_pool.bev_pool_v2_backward(p_og, p_dg, p_fg, pc["depth"], pc["feat"], prd, prf, prb, pln, pst)
     npts = pc["ranks_bev"].numel()
     pool_bytes = npts * (256 * 4 + 4 + 12) + pc["starts"].numel() * (256 * 4 + 8)
-    try:
-        from oracle import build_ref
-        ext = build_ref.load_prebuilt_bev_pool()
-    except Exception:
-        ext = None
-    if ext is not None:
-        ops["ref_bev_pool_fwd"] = lambda: ext.bev_pool_v2_forward(pc["depth"], pc["feat"], p_out, pc["ranks_depth"], pc["ranks_feat"],
-                                                                  pc["ranks_bev"], pc["lengths"], pc["starts"])
-        ops["ref_bev_pool_bwd"] = lambda: ext.bev_pool_v2_backward(p_og, p_dg, p_fg, pc["depth"], pc["feat"], prd, prf, prb, pln, pst)
-        if "bev_pool_fwd" in args.ops:
-            args.ops += ",ref_bev_pool_fwd,ref_bev_pool_bwd"
     _, mask = wrapper.msmv_tap_masks(F8_SHAPES, d["loc"], 6)
     from racformer_b200.multi_scale_deformable_attn_function import msda_tap_masks
     mmask = msda_tap_masks(d["sp"], d["mloc"])
@@ -117,7 +106,7 @@ def main():
     algo["msmv_fwd"], algo["msmv_bwd"] = msmv_bytes(mask, C=64, L=4, feat_bytes=sum(f.numel() * 4 for f in d["feats"]))
     algo["msda_fwd"], algo["msda_bwd"] = msda_bytes(mmask, D=64, value_bytes=d["value"].numel() * 4)
     # per point: feature row (C*4) + depth + 3 ranks; per interval: output row + start/length. Backward reads out_grad rows.
-    algo["bev_pool_fwd"] = algo["bev_pool_bwd"] = algo["ref_bev_pool_fwd"] = algo["ref_bev_pool_bwd"] = pool_bytes
+    algo["bev_pool_fwd"] = algo["bev_pool_bwd"] = pool_bytes
     res = {"case": args.case, "gpu": torch.cuda.get_device_name(0), "l2_flush": not args.no_flush, "peak_hbm_gbs": peaks["hbm_gbs"]}
     for name in args.ops.split(","):
         t = time_op(ops[name], args.iters, args.warmup, flush)
