@@ -418,3 +418,45 @@ def test_ops_on_a_non_current_device():
     value, sp, lsi, mloc, aw, mg = make_msda_inputs(4, B=2, M=4, D=64, Q=9, P=20, shapes=[(16, 16)])
     mo = msda.MultiScaleDeformableAttnFunction_fp32.apply(value.to(d1), sp.to(d1), lsi.to(d1), mloc.to(d1), aw.to(d1), 64)
     assert_close(mo, co.msda_forward(value, sp, lsi, mloc, aw), FWD_RTOL, FWD_ATOL_EXACT * _scale(value), "cuda:1 msda forward")
+
+
+def test_ops_are_cuda_graph_capture_safe_and_repeatable():
+    """Forward + backward of both ops captured in one CUDA graph (incl. the library's own zero-fill memsets), replayed
+    several times: every replay must reproduce the eager forward bit for bit and the eager backward within the atomic
+    reordering tolerance; the library allocates nothing and never synchronises, so capture must succeed as is."""
+    wrapper, msda = _ops()
+    feats, loc, w, g = make_msmv_inputs(8, Bp=4, N=6, C=64, Q=64, P=12, shapes=[(16, 44), (8, 22), (4, 11), (2, 6)],
+                                        lo=-0.1, hi=1.1, device=DEV)
+    value, sp, lsi, mloc, aw, mg = make_msda_inputs(8, B=2, M=4, D=64, Q=64, P=20, shapes=[(32, 32)], lo=-0.05, hi=1.05,
+                                                    device=DEV)
+    eager_out = wrapper.msmv_forward(feats, loc, w)
+    eager_grads = wrapper.msmv_backward(g, feats, loc, w)
+    eager_mout = msda.ext_module.ms_deform_attn_forward(value, sp, lsi, mloc, aw, im2col_step=64)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            wrapper.msmv_backward(g, feats, loc, w)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    gv = torch.zeros_like(value)
+    gl, ga = torch.empty_like(mloc), torch.empty_like(aw)
+    with torch.cuda.graph(graph):
+        out = wrapper.msmv_forward(feats, loc, w)
+        grads = wrapper.msmv_backward(g, feats, loc, w)
+        mout = msda.ext_module.ms_deform_attn_forward(value, sp, lsi, mloc, aw, im2col_step=64)
+        gv.zero_()
+        msda.ext_module.ms_deform_attn_backward(value, sp, lsi, mloc, aw, mg, gv, gl, ga, im2col_step=64)
+    first = None
+    for _ in range(5):
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager_out) and torch.equal(mout, eager_mout)
+        for a, b in zip(grads, eager_grads):
+            assert_close(a, b, BWD_RTOL, BWD_ATOL * _scale(b), "captured backward vs eager backward")
+        if first is None:
+            first = [t.clone() for t in grads] + [gv.clone()]
+        else:   # run-to-run spread of the atomics stays inside the same tolerance
+            for a, b in zip(list(grads) + [gv], first):
+                assert_close(a, b, BWD_RTOL, BWD_ATOL * _scale(b), "replay vs first replay")
