@@ -229,3 +229,42 @@ def test_optin_split_tf32_mixing_stays_at_fp32_noise_level():
     _close(got[0], ref[0], "cls tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
     _close(got[1], ref[1], "box tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
     assert torch.backends.cuda.matmul.allow_tf32 is False   # the global flag is restored
+
+
+@pytest.mark.gpu
+def test_decoder_full_f8_size_cuda_path_vs_cpu_reference_path():
+    """racformer_r50_nuimg_704x256_f8 shapes, batch 1, 2 decoder iterations: the production path (sm_100a sampling
+    kernels, fused point kernels, grouped output, hoisting, CUDA graph) against the same decoder on the reference's
+    PyTorch CPU path (oracle ports, reference schedule), which tests above pin to the unchanged reference."""
+    from racformer_b200.graphs import GraphedDecoderForward
+    from racformer_b200.synthetic import D_REGION_LIST, PC_RANGE, make_decoder_inputs
+    cfg = dict(embed_dims=256, num_frames=8, num_points=4, num_points_bev=4, num_layers=2, num_levels=4, num_classes=10,
+               code_size=10, img_depth_num=3, bev_depth_num=5, pc_range=PC_RANGE, num_ray=150,
+               d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=6)
+    torch.manual_seed(0)
+    cpu_model = RaCFormerTransformer(**cfg, ops=cpu_oracle_ops(), hoist_invariants=False)
+    cpu_model.init_weights()
+    fill_parameters_by_name(cpu_model, seed=1)
+    cpu_model.eval()
+    gpu_model = RaCFormerTransformer(**cfg)
+    gpu_model.load_state_dict(cpu_model.state_dict())
+    gpu_model.eval().cuda()
+    d = make_decoder_inputs(seed=12)
+    g = torch.Generator().manual_seed(5)
+    d["query_bbox"][..., 8:10] = torch.randn(1, 900, 2, generator=g) * 0.5
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    with torch.no_grad():
+        ref_cls, ref_box = cpu_model(d["query_bbox"], d["query_feat"], d["mlvl_feats"], d["lss_bev"], d["radar_bev"], None,
+                                     d["img_metas"])
+    dg = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in d.items() if k != "mlvl_feats"}
+    dg["mlvl_feats"] = [f.cuda() for f in d["mlvl_feats"]]
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cls, box = GraphedDecoderForward(gpu_model, dg)()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    # fp32 end to end; a handful of the 345 600 x 2 sample points sit within an ulp of an image border or a cell edge,
+    # which moves a few query outputs by more than rounding noise -> small outlier allowance
+    _close(cls, ref_cls, "f8 cls CUDA path vs CPU reference path", rtol=1e-3, atol=1e-3, max_outlier_frac=2e-3)
+    _close(box, ref_box, "f8 box CUDA path vs CPU reference path", rtol=1e-3, atol=1e-3, max_outlier_frac=2e-3)
