@@ -197,6 +197,17 @@ int racf_bev_pool_v2_backward(const float* out_grad, const float* depth, const f
                               float* depth_grad, float* feat_grad, racf_stream_t stream);
 
 /*
+ * "next" row: fused core of AdaptiveMixing for inference
+ * (models/racformer_transformer.py:592-604): per (query, group)
+ *     t = relu(layer_norm(x @ M));  out = relu(layer_norm(S @ t))
+ * x [QG, in_points, C], params [QG, C*C + out_points*in_points] (M then S, as parameter_generator emits them),
+ * out [QG, out_points, C]; layer norms over the whole [points, C] slab, no affine. fp32 FMA on the CUDA cores.
+ * Implemented for C == 64, out_points == 128, in_points % 4 == 0, in_points <= 128 (else RACF_ERR_UNSUPPORTED).
+ */
+int racf_adaptive_mixing_forward(const float* x, const float* params, int num_query_groups, int in_points,
+                                 int out_points, int channels, float eps, float* out, racf_stream_t stream);
+
+/*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
  * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
  * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.

@@ -36,6 +36,7 @@ SIGNATURES = {
     "racf_to_sampling_layout": (_i, [_c_float_p, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
     "racf_bev_pool_v2_forward": (_i, [_c_float_p] * 7 + [_i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bev_pool_v2_backward": (_i, [_c_float_p] * 8 + [_i, _i, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "racf_adaptive_mixing_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
     "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bench_scatter_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),

@@ -582,6 +582,7 @@ class AdaptiveMixing(nn.Module):
         self.s_parameters = self.in_points * self.out_points
         self.activation_checkpoint = True
         self.fold_bias = True
+        self.fused_core = True              # inference: csrc/mixing.cu instead of 2 bmm + 2 layer_norm + 2 relu
         self._folded = None
         self.gemm_precision = "fp32"        # "tf32x3": opt-in operand-split TF32 tensor-core GEMMs (inference)
         self._split_gen = self._split_out = None
@@ -612,6 +613,12 @@ class AdaptiveMixing(nn.Module):
     def inner_forward(self, x, query):
         B, Q, G, P, C = x.shape
         params = self._generate(query).reshape(B * Q, G, -1)
+        if self.fused_core and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32:
+            from . import points   # one kernel for matmul-LN-ReLU-matmul-LN-ReLU
+            core = points.adaptive_mixing_core(x.reshape(B * Q * G, P, C).contiguous(),
+                                               params.reshape(B * Q * G, -1).contiguous(), self.out_points)
+            if core is not None:
+                return query + self._project(core.reshape(B, Q, -1))
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)
         s = s.reshape(B * Q, G, self.out_points, self.in_points)
@@ -619,12 +626,14 @@ class AdaptiveMixing(nn.Module):
         out = F.relu(F.layer_norm(out, [out.size(-2), out.size(-1)]))
         out = torch.matmul(s, out)
         out = F.relu(F.layer_norm(out, [out.size(-2), out.size(-1)]))
-        out = out.reshape(B, Q, -1)
+        return query + self._project(out.reshape(B, Q, -1))
+
+    def _project(self, out):
         if self.gemm_precision == "tf32x3" and not torch.is_grad_enabled() and out.is_cuda:
             if self._split_out is None:
                 self._split_out = _SplitTF32Linear(self.out_proj)
-            return query + self._split_out(out)
-        return query + self.out_proj(out)
+            return self._split_out(out)
+        return self.out_proj(out)
 
     def forward(self, x, query):
         return _maybe_checkpoint(self, self.inner_forward, x, query)

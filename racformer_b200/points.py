@@ -76,3 +76,20 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
                                                  _stream(feat.device))
     _lib.check(rc, "racf_to_sampling_layout")
     return out
+
+
+def adaptive_mixing_core(x, params, out_points, eps=1e-5):
+    """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
+    (csrc/mixing.cu). Returns None when the fused kernel does not exist for the shapes (callers use the PyTorch chain)."""
+    _check(x, params)
+    QG, P_in, C = x.shape
+    if params.shape != (QG, C * C + out_points * P_in):
+        raise RuntimeError("adaptive_mixing_core: params must be [QG, C*C + out_points*P_in]")
+    out = torch.empty((QG, out_points, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_adaptive_mixing_forward(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C, float(eps),
+                                                      out.data_ptr(), _stream(x.device))
+    if rc == -6:
+        return None
+    _lib.check(rc, "racf_adaptive_mixing_forward")
+    return out

@@ -140,3 +140,32 @@ def test_channel_last_relayout_kernel_equals_permute():
         feat = torch.randn(B, T * N, G * 64, H, W, device="cuda")
         want = feat.reshape(B, T, N, G, 64, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, 64).contiguous()
         assert torch.equal(points.to_sampling_layout(feat, N, G), want)
+
+
+@pytest.mark.parametrize("p_in", [96, 24, 128, 4])
+def test_fused_adaptive_mixing_core_equals_pytorch_chain(p_in):
+    """csrc/mixing.cu vs the op chain of AdaptiveMixing.inner_forward (racformer_transformer.py:592-604): both are fp32
+    FMA arithmetic, so they agree to rounding / summation order (outputs are layer-normalised, O(1))."""
+    import torch.nn.functional as F
+    from racformer_b200 import points
+    g = torch.Generator().manual_seed(p_in)
+    QG, C, P_out = 300, 64, 128
+    x = torch.randn(QG, p_in, C, generator=g).cuda()
+    params = (torch.randn(QG, C * C + P_out * p_in, generator=g) * 0.2).cuda()
+    m, s = params.split([C * C, P_out * p_in], 1)
+    t = torch.matmul(x, m.reshape(QG, C, C))
+    t = F.relu(F.layer_norm(t, [p_in, C]))
+    ref = torch.matmul(s.reshape(QG, P_out, p_in), t)
+    ref = F.relu(F.layer_norm(ref, [P_out, C]))
+    got = points.adaptive_mixing_core(x, params, P_out)
+    assert got is not None and got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-5
+    assert torch.equal(got, points.adaptive_mixing_core(x, params, P_out)), "deterministic"
+
+
+def test_fused_adaptive_mixing_core_declines_unsupported_shapes():
+    from racformer_b200 import points
+    x = torch.randn(4, 10, 64, device="cuda")          # in_points not a multiple of 4
+    assert points.adaptive_mixing_core(x, torch.randn(4, 64 * 64 + 128 * 10, device="cuda"), 128) is None
+    x = torch.randn(4, 8, 32, device="cuda")           # C != 64
+    assert points.adaptive_mixing_core(x, torch.randn(4, 32 * 32 + 128 * 8, device="cuda"), 128) is None
