@@ -278,8 +278,9 @@ class DecoderWorkload:
         self.mixing_precision = mixing_precision
         self.model.set_mixing_precision(mixing_precision)
         self.inp = make_decoder_inputs(seed=100 + seed, device=self.device, num_cams=num_cams)
-        # our kernels per step: per iteration 1 MSMV + 2 MSDA, and (inference) 1 + 2 fused point-generation kernels
-        self.launches_per_step = 6 * num_layers
+        # our kernels per step: per iteration 1 MSMV + 2 MSDA + 1 + 2 fused point-generation kernels + 1 fused mixing
+        # core, plus one channel-last re-layout launch per FPN level
+        self.launches_per_step = 7 * num_layers + 4
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None
