@@ -246,7 +246,7 @@ class DecoderWorkload:
                                     "full f8 shapes, all host threads")
 
     def __init__(self, device, seed=0, name="decoder_forward_f8", num_layers=6, hoist=True, graph=True, num_cams=6,
-                 mixing_precision="fp32"):
+                 mixing_precision="bf16x6"):
         from racformer_b200.decoder import RaCFormerTransformer, SamplingOps
         self.use_graph = graph and torch.device(device).type == "cuda"
         self._graphed = None
@@ -280,7 +280,9 @@ class DecoderWorkload:
         self.inp = make_decoder_inputs(seed=100 + seed, device=self.device, num_cams=num_cams)
         # our kernels per step: per iteration 1 MSMV + 2 MSDA + 1 + 2 fused point-generation kernels + 1 fused mixing
         # core, plus one channel-last re-layout launch per FPN level
-        self.launches_per_step = 7 * num_layers + 4
+        # with the tcgen05 Linear layers also: 1 operand split + 1 GEMM (parameter_generator), 1 GEMM + 1 split-K reduce
+        # (out_proj) per iteration
+        self.launches_per_step = (11 if mixing_precision.startswith("bf16") else 7) * num_layers + 4
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None
@@ -557,6 +559,8 @@ def build(name, device, seed=0):
         return DecoderWorkload(device, seed=seed)
     if name == "decoder_forward_f8_nohoist":
         return DecoderWorkload(device, seed=seed, name=name, hoist=False, graph=False)
+    if name in ("decoder_forward_f8_sgemm", "decoder_forward_f8_bf16x9"):   # AdaptiveMixing Linear layers: cuBLAS SGEMM / all 9 terms
+        return DecoderWorkload(device, seed=seed, name=name, mixing_precision="fp32" if name.endswith("sgemm") else "bf16x9")
     if name == "decoder_forward_f8_tf32x3":    # OPT-IN variant: AdaptiveMixing GEMMs as operand-split TF32 (not fp32 SGEMM)
         return DecoderWorkload(device, seed=seed, name=name, mixing_precision="tf32x3")
     if name == "decoder_forward_f8_eager":

@@ -206,6 +206,29 @@ int racf_bev_pool_v2_backward(const float* out_grad, const float* depth, const f
  */
 int racf_adaptive_mixing_forward(const float* x, const float* params, int num_query_groups, int in_points,
                                  int out_points, int channels, float eps, float* out, racf_stream_t stream);
+/* Same, but the result is written as three bf16 pieces out3 [3][QG][out_points][C] with value == p0 + p1 + p2 exactly:
+ * the A operand of racf_linear_bf16x3_forward (out_proj), without an fp32 round trip through HBM. */
+int racf_adaptive_mixing_forward_split(const float* x, const float* params, int num_query_groups, int in_points,
+                                       int out_points, int channels, float eps, void* out3, racf_stream_t stream);
+
+/*
+ * "next" row: AdaptiveMixing's two large Linear layers (parameter_generator and out_proj,
+ * models/racformer_transformer.py:560-566, F.linear in fp32) on the tcgen05 tensor cores at fp32-grade accuracy.
+ *
+ * racf_split_bf16x3: x [count] fp32 -> out3 [3][count] bf16 with x == out3[0] + out3[1] + out3[2] exactly
+ *   (count % 4 == 0, x 16-byte aligned).
+ * racf_linear_bf16x3_plan: the K split and workspace size racf_linear_bf16x3_forward wants for a problem
+ *   (K per accumulator is kept <= 512 to bound the tensor cores' truncating accumulation).
+ * racf_linear_bf16x3_forward: out[M,N] = a[M,K] . w[N,K]^T + bias[N] with a3 = split(a) [3][M][K], w3 = split(w)
+ *   [3][N][K] (nn.Linear's weight layout), products a_i * w_j with i + j <= max_order accumulated in fp32 (4: all nine,
+ *   2: six). bias may be NULL. K % 8 == 0. workspace: split_k * M * N floats when split_k > 1 (else may be NULL).
+ *   variant: 0 = 32-wide K blocks / 64-byte swizzle / 2 stages, 1 = 64-wide / 128-byte swizzle / 1 stage.
+ */
+int racf_split_bf16x3(const float* x, long long count, void* out3, racf_stream_t stream);
+int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long long* workspace_bytes);
+int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
+                               int max_order, int split_k, int variant, float* workspace, float* out,
+                               racf_stream_t stream);
 
 /*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over

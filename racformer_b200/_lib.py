@@ -37,6 +37,12 @@ SIGNATURES = {
     "racf_bev_pool_v2_forward": (_i, [_c_float_p] * 7 + [_i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bev_pool_v2_backward": (_i, [_c_float_p] * 8 + [_i, _i, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_adaptive_mixing_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
+    "racf_adaptive_mixing_forward_split": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, ctypes.c_void_p,
+                                                ctypes.c_void_p]),
+    "racf_split_bf16x3": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
+    "racf_linear_bf16x3_plan": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_longlong)]),
+    "racf_linear_bf16x3_forward": (_i, [ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, _i, _c_float_p,
+                                        _c_float_p, ctypes.c_void_p]),
     "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bench_scatter_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),

@@ -1,0 +1,449 @@
+// fp32-grade Linear layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) -- SURVEY.md 8f-4.
+//
+// AdaptiveMixing's two large Linear layers (models/racformer_transformer.py:560-566: parameter_generator
+// [Q,256] x [65536,256]^T and out_proj [Q,32768] x [256,32768]^T, 45 GFLOP per decoder iteration) are fp32 SGEMMs in the
+// reference; on B200 they run on the CUDA cores at ~48 TFLOP/s and are 40 % of the decoder step. Here they run on the
+// tensor cores WITHOUT giving up fp32 accuracy:
+//
+//   * every fp32 operand is split exactly into three bf16 pieces, x = x0 + x1 + x2 (8 + 8 + 8 significand bits,
+//     racf_split_bf16x3), so a product a*w = sum_ij a_i*w_j and every a_i*w_j is exact in the tensor core's fp32
+//     datapath (8 x 8 bit significands);
+//   * terms with i + j <= max_order are accumulated (max_order 4: all 9, nothing dropped; 2: 6 terms, dropped part
+//     <= 3 * 2^-24 relative per product, i.e. below fp32's own rounding);
+//   * the tensor cores truncate (round toward zero) once per MMA into the fp32 accumulator, a bias of ~0.5 ulp per
+//     K = 16 step that grows linearly with the number of MMAs that hit ONE accumulator. So the large term a0*w0
+//     gets its own TMEM accumulator (K/16 steps) and the 2^-8-times smaller cross terms share a second one; the two
+//     are added in fp32 (round to nearest) in the epilogue, and the host keeps K per accumulator <= 512 by
+//     splitting K across CTAs whose partial sums are reduced in fp32 by a second kernel (deterministic, no atomics).
+//
+// Kernel: one 128 x 128 output tile per CTA, 128 threads, two CTAs per SM (so one CTA's epilogue overlaps the other's
+// MMAs). Warp 0 lane 0 = TMA producer (one 3-D box of {BK, 128 rows, 3 pieces} per operand and stage, 64/128-byte
+// swizzle), warp 1 lane 0 = MMA issuer (tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 128, K = 16, operands from
+// shared memory through UMMA descriptors, D in TMEM), mbarrier full/empty ring; then all four warps read their 32 TMEM
+// lanes with tcgen05.ld, stage the tile in (now idle) pipeline shared memory and write it out in full 512-byte rows.
+#include <cuda.h>            // CUtensorMap types (no libcuda link: the encoder is fetched with cudaGetDriverEntryPoint)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "racformer_ops.h"
+
+namespace racf {
+
+constexpr int kLinBM = 128;
+constexpr int kLinBN = 128;
+constexpr int kLinThreads = 128;
+constexpr int kLinTmemCols = 256;      // accumulator of a0*w0 in columns [0,128), of the cross terms in [128,256)
+constexpr int kLinStgStride = 132;     // floats per staged output row (128 + 4: conflict-free 16-byte row-major stores)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32; issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane, register = column)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major [128 rows][BK] bf16 tile whose rows are one swizzle span (64 or 128
+// bytes) wide, as TMA writes it: 8-row groups are SBO = 8 * row bytes apart; LBO is unused for swizzled K-major.
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = kRowBytes == 128 ? 2 : (kRowBytes == 64 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)
+         | ((uint64_t)((8 * kRowBytes) >> 4) << 32)
+         | (1ull << 46)                                                               // descriptor version (sm_100)
+         | (layout << 61);
+}
+
+// Instruction descriptor: D fp32, A and B bf16, both K-major, M = 128, N = 128, dense, no negate.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GEMM kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct LinArgs {
+    const float* bias;      // [N] or nullptr; added only when the kernel writes the final result (num_splits == 1)
+    float* out;             // [M, N] (num_splits == 1) or workspace [num_splits, M, N]
+    int M, N;
+    int m_tiles, n_tiles;
+    int num_kblocks;        // ceil(K / BK)
+    int kblocks_per_split;
+    int max_order;          // accumulate a_i * w_j for i + j <= max_order (4 = all nine terms)
+};
+
+template <int kBK, int kStages>
+__global__ void __launch_bounds__(kLinThreads, 2)
+linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const LinArgs args) {
+    constexpr int kRowBytes = kBK * 2;
+    constexpr int kPieceBytes = 128 * kRowBytes;          // one [128][BK] bf16 tile
+    constexpr int kStageBytes = 6 * kPieceBytes;          // a0 a1 a2 w0 w1 w2
+    static_assert(kStages * kStageBytes >= kLinBM * kLinStgStride * 4, "pipeline smem is reused to stage the output tile");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzled tiles need 1024-byte alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tile = blockIdx.x;
+    const int m_tile = tile % args.m_tiles;
+    const int n_tile = (tile / args.m_tiles) % args.n_tiles;
+    const int split = tile / (args.m_tiles * args.n_tiles);
+    const int kb_begin = split * args.kblocks_per_split;
+    const int kb_end = min(kb_begin + args.kblocks_per_split, args.num_kblocks);
+    const int num_kb = kb_end - kb_begin;
+    const int m0 = m_tile * kLinBM, n0 = n_tile * kLinBN;
+
+    auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+    auto empty_bar = [&](int s) { return smem_u32(&bars[kStages + s]); };
+    const uint32_t tmem_full_bar = smem_u32(&bars[2 * kStages]);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp allocates (and later frees) the CTA's TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "n"(kLinTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % kStages;
+            mbar_wait(empty_bar(s), ((i / kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(full_bar(s), kStageBytes);
+            const uint32_t dst = smem_base + s * kStageBytes;
+            const int k0 = (kb_begin + i) * kBK;
+            tma_load_3d(dst, &map_a, k0, m0, 0, full_bar(s));
+            tma_load_3d(dst + 3 * kPieceBytes, &map_w, k0, n0, 0, full_bar(s));
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_bf16(kLinBM, kLinBN);
+        const uint32_t d_main = tmem_base, d_cross = tmem_base + kLinBN;
+        uint32_t acc_cross = 0;
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % kStages;
+            mbar_wait(full_bar(s), (i / kStages) & 1);
+            tcgen05_fence_after();
+            const uint32_t a_base = smem_base + s * kStageBytes, w_base = a_base + 3 * kPieceBytes;
+#pragma unroll
+            for (int ks = 0; ks < kBK / 16; ++ks) {
+                // smallest terms first; a 16-element K step is 32 bytes further inside the swizzle span
+                for (int order = args.max_order; order >= 1; --order) {
+                    for (int pa = 0; pa <= 2; ++pa) {
+                        const int pw = order - pa;
+                        if (pw < 0 || pw > 2) continue;
+                        umma_bf16(d_cross, umma_desc<kRowBytes>(a_base + pa * kPieceBytes + ks * 32),
+                                  umma_desc<kRowBytes>(w_base + pw * kPieceBytes + ks * 32), idesc, acc_cross);
+                        acc_cross = 1;
+                    }
+                }
+                umma_bf16(d_main, umma_desc<kRowBytes>(a_base + ks * 32), umma_desc<kRowBytes>(w_base + ks * 32), idesc,
+                          (i > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));     // the stage may be refilled once these MMAs have read it
+        }
+        umma_commit(tmem_full_bar);        // accumulators complete
+    }
+    __syncwarp();
+
+    // ===== epilogue: all four warps, warp w owns TMEM lanes / output rows [32w, 32w + 32) =====
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+
+    float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool has_cross = args.max_order >= 1 && num_kb > 0;
+#pragma unroll 1
+    for (int c = 0; c < kLinBN / 32; ++c) {
+        uint32_t v[32], u[32];
+        if (num_kb > 0) {
+            tmem_ld32(lane_addr + c * 32, v);
+            if (has_cross) tmem_ld32(lane_addr + kLinBN + c * 32, u);
+            tmem_ld_wait();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 o;
+            if (num_kb > 0) {
+                o.x = __uint_as_float(v[4 * j + 0]); o.y = __uint_as_float(v[4 * j + 1]);
+                o.z = __uint_as_float(v[4 * j + 2]); o.w = __uint_as_float(v[4 * j + 3]);
+                if (has_cross) {
+                    o.x += __uint_as_float(u[4 * j + 0]); o.y += __uint_as_float(u[4 * j + 1]);
+                    o.z += __uint_as_float(u[4 * j + 2]); o.w += __uint_as_float(u[4 * j + 3]);
+                }
+            } else {
+                o = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4*>(stg + row * kLinStgStride + c * 32 + j * 4) = o;
+        }
+    }
+    __syncwarp();     // each warp reads back only the 32 rows it staged itself
+
+    const int num_splits = gridDim.x / (args.m_tiles * args.n_tiles);
+    float* outp = args.out + (long long)split * args.M * args.N;
+    const int gn = n0 + lane * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (args.bias != nullptr && num_splits == 1) {
+        if (gn + 0 < args.N) b4.x = __ldg(args.bias + gn + 0);
+        if (gn + 1 < args.N) b4.y = __ldg(args.bias + gn + 1);
+        if (gn + 2 < args.N) b4.z = __ldg(args.bias + gn + 2);
+        if (gn + 3 < args.N) b4.w = __ldg(args.bias + gn + 3);
+    }
+    const bool vec_ok = (args.N & 3) == 0 && gn + 3 < args.N;
+    for (int r = 0; r < 32; ++r) {
+        const int gm = m0 + warp * 32 + r;
+        if (gm >= args.M) break;
+        float4 o = *reinterpret_cast<const float4*>(stg + (warp * 32 + r) * kLinStgStride + lane * 4);
+        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+        float* dst = outp + (long long)gm * args.N + gn;
+        if (vec_ok) {
+            *reinterpret_cast<float4*>(dst) = o;
+        } else {
+            if (gn + 0 < args.N) dst[0] = o.x;
+            if (gn + 1 < args.N) dst[1] = o.y;
+            if (gn + 2 < args.N) dst[2] = o.z;
+            if (gn + 3 < args.N) dst[3] = o.w;
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kLinTmemCols) : "memory");
+    }
+}
+
+// out[m, n] = bias[n] + sum_s ws[s, m, n]   (fp32, round to nearest, fixed order)
+__global__ void __launch_bounds__(256)
+linear_splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ out,
+                            long long mn, int n, int num_splits) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= mn) return;
+    if (i4 + 3 < mn && (n & 3) == 0) {
+        float4 acc = *reinterpret_cast<const float4*>(ws + i4);
+        for (int s = 1; s < num_splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(ws + (long long)s * mn + i4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (bias != nullptr) {
+            const int c = (int)(i4 % n);
+            acc.x += __ldg(bias + c); acc.y += __ldg(bias + c + 1); acc.z += __ldg(bias + c + 2); acc.w += __ldg(bias + c + 3);
+        }
+        *reinterpret_cast<float4*>(out + i4) = acc;
+    } else {
+        for (long long i = i4; i < mn && i < i4 + 4; ++i) {
+            float acc = ws[i];
+            for (int s = 1; s < num_splits; ++s) acc += ws[(long long)s * mn + i];
+            if (bias != nullptr) acc += __ldg(bias + (int)(i % n));
+            out[i] = acc;
+        }
+    }
+}
+
+// x = p0 + p1 + p2 exactly (round-to-nearest bf16 at each step; the residuals are exact in fp32)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+    p0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p0);
+    p1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(p1);
+    p2 = __float2bfloat16_rn(r2);
+}
+
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __align__(8) __nv_bfloat16 p[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split3(f[j], p[0][j], p[1][j], p[2][j]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(out + k * n + i) = *reinterpret_cast<const uint2*>(p[k]);
+    } else {
+        for (long long j = i; j < n; ++j) split3(x[j], out[j], out[n + j], out[2 * n + j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [3 pieces][rows][K] bf16, box {BK, 128 rows, 3 pieces}; out-of-range rows / K are zero-filled by TMA
+static int make_operand_map(CUtensorMap* map, const void* base, int rows, int K, int bk) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (enc == nullptr) return RACF_ERR_UNSUPPORTED;
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * (cuuint64_t)K * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, 128, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RACF_ERR_BAD_SHAPE;
+}
+
+template <int kBK, int kStages>
+static int launch_linear(const CUtensorMap& ma, const CUtensorMap& mw, const LinArgs& args, int num_splits, cudaStream_t st) {
+    constexpr int smem = kStages * 6 * 128 * kBK * 2 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(linear_bf16x3_kernel<kBK, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)(args.m_tiles * args.n_tiles * num_splits);
+    linear_bf16x3_kernel<kBK, kStages><<<grid, kLinThreads, smem, st>>>(ma, mw, args);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace racf
+
+extern "C" int racf_split_bf16x3(const float* x, long long count, void* out3, racf_stream_t stream) {
+    using namespace racf;
+    if (!x || !out3) return RACF_ERR_NULL_POINTER;
+    if (count <= 0) return RACF_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(out3) & 7u) || (count & 3)) return RACF_ERR_UNSUPPORTED;
+    const long long threads = (count + 3) / 4;
+    split_bf16x3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, count, static_cast<__nv_bfloat16*>(out3));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long long* workspace_bytes) {
+    if (!split_k || !workspace_bytes) return RACF_ERR_NULL_POINTER;
+    if (M <= 0 || N <= 0 || K <= 0) return RACF_ERR_BAD_SHAPE;
+    // at most 512 of K (32 MMA steps) per TMEM accumulator: bounds the tensor cores' truncation bias (see the header)
+    const int s = (K + 511) / 512;
+    *split_k = s;
+    *workspace_bytes = s > 1 ? (long long)s * M * N * 4 : 0;
+    return RACF_OK;
+}
+
+extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
+                                          int max_order, int split_k, int variant, float* workspace, float* out,
+                                          racf_stream_t stream) {
+    using namespace racf;
+    if (!a3 || !w3 || !out) return RACF_ERR_NULL_POINTER;
+    if (M <= 0 || N <= 0 || K <= 0 || split_k <= 0) return RACF_ERR_BAD_SHAPE;
+    if ((K & 7) != 0 || max_order < 0 || max_order > 4) return RACF_ERR_UNSUPPORTED;   // TMA: 16-byte global strides
+    if ((reinterpret_cast<uintptr_t>(a3) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(out)) & 15u)
+        return RACF_ERR_UNSUPPORTED;
+    if (split_k > 1 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15u))) return RACF_ERR_NULL_POINTER;
+    const int bk = variant == 1 ? 64 : 32;
+    const int num_kblocks = (K + bk - 1) / bk;
+    if (split_k > num_kblocks) split_k = num_kblocks;
+    const int kbps = (num_kblocks + split_k - 1) / split_k;
+    split_k = (num_kblocks + kbps - 1) / kbps;           // no empty splits
+
+    CUtensorMap ma, mw;
+    int rc = make_operand_map(&ma, a3, M, K, bk);
+    if (rc != 0) return rc;
+    rc = make_operand_map(&mw, w3, N, K, bk);
+    if (rc != 0) return rc;
+
+    LinArgs args;
+    args.bias = bias;
+    args.out = split_k > 1 ? workspace : out;
+    args.M = M; args.N = N;
+    args.m_tiles = (M + kLinBM - 1) / kLinBM;
+    args.n_tiles = (N + kLinBN - 1) / kLinBN;
+    args.num_kblocks = num_kblocks;
+    args.kblocks_per_split = kbps;
+    args.max_order = max_order;
+    if ((long long)args.m_tiles * args.n_tiles * split_k > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = variant == 1 ? launch_linear<64, 1>(ma, mw, args, split_k, st) : launch_linear<32, 2>(ma, mw, args, split_k, st);
+    if (rc != 0) return rc;
+    if (split_k > 1) {
+        const long long mn = (long long)M * N;
+        const long long threads = (mn + 3) / 4;
+        linear_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(workspace, bias, out, mn, N, split_k);
+        return (int)cudaGetLastError();
+    }
+    return RACF_OK;
+}

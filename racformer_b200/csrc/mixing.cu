@@ -12,6 +12,7 @@
 //
 // Layouts: x [BQ, G, P_in, C] (what racf_msmv_forward_grouped writes), params [BQ, G, C*C + P_out*P_in] (M row-major
 // [C][C], then S row-major [P_out][P_in]), out [BQ, G, P_out, C]. C == 64, P_out == 128, P_in % 4 == 0, P_in <= 128.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -50,9 +51,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // touches in the same instruction fall into different banks although the row stride is a multiple of 32 words
 __device__ __forceinline__ int swz64(int row, int chunk) { return row * kMixC + ((chunk ^ (row & 7)) << 2); }
 
+// kSplitOut: write the result as three bf16 pieces (out3 [3][QG][128][64], value == p0 + p1 + p2 exactly) -- the A
+// operand of the tensor-core out_proj (csrc/linear.cu) -- instead of fp32, saving a 118 MB read + 177 MB write pass.
+template <bool kSplitOut>
 __global__ void __launch_bounds__(kMixThreads, 2)
 adaptive_mixing_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ out,
-                       int p_in, float eps) {
+                       __nv_bfloat16* __restrict__ out3, long long piece_stride, int p_in, float eps) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                          // [p_in][64] swizzled; reused for the normalised intermediate
     float* ms = xs + 128 * kMixC;              // [64][64]
@@ -183,27 +187,62 @@ adaptive_mixing_kernel(const float* __restrict__ x, const float* __restrict__ pa
             o.y = fmaxf((acc[i].y - mean) * rstd, 0.f);
             o.z = fmaxf((acc[i].z - mean) * rstd, 0.f);
             o.w = fmaxf((acc[i].w - mean) * rstd, 0.f);
-            *reinterpret_cast<float4*>(og + (ty + 16 * i) * kMixC + tx * 4) = o;
+            const long long off = (ty + 16 * i) * kMixC + tx * 4;
+            if constexpr (kSplitOut) {
+                const float f[4] = {o.x, o.y, o.z, o.w};
+                __align__(8) __nv_bfloat16 p[3][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    p[0][j] = __float2bfloat16_rn(f[j]);
+                    const float r1 = f[j] - __bfloat162float(p[0][j]);
+                    p[1][j] = __float2bfloat16_rn(r1);
+                    p[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][j]));
+                }
+                __nv_bfloat16* o3 = out3 + qg * (long long)(kMixPout * kMixC) + off;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(o3 + k * piece_stride) = *reinterpret_cast<const uint2*>(p[k]);
+            } else {
+                *reinterpret_cast<float4*>(og + off) = o;
+            }
         }
     }
 }
 
 }  // namespace racf
 
-extern "C" int racf_adaptive_mixing_forward(const float* x, const float* params, int num_query_groups, int in_points,
-                                            int out_points, int channels, float eps, float* out, racf_stream_t stream) {
+static int mixing_launch(const float* x, const float* params, int num_query_groups, int in_points, int out_points,
+                         int channels, float eps, float* out, void* out3, racf_stream_t stream) {
     using namespace racf;
-    if (!x || !params || !out) return RACF_ERR_NULL_POINTER;
+    if (!x || !params || (!out && !out3)) return RACF_ERR_NULL_POINTER;
     if (num_query_groups <= 0) return RACF_ERR_BAD_SHAPE;
     if (channels != kMixC || out_points != kMixPout || in_points <= 0 || in_points > 128 || (in_points & 3) != 0)
         return RACF_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(out)) & 15u)
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(out3)) & 15u)
         return RACF_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float) * (size_t)(128 * kMixC + kMixC * kMixC + kMixPout * in_points);
     // opt in to > 48 KB of dynamic shared memory (per device, idempotent, not a stream operation)
-    cudaError_t e = cudaFuncSetAttribute(adaptive_mixing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 114688);
+    cudaError_t e = cudaFuncSetAttribute(adaptive_mixing_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114688);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(adaptive_mixing_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 114688);
     if (e != cudaSuccess) return (int)e;
-    adaptive_mixing_kernel<<<(unsigned)num_query_groups, kMixThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, params, out, in_points, eps);
+    const long long piece_stride = (long long)num_query_groups * kMixPout * kMixC;
+    if (out3 != nullptr)
+        adaptive_mixing_kernel<true><<<(unsigned)num_query_groups, kMixThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+            x, params, nullptr, static_cast<__nv_bfloat16*>(out3), piece_stride, in_points, eps);
+    else
+        adaptive_mixing_kernel<false><<<(unsigned)num_query_groups, kMixThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+            x, params, out, nullptr, 0, in_points, eps);
     return (int)cudaGetLastError();
+}
+
+extern "C" int racf_adaptive_mixing_forward(const float* x, const float* params, int num_query_groups, int in_points,
+                                            int out_points, int channels, float eps, float* out, racf_stream_t stream) {
+    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, out, nullptr, stream);
+}
+
+extern "C" int racf_adaptive_mixing_forward_split(const float* x, const float* params, int num_query_groups, int in_points,
+                                                  int out_points, int channels, float eps, void* out3,
+                                                  racf_stream_t stream) {
+    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, nullptr, out3, stream);
 }

@@ -584,8 +584,13 @@ class AdaptiveMixing(nn.Module):
         self.fold_bias = True
         self.fused_core = True              # inference: csrc/mixing.cu instead of 2 bmm + 2 layer_norm + 2 relu
         self._folded = None
-        self.gemm_precision = "fp32"        # "tf32x3": opt-in operand-split TF32 tensor-core GEMMs (inference)
+        # the two large Linear layers in inference on CUDA: "bf16x6" / "bf16x9" = csrc/linear.cu (tcgen05; every fp32
+        # operand split exactly into three bf16 pieces, the six largest / all nine piece products accumulated in fp32 --
+        # measured closer to an fp64 product than cuBLAS SGEMM, profiles/r01_linear_bf16x3_check.json); "fp32" = cuBLAS
+        # SGEMM; "tf32x3" = the earlier cuBLAS TF32 operand-split experiment (less accurate, opt-in only)
+        self.gemm_precision = "bf16x6"
         self._split_gen = self._split_out = None
+        self._split = {}
         self.parameter_generator = nn.Linear(in_dim, n_groups * (self.m_parameters + self.s_parameters))
         self.out_proj = nn.Linear(self.eff_out_dim * self.out_points * n_groups, in_dim)
 
@@ -593,11 +598,27 @@ class AdaptiveMixing(nn.Module):
     def init_weights(self):
         nn.init.zeros_(self.parameter_generator.weight)
 
+    def _tensor_core_linear(self, query):
+        """True when the two large Linear layers run on csrc/linear.cu (tcgen05, exact bf16 operand splitting)."""
+        return (self.gemm_precision in ("bf16x9", "bf16x6") and not torch.is_grad_enabled() and query.is_cuda
+                and query.dtype == torch.float32 and self.in_dim % 8 == 0 and self.out_proj.in_features % 8 == 0)
+
+    def _split_linear(self, name):
+        from . import linear
+        order = linear.ALL_TERMS if self.gemm_precision == "bf16x9" else linear.SIX_TERMS
+        cur = self._split.get(name)
+        if cur is None or cur.max_order != order:
+            cur = self._split[name] = linear.SplitLinear(getattr(self, name), max_order=order)
+        return cur
+
     def _generate(self, query):
-        """parameter_generator(query). In inference the bias is folded into the GEMM as an extra K column
-        ([q, 1] @ [W, b]^T): cuBLAS otherwise adds it in a separate pass over the 236 MB output (0.16 ms per layer on
-        B200, profiles/r01_decoder_forward_kernel_breakdown_fused.json). Same sum, rounded inside the accumulator."""
+        """parameter_generator(query). Inference on CUDA: the tcgen05 kernel (bias added in its epilogue). With
+        gemm_precision == "fp32" the bias is folded into the cuBLAS GEMM as an extra K column ([q, 1] @ [W, b]^T): cuBLAS
+        otherwise adds it in a separate pass over the 236 MB output (0.16 ms per layer on B200,
+        profiles/r01_decoder_forward_kernel_breakdown_fused.json). Same sum, rounded inside the accumulator."""
         lin = self.parameter_generator
+        if self._tensor_core_linear(query):
+            return self._split_linear("parameter_generator")(query)
         if torch.is_grad_enabled() or not query.is_cuda or lin.bias is None or not self.fold_bias:
             return lin(query)
         if self.gemm_precision == "tf32x3":
@@ -615,9 +636,13 @@ class AdaptiveMixing(nn.Module):
         params = self._generate(query).reshape(B * Q, G, -1)
         if self.fused_core and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32:
             from . import points   # one kernel for matmul-LN-ReLU-matmul-LN-ReLU
+            split = self._tensor_core_linear(query)      # emit the bf16 pieces out_proj consumes, no fp32 round trip
             core = points.adaptive_mixing_core(x.reshape(B * Q * G, P, C).contiguous(),
-                                               params.reshape(B * Q * G, -1).contiguous(), self.out_points)
+                                               params.reshape(B * Q * G, -1).contiguous(), self.out_points, split=split)
             if core is not None:
+                if split:
+                    proj = self._split_linear("out_proj")(query, x3=core.reshape(3, B * Q, -1))
+                    return query + proj.reshape(B, Q, -1)
                 return query + self._project(core.reshape(B, Q, -1))
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)
@@ -629,6 +654,8 @@ class AdaptiveMixing(nn.Module):
         return query + self._project(out.reshape(B, Q, -1))
 
     def _project(self, out):
+        if self._tensor_core_linear(out):
+            return self._split_linear("out_proj")(out)
         if self.gemm_precision == "tf32x3" and not torch.is_grad_enabled() and out.is_cuda:
             if self._split_out is None:
                 self._split_out = _SplitTF32Linear(self.out_proj)
@@ -802,8 +829,9 @@ class RaCFormerTransformer(nn.Module):
                 m.fused_points = enabled
 
     def set_mixing_precision(self, precision):
-        """"fp32" (default, SGEMM like the reference) or "tf32x3" (opt-in, see _SplitTF32Linear)."""
-        assert precision in ("fp32", "tf32x3")
+        """"bf16x6" (default) / "bf16x9": tcgen05 kernel with exact bf16 operand splitting (fp32-grade, csrc/linear.cu);
+        "fp32": cuBLAS SGEMM like the reference; "tf32x3": opt-in cuBLAS TF32 operand split (see _SplitTF32Linear)."""
+        assert precision in ("fp32", "tf32x3", "bf16x6", "bf16x9")
         for m in self.modules():
             if isinstance(m, AdaptiveMixing):
                 m.gemm_precision = precision

@@ -1,0 +1,93 @@
+"""fp32-grade Linear layers on the tcgen05 tensor cores (racformer_b200/csrc/linear.cu).
+
+`y = F.linear(x, weight, bias)` for AdaptiveMixing's parameter_generator and out_proj
+(models/racformer_transformer.py:560-566) with every fp32 operand split exactly into three bf16 pieces; all nine (or the
+six largest) piece products are accumulated in fp32 in tensor memory. Forward / inference only; CUDA only -- there is no
+CPU or PyTorch fallback in this module.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_lib.load()
+
+ALL_TERMS = 4      # max_order: products a_i * w_j with i + j <= max_order; 4 keeps all nine
+SIX_TERMS = 2
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def split_bf16x3(x):
+    """fp32 CUDA tensor -> bf16 tensor [3, *x.shape] with x == pieces.float().sum(0) exactly."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise RuntimeError("split_bf16x3 needs a contiguous fp32 CUDA tensor")
+    if x.numel() % 4 != 0 or x.numel() == 0:
+        raise RuntimeError("split_bf16x3: element count must be a positive multiple of 4")
+    out = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_split_bf16x3(x.data_ptr(), x.numel(), out.data_ptr(), _stream(x.device))
+    _lib.check(rc, "racf_split_bf16x3")
+    return out
+
+
+def plan(M, N, K):
+    """-> (split_k, workspace_bytes) the library wants for this problem."""
+    s, w = ctypes.c_int(0), ctypes.c_longlong(0)
+    _lib.check(_lib.load().racf_linear_bf16x3_plan(M, N, K, ctypes.byref(s), ctypes.byref(w)), "racf_linear_bf16x3_plan")
+    return s.value, w.value
+
+
+def linear_bf16x3(a3, w3, bias=None, max_order=ALL_TERMS, split_k=None, variant=0):
+    """a3 [3, M, K], w3 [3, N, K] (bf16 pieces from split_bf16x3), bias [N] fp32 or None -> [M, N] fp32."""
+    if not (a3.is_cuda and w3.is_cuda and a3.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16
+            and a3.is_contiguous() and w3.is_contiguous() and a3.device == w3.device):
+        raise RuntimeError("linear_bf16x3 needs contiguous bf16 CUDA piece tensors on one device")
+    if a3.dim() != 3 or w3.dim() != 3 or a3.shape[0] != 3 or w3.shape[0] != 3 or a3.shape[2] != w3.shape[2]:
+        raise RuntimeError("linear_bf16x3: a3 must be [3, M, K] and w3 [3, N, K]")
+    M, K = a3.shape[1], a3.shape[2]
+    N = w3.shape[1]
+    if K % 8 != 0:
+        raise RuntimeError("linear_bf16x3: K must be a multiple of 8")
+    if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous()
+                                 and bias.numel() == N and bias.device == a3.device):
+        raise RuntimeError("linear_bf16x3: bias must be a contiguous fp32 CUDA tensor of N elements")
+    if split_k is None:
+        split_k, _ = plan(M, N, K)
+    out = torch.empty((M, N), dtype=torch.float32, device=a3.device)
+    ws = torch.empty((split_k, M, N), dtype=torch.float32, device=a3.device) if split_k > 1 else None
+    with torch.cuda.device(a3.device):
+        rc = _lib.load().racf_linear_bf16x3_forward(
+            a3.data_ptr(), w3.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, K, int(max_order),
+            int(split_k), int(variant), ws.data_ptr() if ws is not None else None, out.data_ptr(), _stream(a3.device))
+    _lib.check(rc, "racf_linear_bf16x3_forward")
+    return out
+
+
+class SplitLinear:
+    """Inference-time stand-in for an nn.Linear: caches the bf16 pieces of the weight (re-split when the parameter
+    changes) and runs x @ W^T + b through racf_linear_bf16x3_forward."""
+
+    def __init__(self, linear, max_order=ALL_TERMS, variant=0):
+        self.linear, self.max_order, self.variant = linear, max_order, variant
+        self._key, self._w3 = None, None
+
+    def weight_pieces(self):
+        w = self.linear.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._key != key:
+            self._w3 = split_bf16x3(w.detach().contiguous())
+            self._key = key
+        return self._w3
+
+    def __call__(self, x, x3=None):
+        """x [..., K] fp32 (or its pieces x3 [3, rows, K]) -> [..., N] fp32."""
+        lead = x.shape[:-1]
+        if x3 is None:
+            x3 = split_bf16x3(x.reshape(-1, x.shape[-1]).contiguous())
+        bias = self.linear.bias.detach() if self.linear.bias is not None else None
+        y = linear_bf16x3(x3, self.weight_pieces(), bias, self.max_order, variant=self.variant)
+        return y.reshape(*lead, -1)

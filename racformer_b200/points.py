@@ -78,17 +78,25 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
     return out
 
 
-def adaptive_mixing_core(x, params, out_points, eps=1e-5):
+def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False):
     """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
-    (csrc/mixing.cu). Returns None when the fused kernel does not exist for the shapes (callers use the PyTorch chain)."""
+    (csrc/mixing.cu). With split=True the result comes back as its three bf16 pieces [3, QG, out_points, C] (their sum is
+    the fp32 result exactly), ready for linear.linear_bf16x3. Returns None when the fused kernel does not exist for the
+    shapes (callers use the PyTorch chain)."""
     _check(x, params)
     QG, P_in, C = x.shape
     if params.shape != (QG, C * C + out_points * P_in):
         raise RuntimeError("adaptive_mixing_core: params must be [QG, C*C + out_points*P_in]")
-    out = torch.empty((QG, out_points, C), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
     with torch.cuda.device(x.device):
-        rc = _lib.load().racf_adaptive_mixing_forward(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C, float(eps),
-                                                      out.data_ptr(), _stream(x.device))
+        if split:
+            out = torch.empty((3, QG, out_points, C), dtype=torch.bfloat16, device=x.device)
+            rc = lib.racf_adaptive_mixing_forward_split(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C,
+                                                        float(eps), out.data_ptr(), _stream(x.device))
+        else:
+            out = torch.empty((QG, out_points, C), dtype=torch.float32, device=x.device)
+            rc = lib.racf_adaptive_mixing_forward(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C, float(eps),
+                                                  out.data_ptr(), _stream(x.device))
     if rc == -6:
         return None
     _lib.check(rc, "racf_adaptive_mixing_forward")

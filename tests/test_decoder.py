@@ -220,6 +220,7 @@ def test_optin_split_tf32_mixing_stays_at_fp32_noise_level():
     try:
         model = _my_model().cuda()
         with torch.no_grad():
+            model.set_mixing_precision("fp32")
             ref = model(*args)
             model.set_mixing_precision("tf32x3")
             got = model(*args)
@@ -229,6 +230,32 @@ def test_optin_split_tf32_mixing_stays_at_fp32_noise_level():
     _close(got[0], ref[0], "cls tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
     _close(got[1], ref[1], "box tf32x3 vs fp32", rtol=DEC_RTOL, atol=DEC_ATOL)
     assert torch.backends.cuda.matmul.allow_tf32 is False   # the global flag is restored
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16x6", "bf16x9"])
+def test_tensor_core_mixing_linears_match_sgemm_decoder(precision):
+    """Default inference path: AdaptiveMixing's parameter_generator / out_proj on csrc/linear.cu (tcgen05, exact bf16
+    operand splitting) against the same decoder with cuBLAS SGEMM for those layers. Both are fp32-grade evaluations of
+    the same sums (tests/test_linear.py bounds each against fp64), so the decoder outputs agree to the reordering noise
+    that separates two fp32 implementations."""
+    d, feats, metas = _fixture_inputs("cuda")
+    args = (d["query_bbox"].cuda(), d["query_feat"].cuda(), feats, d["lss_bev"].cuda(), d["radar_bev"].cuda(), None, metas)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        model = _my_model().cuda()
+        with torch.no_grad():
+            model.set_mixing_precision("fp32")
+            ref = model(*args)
+            model.set_mixing_precision(precision)
+            got = model(*args)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    mix = model.decoder.decoder_layer.mixing
+    assert mix._tensor_core_linear(args[1]) and set(mix._split) == {"parameter_generator", "out_proj"}   # it really ran
+    _close(got[0], ref[0], f"cls {precision} vs sgemm", rtol=DEC_RTOL, atol=DEC_ATOL)
+    _close(got[1], ref[1], f"box {precision} vs sgemm", rtol=DEC_RTOL, atol=DEC_ATOL)
 
 
 @pytest.mark.gpu

@@ -1,0 +1,147 @@
+"""The tcgen05 Linear layers (csrc/linear.cu) behind racformer_b200.linear.
+
+Reference computation: F.linear in fp32 (AdaptiveMixing.parameter_generator / out_proj, models/racformer_transformer.py:560-566,
+called at :592 and :606). A floating-point kernel, so the checker is a torch reference: the fp64 product is the truth, and
+cuBLAS SGEMM (what the reference runs on a GPU) sets the bar -- the tensor-core path must be at least as close to fp64.
+
+Error measure: |y - y64| / (sum_k |a_k||w_k| + |b|), the natural scale of a dot product's rounding error.
+Stated tolerance: max 6e-7, mean 4e-8 (fp32 unit roundoff is 6e-8; SGEMM measures 3.6e-7 / 1.9e-8 on these shapes).
+"""
+import pytest
+import torch
+
+from racformer_b200 import _lib
+
+MAX_TOL, MEAN_TOL = 6e-7, 4e-8
+
+
+def _normalised_error(y, a, w, b):
+    ref = a.double() @ w.double().t()
+    scale = a.double().abs() @ w.double().abs().t()
+    if b is not None:
+        ref += b.double()
+        scale += b.double().abs()
+    return (y.double() - ref).abs() / scale
+
+
+def test_plan_bounds_k_per_accumulator():
+    """Host logic (no GPU): the K split keeps every TMEM accumulator at <= 512 of K and sizes the workspace."""
+    import ctypes
+    lib = _lib.load()
+    for (M, N, K) in [(900, 65536, 256), (900, 256, 32768), (5, 7, 8), (128, 128, 513)]:
+        s, ws = ctypes.c_int(0), ctypes.c_longlong(0)
+        assert lib.racf_linear_bf16x3_plan(M, N, K, ctypes.byref(s), ctypes.byref(ws)) == 0
+        assert s.value == (K + 511) // 512
+        assert ws.value == (s.value * M * N * 4 if s.value > 1 else 0)
+    s, ws = ctypes.c_int(0), ctypes.c_longlong(0)
+    assert lib.racf_linear_bf16x3_plan(0, 4, 8, ctypes.byref(s), ctypes.byref(ws)) == -3
+    assert lib.racf_linear_bf16x3_plan(4, 4, 8, None, None) == -1
+
+
+def test_forward_rejects_bad_arguments_without_touching_the_gpu():
+    """Argument errors are reported before any CUDA call (so this runs on a CPU-only box)."""
+    lib = _lib.load()
+    p = 0x1000   # never dereferenced
+    assert lib.racf_linear_bf16x3_forward(None, p, None, 4, 4, 8, 4, 1, 0, None, p, None) == -1
+    assert lib.racf_linear_bf16x3_forward(p, p, None, 4, 4, 12, 4, 1, 0, None, p, None) == -6      # K % 8
+    assert lib.racf_linear_bf16x3_forward(p, p, None, 4, 4, 8, 5, 1, 0, None, p, None) == -6       # max_order
+    assert lib.racf_linear_bf16x3_forward(p, p, None, 4, 0, 8, 4, 1, 0, None, p, None) == -3
+    assert lib.racf_linear_bf16x3_forward(p, p, None, 4, 4, 1024, 4, 2, 0, None, p, None) == -1    # split without workspace
+    assert lib.racf_split_bf16x3(None, 4, p, None) == -1
+    assert lib.racf_split_bf16x3(p, 6, p, None) == -6
+
+
+@pytest.mark.gpu
+def test_split_is_exact_and_ordered():
+    from racformer_b200 import linear
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(1000, 64, device="cuda", generator=g) * torch.logspace(-20, 20, 64, device="cuda")
+    x[0, :8] = torch.tensor([0.0, -0.0, 1.0, -1.0, 3.0e38, 1.0e-30, 1.0 + 2.0 ** -23, 65504.0], device="cuda")
+    p = linear.split_bf16x3(x)
+    assert p.shape == (3, 1000, 64) and p.dtype == torch.bfloat16
+    assert torch.equal(p.double().sum(0), x.double())                       # exact: 8 + 8 + 8 significand bits
+    assert bool((p[1].float().abs() <= p[0].float().abs() * 2.0 ** -8 + 1e-45).all())   # each piece 2^-8 of the previous
+    assert bool((p[2].float().abs() <= p[1].float().abs() * 2.0 ** -8 + 1e-45).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(128, 128, 32), (77, 200, 40), (1, 8, 8), (300, 132, 264), (900, 256, 256), (257, 1030, 520)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_linear_matches_fp64_like_sgemm(shape, variant):
+    """Ragged M / N / K (TMA zero-fills the tails), bias on, all nine terms and the six-term default."""
+    from racformer_b200 import linear
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    a3, w3 = linear.split_bf16x3(a), linear.split_bf16x3(w)
+    for order in (linear.ALL_TERMS, linear.SIX_TERMS):
+        y = linear.linear_bf16x3(a3, w3, b, max_order=order, variant=variant)
+        err = _normalised_error(y, a, w, b)
+        assert err.max().item() < MAX_TOL and err.mean().item() < MEAN_TOL, (shape, order, err.max().item(), err.mean().item())
+        assert torch.equal(y, linear.linear_bf16x3(a3, w3, b, max_order=order, variant=variant)), "deterministic"
+    y0 = linear.linear_bf16x3(a3, w3, None, variant=variant)
+    assert _normalised_error(y0, a, w, None).max().item() < MAX_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(900, 65536, 256), (900, 256, 32768)])
+def test_linear_f8_shapes_no_worse_than_sgemm(shape):
+    """AdaptiveMixing's two layers at racformer_r50_nuimg_704x256_f8 sizes: closer to fp64 than (or as close as) cuBLAS
+    SGEMM, and inside the stated tolerance. out_proj exercises the K split (64 partial tiles + fp32 reduction)."""
+    from racformer_b200 import linear
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    lin = torch.nn.Linear(K, N, device="cuda")
+    with torch.no_grad():
+        lin.weight.copy_(w)
+        lin.bias.copy_(b)
+        fast = linear.SplitLinear(lin, max_order=linear.SIX_TERMS)
+        y = fast(a)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        y32 = lin(a)
+        torch.backends.cuda.matmul.allow_tf32 = old
+    rows = slice(0, 200)
+    err = _normalised_error(y[rows], a[rows], w, b)
+    err32 = _normalised_error(y32[rows], a[rows], w, b)
+    assert err.max().item() < MAX_TOL and err.mean().item() < MEAN_TOL
+    assert err.mean().item() <= 1.25 * err32.mean().item(), (err.mean().item(), err32.mean().item())
+    torch.testing.assert_close(y, y32, rtol=1e-5, atol=2e-5)
+    # weight cache: re-split when the parameter changes in place
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+        torch.testing.assert_close(fast(a) - b, 2.0 * (y - b), rtol=1e-5, atol=4e-5)
+
+
+@pytest.mark.gpu
+def test_mixing_core_split_output_is_the_fp32_output():
+    """racf_adaptive_mixing_forward_split: the three bf16 pieces sum to the fp32 kernel's result bit for bit."""
+    from racformer_b200 import points
+    g = torch.Generator(device="cuda").manual_seed(1)
+    QG, P_in, C, P_out = 48, 96, 64, 128
+    x = torch.randn(QG, P_in, C, device="cuda", generator=g)
+    params = torch.randn(QG, C * C + P_out * P_in, device="cuda", generator=g) * 0.2
+    full = points.adaptive_mixing_core(x, params, P_out)
+    pieces = points.adaptive_mixing_core(x, params, P_out, split=True)
+    assert pieces.shape == (3, QG, P_out, C) and pieces.dtype == torch.bfloat16
+    assert torch.equal(pieces.double().sum(0), full.double())
+
+
+@pytest.mark.gpu
+def test_linear_python_layer_rejects_bad_inputs():
+    from racformer_b200 import linear
+    a3 = torch.zeros(3, 8, 16, dtype=torch.bfloat16, device="cuda")
+    w3 = torch.zeros(3, 8, 24, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):
+        linear.linear_bf16x3(a3, w3)                                   # K mismatch
+    with pytest.raises(RuntimeError):
+        linear.linear_bf16x3(a3.float(), a3.float())                   # not bf16 pieces
+    with pytest.raises(RuntimeError):
+        linear.split_bf16x3(torch.zeros(8, 16))                        # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        linear.linear_bf16x3(a3, a3, bias=torch.zeros(3, device="cuda"))
