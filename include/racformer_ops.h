@@ -225,6 +225,11 @@ int racf_adaptive_mixing_forward_split(const float* x, const float* params, int 
  *   variant: 0 = 32-wide K blocks / 64-byte swizzle / 2 stages, 1 = 64-wide / 128-byte swizzle / 1 stage.
  */
 int racf_split_bf16x3(const float* x, long long count, void* out3, racf_stream_t stream);
+/* (in [batch][channels][positions] + pos [channels][positions] (may be NULL)) -> out3 [3][batch * positions][channels]:
+ * the add, permute and copy in front of BEVSelfAttention.value_proj (models/bev_self_attention.py:162-174) fused with the
+ * operand split; channels % 8 == 0. */
+int racf_split_bf16x3_chw_to_hwc(const float* in, const float* pos, int batch, int channels, int positions,
+                                 void* out3, racf_stream_t stream);
 int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long long* workspace_bytes);
 int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
                                int max_order, int split_k, int variant, float* workspace, float* out,

@@ -40,6 +40,7 @@ SIGNATURES = {
     "racf_adaptive_mixing_forward_split": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, ctypes.c_void_p,
                                                 ctypes.c_void_p]),
     "racf_split_bf16x3": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
+    "racf_split_bf16x3_chw_to_hwc": (_i, [_c_float_p, _c_float_p, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
     "racf_linear_bf16x3_plan": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_longlong)]),
     "racf_linear_bf16x3_forward": (_i, [ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, _i, _c_float_p,
                                         _c_float_p, ctypes.c_void_p]),

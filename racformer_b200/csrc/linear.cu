@@ -337,6 +337,39 @@ split_bf16x3_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __r
     }
 }
 
+// (in[bt][c][s] + pos[c][s]) -> bf16 pieces out3[piece][bt * S + s][c]: the channel-first BEV maps become the K-major A
+// operand of value_proj (models/bev_self_attention.py:162-174 does this with an add, a permute + copy and a GEMM whose
+// bias is added in a fourth pass). 64 channels x 32 positions per CTA through a padded shared-memory tile.
+__global__ void __launch_bounds__(256)
+split_bf16x3_chw_to_hwc_kernel(const float* __restrict__ in, const float* __restrict__ pos, int C, int S,
+                               long long piece_stride, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[64][33];
+    const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 64, bt = blockIdx.z;
+    const int t = threadIdx.x;
+    {
+        const int sl = t & 31, s = s0 + sl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int cl = (t >> 5) + 8 * i, c = c0 + cl;
+            float v = 0.f;
+            if (s < S && c < C) {
+                v = in[((long long)bt * C + c) * S + s];
+                if (pos != nullptr) v += __ldg(pos + (long long)c * S + s);
+            }
+            tile[cl][sl] = v;
+        }
+    }
+    __syncthreads();
+    const int sl = t >> 3, c8 = (t & 7) * 8, s = s0 + sl;
+    if (s >= S || c0 + c8 >= C) return;      // C % 8 == 0 is checked by the host
+    __align__(16) __nv_bfloat16 p[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3(tile[c8 + j][sl], p[0][j], p[1][j], p[2][j]);
+    __nv_bfloat16* o = out + ((long long)bt * S + s) * C + c0 + c8;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(o + k * piece_stride) = *reinterpret_cast<const uint4*>(p[k]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
@@ -391,6 +424,18 @@ extern "C" int racf_split_bf16x3(const float* x, long long count, void* out3, ra
     const long long threads = (count + 3) / 4;
     split_bf16x3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, count, static_cast<__nv_bfloat16*>(out3));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int racf_split_bf16x3_chw_to_hwc(const float* in, const float* pos, int batch, int channels, int positions,
+                                            void* out3, racf_stream_t stream) {
+    using namespace racf;
+    if (!in || !out3) return RACF_ERR_NULL_POINTER;
+    if (batch <= 0 || channels <= 0 || positions <= 0 || batch > 65535) return RACF_ERR_BAD_SHAPE;
+    if ((channels & 7) != 0 || (reinterpret_cast<uintptr_t>(out3) & 15u)) return RACF_ERR_UNSUPPORTED;
+    const dim3 grid((unsigned)((positions + 31) / 32), (unsigned)((channels + 63) / 64), (unsigned)batch);
+    split_bf16x3_chw_to_hwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, pos, channels, positions, (long long)batch * positions * channels, static_cast<__nv_bfloat16*>(out3));
     return (int)cudaGetLastError();
 }
 

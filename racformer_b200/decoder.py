@@ -352,9 +352,24 @@ class BEVSelfAttention(nn.Module):
         if self.queue_weight:
             _xavier_uniform(self.bev_queue_weight)
 
-    def project_value(self, bev):
-        """[B,T,C,H,W] -> value [B*T, H*W, heads, C/heads] (bev_self_attention.py:162-174). Query-independent."""
+    tensor_core_value_proj = True     # inference on CUDA: csrc/linear.cu (see AdaptiveMixing.gemm_precision)
+
+    def project_value(self, bev, pos=None):
+        """([B,T,C,H,W] + pos [C,H,W]) -> value [B*T, H*W, heads, C/heads] (bev_self_attention.py:162-174).
+        Query-independent. Inference on CUDA: the add, the permute + copy and the operand split are one kernel and the
+        projection (with its bias) runs on the tcgen05 Linear kernel; otherwise the PyTorch ops of the reference."""
         B, T, C = bev.shape[:3]
+        if (self.tensor_core_value_proj and not torch.is_grad_enabled() and bev.is_cuda and bev.dtype == torch.float32
+                and C % 8 == 0 and (pos is None or pos.numel() == bev[0, 0].numel())):
+            from . import linear
+            if getattr(self, "_split_value_proj", None) is None:
+                self._split_value_proj = linear.SplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
+            x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(),
+                                                None if pos is None else pos.reshape(C, -1).contiguous())
+            v = self._split_value_proj(x3=x3)
+            return v.reshape(B * T, x3.shape[1] // (B * T), self.num_heads, -1)
+        if pos is not None:
+            bev = bev + pos.view(1, 1, C, *bev.shape[3:])
         v = self.value_proj(bev.reshape(B * T, C, -1).permute(0, 2, 1))
         return v.reshape(B * T, v.shape[1], self.num_heads, -1)
 
@@ -479,6 +494,8 @@ class BEVSampling(nn.Module):
             bev_feats = self.temporal_encoder(bev_feats)
         B, T, C, H, W = bev_feats.shape
         pos = self.positional_encoding(B, H, W, bev_feats.device).to(bev_feats.dtype)
+        if B == 1:
+            return self.attention.project_value(bev_feats, pos.reshape(C, H, W)), (H, W)
         return self.attention.project_value(bev_feats + pos.view(B, 1, C, H, W)), (H, W)
 
     def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region):
@@ -641,8 +658,7 @@ class AdaptiveMixing(nn.Module):
                                                params.reshape(B * Q * G, -1).contiguous(), self.out_points, split=split)
             if core is not None:
                 if split:
-                    proj = self._split_linear("out_proj")(query, x3=core.reshape(3, B * Q, -1))
-                    return query + proj.reshape(B, Q, -1)
+                    return query + self._split_linear("out_proj")(x3=core.reshape(3, B * Q, -1), lead=(B, Q))
                 return query + self._project(core.reshape(B, Q, -1))
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)

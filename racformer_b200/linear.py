@@ -34,6 +34,25 @@ def split_bf16x3(x):
     return out
 
 
+def split_bf16x3_chw_to_hwc(x, pos=None):
+    """x [BT, C, S] fp32 (+ pos [C, S], broadcast over BT) -> bf16 pieces [3, BT * S, C] of the channel-last sum: the add,
+    permute and copy in front of BEVSelfAttention.value_proj fused with the operand split."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3):
+        raise RuntimeError("split_bf16x3_chw_to_hwc needs a contiguous fp32 CUDA tensor [BT, C, S]")
+    BT, C, S = x.shape
+    if pos is not None and not (pos.is_cuda and pos.dtype == torch.float32 and pos.is_contiguous()
+                                and pos.numel() == C * S and pos.device == x.device):
+        raise RuntimeError("split_bf16x3_chw_to_hwc: pos must be a contiguous fp32 CUDA tensor of C * S elements")
+    if C % 8 != 0:
+        raise RuntimeError("split_bf16x3_chw_to_hwc: channels must be a multiple of 8")
+    out = torch.empty((3, BT * S, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_split_bf16x3_chw_to_hwc(x.data_ptr(), pos.data_ptr() if pos is not None else None, BT, C, S,
+                                                      out.data_ptr(), _stream(x.device))
+    _lib.check(rc, "racf_split_bf16x3_chw_to_hwc")
+    return out
+
+
 def plan(M, N, K):
     """-> (split_k, workspace_bytes) the library wants for this problem."""
     s, w = ctypes.c_int(0), ctypes.c_longlong(0)
@@ -83,11 +102,13 @@ class SplitLinear:
             self._key = key
         return self._w3
 
-    def __call__(self, x, x3=None):
-        """x [..., K] fp32 (or its pieces x3 [3, rows, K]) -> [..., N] fp32."""
-        lead = x.shape[:-1]
+    def __call__(self, x=None, x3=None, lead=None):
+        """x [..., K] fp32, or its pieces x3 [3, rows, K] with the leading shape `lead` of the result -> [..., N] fp32."""
         if x3 is None:
+            lead = x.shape[:-1]
             x3 = split_bf16x3(x.reshape(-1, x.shape[-1]).contiguous())
+        elif lead is None:
+            lead = (x3.shape[1],)
         bias = self.linear.bias.detach() if self.linear.bias is not None else None
         y = linear_bf16x3(x3, self.weight_pieces(), bias, self.max_order, variant=self.variant)
         return y.reshape(*lead, -1)

@@ -145,3 +145,29 @@ def test_linear_python_layer_rejects_bad_inputs():
         linear.split_bf16x3(torch.zeros(8, 16))                        # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         linear.linear_bf16x3(a3, a3, bias=torch.zeros(3, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_chw_to_hwc_split_and_tensor_core_value_proj():
+    """racf_split_bf16x3_chw_to_hwc == split(permute(x + pos)) exactly, and BEVSelfAttention.project_value on the
+    tensor-core path equals the reference's add / permute / F.linear chain (models/bev_self_attention.py:162-174)."""
+    from racformer_b200 import linear
+    from racformer_b200.decoder import BEVSelfAttention
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(3, 40, 50, device="cuda", generator=g)
+    pos = torch.rand(40, 50, device="cuda", generator=g)
+    p = linear.split_bf16x3_chw_to_hwc(x, pos)
+    assert p.shape == (3, 150, 40)
+    assert torch.equal(p.double().sum(0), (x + pos).permute(0, 2, 1).reshape(150, 40).double())
+    assert torch.equal(linear.split_bf16x3_chw_to_hwc(x).double().sum(0), x.permute(0, 2, 1).reshape(150, 40).double())
+
+    attn = BEVSelfAttention(embed_dims=64, num_heads=4, num_levels=1, num_points=4, num_bev_queue=2).cuda().eval()
+    bev = torch.randn(1, 2, 64, 9, 13, device="cuda", generator=g)
+    pos = torch.rand(64, 9, 13, device="cuda", generator=g)
+    with torch.no_grad():
+        fast = attn.project_value(bev, pos)
+        attn.tensor_core_value_proj = False
+        slow = attn.project_value(bev, pos)
+    assert fast.shape == slow.shape == (2, 117, 4, 16)
+    torch.testing.assert_close(fast, slow, rtol=1e-5, atol=1e-5)
+    assert attn._split_value_proj is not None
