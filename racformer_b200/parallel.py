@@ -14,6 +14,31 @@ def env_rank_world():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, BEFORE any pinned host buffer is allocated, so the
+    staging memory of the end-to-end path is first-touched on the GPU's NUMA node and eight ranks do not funnel their
+    host-to-device traffic through one socket. Best effort: returns the CPU list or None (no NVML, containers that hide
+    the topology, affinity not permitted)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def init_distributed(backend=None):
     """Initialise the default process group from the torchrun environment. Returns (rank, world, device)."""
     rank, world, local_rank = env_rank_world()
@@ -21,6 +46,8 @@ def init_distributed(backend=None):
     device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
     if use_cuda:
         torch.cuda.set_device(device)
+        if world > 1 and os.environ.get("RACF_NUMA_BIND", "1") != "0":
+            bind_to_gpu_numa_node(local_rank)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
