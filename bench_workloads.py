@@ -280,9 +280,10 @@ class DecoderWorkload:
         self.inp = make_decoder_inputs(seed=100 + seed, device=self.device, num_cams=num_cams)
         # our kernels per step: per iteration 1 MSMV + 2 MSDA + 1 + 2 fused point-generation kernels + 1 fused mixing
         # core, plus one channel-last re-layout launch per FPN level
-        # with the tcgen05 Linear layers also: 1 operand split + 1 GEMM (parameter_generator), 1 GEMM + 1 split-K reduce
-        # (out_proj) per iteration
-        self.launches_per_step = (11 if mixing_precision.startswith("bf16") else 7) * num_layers + 4
+        # with the tcgen05 Linear layers also, per iteration: 1 operand split + 1 GEMM (parameter_generator), 1 GEMM + 1
+        # split-K reduce (out_proj), 1 operand split + 1 stacked-heads GEMM; per sample: 2 x (split + GEMM) for value_proj
+        tc = mixing_precision.startswith("bf16")
+        self.launches_per_step = (13 if tc else 7) * num_layers + (8 if tc else 4)
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None

@@ -236,6 +236,19 @@ int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias
                                racf_stream_t stream);
 
 /*
+ * Several Linear layers that share one input (the sampling heads of a decoder iteration all read the same query
+ * features: sampling_offset / scale_weights / ray_points_offset of RaCFormerSampling and the two BEVSampling branches,
+ * bev_queue_weight; models/racformer_transformer.py:361-366,493-496, models/bev_self_attention.py:193) in ONE launch:
+ * out_i[M, seg_n[i]] = a . w_i^T + bias_i. w3 is [3][sum_i pad128(seg_n[i])][K]: the bf16 pieces of the weights stacked
+ * along N, each layer padded with zero rows to a multiple of 128. K <= 512, num_segments <= RACF_LINEAR_MAX_SEGMENTS.
+ * seg_n / seg_bias / seg_out are HOST arrays (of device pointers); seg_bias or its entries may be NULL.
+ */
+#define RACF_LINEAR_MAX_SEGMENTS 16
+int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int K, int num_segments,
+                                     const int* seg_n, const float* const* seg_bias, float* const* seg_out,
+                                     int max_order, racf_stream_t stream);
+
+/*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
  * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
  * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.

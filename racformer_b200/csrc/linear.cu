@@ -125,6 +125,13 @@ struct LinArgs {
     int num_kblocks;        // ceil(K / BK)
     int kblocks_per_split;
     int max_order;          // accumulate a_i * w_j for i + j <= max_order (4 = all nine terms)
+    // Several Linear layers that share the input (racf_linear_bf16x3_multi_forward): their weights are stacked along N,
+    // each padded with zero rows to a multiple of 128, and every layer has its own dense output and bias.
+    int num_segments;       // 0 = one layer (the fields above)
+    int seg_tile_start[RACF_LINEAR_MAX_SEGMENTS + 1];
+    int seg_n[RACF_LINEAR_MAX_SEGMENTS];
+    float* seg_out[RACF_LINEAR_MAX_SEGMENTS];
+    const float* seg_bias[RACF_LINEAR_MAX_SEGMENTS];
 };
 
 template <int kBK, int kStages>
@@ -252,28 +259,37 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     const int num_splits = gridDim.x / (args.m_tiles * args.n_tiles);
     float* outp = args.out + (long long)split * args.M * args.N;
-    const int gn = n0 + lane * 4;
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (args.bias != nullptr && num_splits == 1) {
-        if (gn + 0 < args.N) b4.x = __ldg(args.bias + gn + 0);
-        if (gn + 1 < args.N) b4.y = __ldg(args.bias + gn + 1);
-        if (gn + 2 < args.N) b4.z = __ldg(args.bias + gn + 2);
-        if (gn + 3 < args.N) b4.w = __ldg(args.bias + gn + 3);
+    const float* biasp = num_splits == 1 ? args.bias : nullptr;
+    int N = args.N, gn = n0 + lane * 4;
+    if (args.num_segments > 0) {     // which stacked layer does this column tile belong to?
+        int sg = 0;
+        while (sg + 1 < args.num_segments && n_tile >= args.seg_tile_start[sg + 1]) ++sg;
+        outp = args.seg_out[sg];
+        biasp = args.seg_bias[sg];
+        N = args.seg_n[sg];
+        gn = (n_tile - args.seg_tile_start[sg]) * kLinBN + lane * 4;
     }
-    const bool vec_ok = (args.N & 3) == 0 && gn + 3 < args.N;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (biasp != nullptr) {
+        if (gn + 0 < N) b4.x = __ldg(biasp + gn + 0);
+        if (gn + 1 < N) b4.y = __ldg(biasp + gn + 1);
+        if (gn + 2 < N) b4.z = __ldg(biasp + gn + 2);
+        if (gn + 3 < N) b4.w = __ldg(biasp + gn + 3);
+    }
+    const bool vec_ok = (N & 3) == 0 && gn + 3 < N;
     for (int r = 0; r < 32; ++r) {
         const int gm = m0 + warp * 32 + r;
-        if (gm >= args.M) break;
+        if (gm >= args.M || gn >= N) break;
         float4 o = *reinterpret_cast<const float4*>(stg + (warp * 32 + r) * kLinStgStride + lane * 4);
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-        float* dst = outp + (long long)gm * args.N + gn;
+        float* dst = outp + (long long)gm * N + gn;
         if (vec_ok) {
             *reinterpret_cast<float4*>(dst) = o;
         } else {
-            if (gn + 0 < args.N) dst[0] = o.x;
-            if (gn + 1 < args.N) dst[1] = o.y;
-            if (gn + 2 < args.N) dst[2] = o.z;
-            if (gn + 3 < args.N) dst[3] = o.w;
+            if (gn + 0 < N) dst[0] = o.x;
+            if (gn + 1 < N) dst[1] = o.y;
+            if (gn + 2 < N) dst[2] = o.z;
+            if (gn + 3 < N) dst[3] = o.w;
         }
     }
 
@@ -472,6 +488,7 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
     if (rc != 0) return rc;
 
     LinArgs args;
+    args.num_segments = 0;
     args.bias = bias;
     args.out = split_k > 1 ? workspace : out;
     args.M = M; args.N = N;
@@ -491,4 +508,47 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
         return (int)cudaGetLastError();
     }
     return RACF_OK;
+}
+
+extern "C" int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int K, int num_segments,
+                                                const int* seg_n, const float* const* seg_bias, float* const* seg_out,
+                                                int max_order, racf_stream_t stream) {
+    using namespace racf;
+    if (!a3 || !w3 || !seg_n || !seg_out) return RACF_ERR_NULL_POINTER;
+    if (M <= 0 || K <= 0 || num_segments <= 0) return RACF_ERR_BAD_SHAPE;
+    if (num_segments > RACF_LINEAR_MAX_SEGMENTS || (K & 7) != 0 || K > 512 || max_order < 0 || max_order > 4)
+        return RACF_ERR_UNSUPPORTED;    // K <= 512: one accumulator pass, no K split
+    if ((reinterpret_cast<uintptr_t>(a3) | reinterpret_cast<uintptr_t>(w3)) & 15u) return RACF_ERR_UNSUPPORTED;
+    LinArgs args;
+    args.bias = nullptr;
+    args.out = nullptr;
+    args.M = M;
+    args.num_segments = num_segments;
+    int tiles = 0;
+    for (int i = 0; i < num_segments; ++i) {
+        if (seg_n[i] <= 0) return RACF_ERR_BAD_SHAPE;
+        if (!seg_out[i]) return RACF_ERR_NULL_POINTER;
+        if ((reinterpret_cast<uintptr_t>(seg_out[i]) & 15u) && (seg_n[i] & 3) == 0) return RACF_ERR_UNSUPPORTED;
+        args.seg_tile_start[i] = tiles;
+        args.seg_n[i] = seg_n[i];
+        args.seg_out[i] = seg_out[i];
+        args.seg_bias[i] = seg_bias ? seg_bias[i] : nullptr;
+        tiles += (seg_n[i] + kLinBN - 1) / kLinBN;
+    }
+    args.seg_tile_start[num_segments] = tiles;
+    for (int i = num_segments; i < RACF_LINEAR_MAX_SEGMENTS; ++i) {
+        args.seg_tile_start[i + 1] = tiles; args.seg_n[i] = 0; args.seg_out[i] = nullptr; args.seg_bias[i] = nullptr;
+    }
+    args.N = tiles * kLinBN;                  // rows of the stacked, padded weight
+    args.m_tiles = (M + kLinBM - 1) / kLinBM;
+    args.n_tiles = tiles;
+    args.num_kblocks = (K + 31) / 32;
+    args.kblocks_per_split = args.num_kblocks;
+    args.max_order = max_order;
+    CUtensorMap ma, mw;
+    int rc = make_operand_map(&ma, a3, M, K, 32);
+    if (rc != 0) return rc;
+    rc = make_operand_map(&mw, w3, args.N, K, 32);
+    if (rc != 0) return rc;
+    return launch_linear<32, 2>(ma, mw, args, 1, static_cast<cudaStream_t>(stream));
 }

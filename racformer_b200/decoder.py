@@ -294,14 +294,16 @@ class RaCFormerSampling(nn.Module):
         nn.init.zeros_(self.sampling_offset.weight)
         nn.init.uniform_(self.sampling_offset.bias, -0.5, 0.5)
 
-    def inner_forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region):
+    def inner_forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region, heads=None):
         B, Q, _ = query_ray.shape
         T, G, Pn, D, pr = self.num_frames, self.num_groups, self.num_points, self.depth_num, self.pc_range
         if _use_fused_points(self, query_ray, query_feat, meta["lidar2img"]):
             from . import points   # one kernel instead of the ~150 PyTorch launches below
+            off, ray, sw = heads if heads is not None else (self.sampling_offset(query_feat),
+                                                            self.ray_points_offset(query_feat),
+                                                            self.scale_weights(query_feat))
             loc, w = points.msmv_points(
-                query_ray.contiguous(), self.sampling_offset(query_feat), self.ray_points_offset(query_feat),
-                self.scale_weights(query_feat), meta["time_diff"], meta["lidar2img"],
+                query_ray.contiguous(), off, ray, sw, meta["time_diff"], meta["lidar2img"],
                 _depth_base(d_region, D, query_feat.device), pr, d_region, meta["image_w"], meta["image_h"],
                 T, G, Pn, D, self.num_levels)
             if getattr(ops, "msmv_grouped", None) is not None:
@@ -326,8 +328,8 @@ class RaCFormerSampling(nn.Module):
         w = torch.softmax(w, dim=-1)
         return sampling_4d(ops, pts, mlvl_feats, w, meta["lidar2img"], meta["image_h"], meta["image_w"])
 
-    def forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region=0.1):
-        fn = lambda qr, qf, *feats: self.inner_forward(ops, qr, qf, list(feats), meta, d_region)
+    def forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region=0.1, heads=None):
+        fn = lambda qr, qf, *feats: self.inner_forward(ops, qr, qf, list(feats), meta, d_region, heads)
         return _maybe_checkpoint(self, fn, query_ray, query_feat, *mlvl_feats)
 
 
@@ -380,8 +382,9 @@ class BEVSelfAttention(nn.Module):
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
         return self.attend(ops, query, value, loc, aw, spatial_shapes)
 
-    def attend(self, ops, query, value, loc, aw, spatial_shapes):
-        """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing."""
+    def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None):
+        """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing; queue_logits: bev_queue_weight(query)
+        when the caller has already computed it (the decoder layer's stacked head launch)."""
         B, Q, C = query.shape
         T = self.num_bev_queue
         shapes = _const_long((tuple(int(v) for v in spatial_shapes),), value.device)
@@ -389,7 +392,8 @@ class BEVSelfAttention(nn.Module):
         out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
         out = out.permute(1, 2, 0).reshape(Q, C, B, T)
         if self.queue_weight:
-            qw = torch.softmax(self.bev_queue_weight(query).permute(1, 0, 2).reshape(Q, 1, B, T), dim=-1)
+            logits = queue_logits if queue_logits is not None else self.bev_queue_weight(query)
+            qw = torch.softmax(logits.permute(1, 0, 2).reshape(Q, 1, B, T), dim=-1)
             out = torch.sum(out * qw, dim=-1)
         else:
             out = torch.sum(out, dim=-1) / T
@@ -498,16 +502,17 @@ class BEVSampling(nn.Module):
             return self.attention.project_value(bev_feats, pos.reshape(C, H, W)), (H, W)
         return self.attention.project_value(bev_feats + pos.view(B, 1, C, H, W)), (H, W)
 
-    def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region):
+    def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region, heads=None):
         B, Q, _ = query_ray.shape
         T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
         if self.num_levels == 1 and _use_fused_points(self, query_ray, query_feat, value):
             from . import points
-            loc, aw = points.bev_points(
-                query_ray.contiguous(), self.sampling_offset(query_feat), self.ray_points_offset(query_feat),
-                self.scale_weights(query_feat), meta["time_diff"], _depth_base(d_region, D, query_feat.device), pr,
-                d_region, T, M, Pn, D)
-            return self.attention.attend(ops, query_feat, value, loc, aw, hw)
+            off, ray, sw, qw = heads if heads is not None else (self.sampling_offset(query_feat),
+                                                                self.ray_points_offset(query_feat),
+                                                                self.scale_weights(query_feat), None)
+            loc, aw = points.bev_points(query_ray.contiguous(), off, ray, sw, meta["time_diff"],
+                                        _depth_base(d_region, D, query_feat.device), pr, d_region, T, M, Pn, D)
+            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw)
         query_bbox = theta_d2xy_coods(query_ray)
         offset = self.sampling_offset(query_feat).view(B, Q, M * Pn * D, 2)
         offset = torch.cat([offset, torch.zeros_like(offset[..., 0:1])], dim=-1)
@@ -523,10 +528,10 @@ class BEVSampling(nn.Module):
         w = torch.softmax(w, dim=-1).expand(B, Q, M, T, self.num_levels, D * Pn).contiguous()
         return self.attention(ops, query_feat, value, loc, w, hw)
 
-    def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None):
+    def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None, heads=None):
         def fn(qr, qf, bev):
             value, hw = prepared if prepared is not None else self.prepare_value(bev)
-            return self.sample(ops, qr, qf, value, hw, meta, d_region)
+            return self.sample(ops, qr, qf, value, hw, meta, d_region, heads)
         return _maybe_checkpoint(self, fn, query_ray, query_feat, bev_feats)
 
 
@@ -729,6 +734,28 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         nn.init.constant_(self.cls_branch[-1].bias, float(-math.log((1 - 0.01) / 0.01)))
         _xavier_uniform(self.fusion)
 
+    stacked_heads = True    # inference on CUDA: the 11 sampling heads that read query_feat run as one tcgen05 launch
+
+    def _sampling_heads(self, query_feat):
+        """sampling_offset / ray_points_offset / scale_weights (/ bev_queue_weight) of the radar-BEV, LSS-BEV and image
+        samplers all read the same query features: one stacked Linear launch (csrc/linear.cu) instead of 11 small SGEMMs
+        with separate bias kernels. Returns (radar 4, lss 4, image 3) or None when the fused point kernels are not in use."""
+        radar, lss, img = self.sampling_radar_bev, self.sampling_lss_bev, self.sampling
+        if (not self.stacked_heads or torch.is_grad_enabled() or not query_feat.is_cuda or query_feat.dtype != torch.float32
+                or self.embed_dims % 8 != 0 or self.embed_dims > 512 or radar.num_levels != 1 or lss.num_levels != 1
+                or not all(getattr(m, "fused_points", True) for m in (radar, lss, img))
+                or not (radar.attention.queue_weight and lss.attention.queue_weight)):
+            return None
+        if getattr(self, "_heads", None) is None:
+            from . import linear
+            self._heads = linear.MultiSplitLinear(
+                [radar.sampling_offset, radar.ray_points_offset, radar.scale_weights, radar.attention.bev_queue_weight,
+                 lss.sampling_offset, lss.ray_points_offset, lss.scale_weights, lss.attention.bev_queue_weight,
+                 img.sampling_offset, img.ray_points_offset, img.scale_weights])
+        B, Q, _ = query_feat.shape
+        outs = [o.view(B, Q, -1) for o in self._heads(query_feat)]
+        return outs[0:4], outs[4:8], outs[8:11]
+
     def refine_bbox(self, proposal, delta):
         dz = torch.sigmoid(delta[..., 1:3] + inverse_sigmoid(proposal[..., 1:3]))
         theta = proposal[..., 0:1] + (torch.sigmoid(delta[..., 0:1]) * 2 - 1) / self.num_ray
@@ -740,11 +767,12 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
         query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
+        heads = self._sampling_heads(query_feat) or (None, None, None)
         radar = self.norm_radar_bev(self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta,
-                                                            d_region=d_region, prepared=prep_radar))
+                                                            d_region=d_region, prepared=prep_radar, heads=heads[0]))
         lss = self.norm_lss_bev(self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta,
-                                                      d_region=d_region, prepared=prep_lss))
-        sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region)
+                                                      d_region=d_region, prepared=prep_lss, heads=heads[1]))
+        sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region, heads=heads[2])
         query_feat = self.norm2(self.mixing(sampled, query_feat))
         query_feat = self.norm_fusion(self.fusion(torch.cat((query_feat, radar, lss), dim=-1)))
         query_feat = self.norm3(self.ffn(query_feat))
@@ -848,9 +876,14 @@ class RaCFormerTransformer(nn.Module):
         """"bf16x6" (default) / "bf16x9": tcgen05 kernel with exact bf16 operand splitting (fp32-grade, csrc/linear.cu);
         "fp32": cuBLAS SGEMM like the reference; "tf32x3": opt-in cuBLAS TF32 operand split (see _SplitTF32Linear)."""
         assert precision in ("fp32", "tf32x3", "bf16x6", "bf16x9")
+        tensor_core = precision.startswith("bf16")
         for m in self.modules():
             if isinstance(m, AdaptiveMixing):
                 m.gemm_precision = precision
+            elif isinstance(m, BEVSelfAttention):            # value_proj and the stacked sampling heads follow
+                m.tensor_core_value_proj = tensor_core
+            elif isinstance(m, RaCFormerTransformerDecoderLayer):
+                m.stacked_heads = tensor_core
 
     def set_activation_checkpoint(self, enabled):
         for m in self.modules():

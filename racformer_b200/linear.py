@@ -112,3 +112,49 @@ class SplitLinear:
         bias = self.linear.bias.detach() if self.linear.bias is not None else None
         y = linear_bf16x3(x3, self.weight_pieces(), bias, self.max_order, variant=self.variant)
         return y.reshape(*lead, -1)
+
+
+class MultiSplitLinear:
+    """Several nn.Linear layers applied to the SAME input in one tcgen05 launch (racf_linear_bf16x3_multi_forward):
+    their weights are stacked along N (each padded with zero rows to a multiple of 128) and split once; every layer gets
+    its own dense output. Inference only."""
+
+    MAX_SEGMENTS = 16
+
+    def __init__(self, linears, max_order=SIX_TERMS):
+        self.linears, self.max_order = list(linears), max_order
+        if not 0 < len(self.linears) <= self.MAX_SEGMENTS:
+            raise RuntimeError("MultiSplitLinear: 1..16 layers")
+        k = {lin.in_features for lin in self.linears}
+        if len(k) != 1 or next(iter(k)) % 8 != 0 or next(iter(k)) > 512:
+            raise RuntimeError("MultiSplitLinear: the layers must share in_features (a multiple of 8, at most 512)")
+        self._key, self._w3 = None, None
+
+    def weight_pieces(self):
+        key = tuple((lin.weight.data_ptr(), lin.weight._version) for lin in self.linears)
+        if self._key != key:
+            rows = []
+            for lin in self.linears:
+                w = lin.weight.detach()
+                pad = (-w.shape[0]) % 128
+                rows.append(torch.cat([w, w.new_zeros(pad, w.shape[1])]) if pad else w)
+            self._w3 = split_bf16x3(torch.cat(rows).contiguous())
+            self._key = key
+        return self._w3
+
+    def __call__(self, x=None, x3=None):
+        """x [..., K] (or its pieces x3 [3, rows, K]) -> list of [rows, N_i] fp32 tensors, one per layer."""
+        if x3 is None:
+            x3 = split_bf16x3(x.reshape(-1, x.shape[-1]).contiguous())
+        w3 = self.weight_pieces()
+        M, K = x3.shape[1], x3.shape[2]
+        n = len(self.linears)
+        outs = [torch.empty((M, lin.out_features), dtype=torch.float32, device=x3.device) for lin in self.linears]
+        seg_n = (ctypes.c_int * n)(*[lin.out_features for lin in self.linears])
+        seg_bias = (ctypes.c_void_p * n)(*[lin.bias.data_ptr() if lin.bias is not None else None for lin in self.linears])
+        seg_out = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(x3.device):
+            rc = _lib.load().racf_linear_bf16x3_multi_forward(x3.data_ptr(), w3.data_ptr(), M, K, n, seg_n, seg_bias, seg_out,
+                                                              int(self.max_order), _stream(x3.device))
+        _lib.check(rc, "racf_linear_bf16x3_multi_forward")
+        return outs

@@ -171,3 +171,27 @@ def test_chw_to_hwc_split_and_tensor_core_value_proj():
     assert fast.shape == slow.shape == (2, 117, 4, 16)
     torch.testing.assert_close(fast, slow, rtol=1e-5, atol=1e-5)
     assert attn._split_value_proj is not None
+
+
+@pytest.mark.gpu
+def test_multi_linear_equals_the_separate_layers():
+    """racf_linear_bf16x3_multi_forward: the sampling heads that share the query features, one launch, each output
+    dense in its own tensor -- equal to the per-layer tensor-core results bit for bit, and to F.linear to fp32 noise."""
+    from racformer_b200 import linear
+    torch.manual_seed(4)
+    sizes = [160, 5, 80, 8, 144, 3, 1536, 256]
+    lins = [torch.nn.Linear(256, n, device="cuda") for n in sizes]
+    lins[3].bias = None
+    x = torch.randn(2, 450, 256, device="cuda")
+    with torch.no_grad():
+        multi = linear.MultiSplitLinear(lins)
+        outs = multi(x)
+        assert [tuple(o.shape) for o in outs] == [(900, n) for n in sizes]
+        for lin, o in zip(lins, outs):
+            single = linear.SplitLinear(lin, max_order=linear.SIX_TERMS)(x).reshape(900, -1)
+            assert torch.equal(o, single)
+            torch.testing.assert_close(o, lin(x).reshape(900, -1), rtol=1e-5, atol=1e-5)
+        lins[1].weight.add_(1.0)              # the stacked weight is rebuilt when any layer changes
+        torch.testing.assert_close(multi(x)[1], lins[1](x).reshape(900, -1), rtol=1e-5, atol=2e-5)
+    with pytest.raises(RuntimeError):
+        linear.MultiSplitLinear([torch.nn.Linear(256, 8), torch.nn.Linear(128, 8)])
