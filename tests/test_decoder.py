@@ -291,7 +291,14 @@ def test_decoder_full_f8_size_cuda_path_vs_cpu_reference_path():
         cls, box = GraphedDecoderForward(gpu_model, dg)()
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    # fp32 end to end; a handful of the 345 600 x 2 sample points sit within an ulp of an image border or a cell edge,
-    # which moves a few query outputs by more than rounding noise -> small outlier allowance
-    _close(cls, ref_cls, "f8 cls CUDA path vs CPU reference path", rtol=1e-3, atol=1e-3, max_outlier_frac=2e-3)
-    _close(box, ref_box, "f8 box CUDA path vs CPU reference path", rtol=1e-3, atol=1e-3, max_outlier_frac=2e-3)
+    # fp32 end to end. The view selection and the in-image test of a sample point are discontinuous: a point within
+    # rounding noise of an image border flips, and then ALL outputs of that query move (by up to ~0.06), whichever fp32
+    # implementation of the dense layers produced the noise (profiles/r01_decoder_precision_diag.json: 3 such queries
+    # with cuBLAS SGEMM, 4 with the tensor-core Linear layers on this seed, 0 / 1 on another). So: at most 6 of the
+    # 2 x 900 (iteration, query) rows may contain an element outside rtol = atol = 1e-3, every other row is inside,
+    # and the typical difference is at rounding level.
+    for got, ref, what in ((cls, ref_cls, "cls"), (box, ref_box, "box")):
+        a, b = got.detach().cpu().double(), ref.detach().cpu().double()
+        bad_rows = ((a - b).abs() > 1e-3 + 1e-3 * b.abs()).any(-1)
+        assert int(bad_rows.sum()) <= 6, f"f8 {what}: {int(bad_rows.sum())} query rows differ, worst {float((a - b).abs().max()):.3g}"
+        assert float((a - b).abs().median()) < 5e-5, what
