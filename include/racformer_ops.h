@@ -208,8 +208,11 @@ int racf_adaptive_mixing_forward(const float* x, const float* params, int num_qu
                                  int out_points, int channels, float eps, float* out, racf_stream_t stream);
 /* Same, but the result is written as three bf16 pieces out3 [3][QG][out_points][C] with value == p0 + p1 + p2 exactly:
  * the A operand of racf_linear_bf16x3_forward (out_proj), without an fp32 round trip through HBM. */
+/* tiled_groups > 0: out3 is instead the pre-tiled A operand (racf_linear_tiled_bytes(QG / tiled_groups, tiled_groups *
+ * out_points * C) bytes) of a [QG / tiled_groups, tiled_groups * out_points * C] matrix, tiled_groups = n_groups. */
 int racf_adaptive_mixing_forward_split(const float* x, const float* params, int num_query_groups, int in_points,
-                                       int out_points, int channels, float eps, void* out3, racf_stream_t stream);
+                                       int out_points, int channels, float eps, void* out3, int tiled_groups,
+                                       racf_stream_t stream);
 
 /*
  * "next" row: AdaptiveMixing's two large Linear layers (parameter_generator and out_proj,
@@ -222,14 +225,24 @@ int racf_adaptive_mixing_forward_split(const float* x, const float* params, int 
  * racf_linear_bf16x3_forward: out[M,N] = a[M,K] . w[N,K]^T + bias[N] with a3 = split(a) [3][M][K], w3 = split(w)
  *   [3][N][K] (nn.Linear's weight layout), products a_i * w_j with i + j <= max_order accumulated in fp32 (4: all nine,
  *   2: six). bias may be NULL. K % 8 == 0. workspace: split_k * M * N floats when split_k > 1 (else may be NULL).
- *   variant: 0 = 32-wide K blocks / 64-byte swizzle / 2 stages, 1 = 64-wide / 128-byte swizzle / 1 stage.
+ *   variant: 0 = plain pieces through tensor maps, 32-wide K blocks / 64-byte swizzle / 2 stages; 1 = the same with
+ *   64-wide K blocks / 128-byte swizzle / 1 stage; 2 = a3 and w3 are in the tiled format (bulk copies, any K).
  */
 int racf_split_bf16x3(const float* x, long long count, void* out3, racf_stream_t stream);
 /* (in [batch][channels][positions] + pos [channels][positions] (may be NULL)) -> out3 [3][batch * positions][channels]:
  * the add, permute and copy in front of BEVSelfAttention.value_proj (models/bev_self_attention.py:162-174) fused with the
  * operand split; channels % 8 == 0. */
 int racf_split_bf16x3_chw_to_hwc(const float* in, const float* pos, int batch, int channels, int positions,
-                                 void* out3, racf_stream_t stream);
+                                 int tiled, void* out3, racf_stream_t stream);
+/*
+ * The kernel's preferred operand format ("tiled", variant 2 / tiled != 0 below): the three bf16 pieces cut into
+ * [128 rows][32 k] tiles stored in global memory as the shared-memory image the MMA reads (K-major, 64-byte swizzle),
+ * ordered [row tile][k block][piece], so that a pipeline stage is one contiguous 24 KB bulk copy
+ * (racformer_b200/csrc/linear_tiled.cuh). racf_linear_tiled_bytes: buffer size for a [rows][K] matrix;
+ * racf_split_bf16x3_tiled: fp32 [rows][K] row-major -> tiled pieces (any K; the K tail is zero-filled).
+ */
+long long racf_linear_tiled_bytes(long long rows, int K);
+int racf_split_bf16x3_tiled(const float* x, long long rows, int K, void* out, racf_stream_t stream);
 int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long long* workspace_bytes);
 int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
                                int max_order, int split_k, int variant, float* workspace, float* out,
@@ -246,7 +259,7 @@ int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias
 #define RACF_LINEAR_MAX_SEGMENTS 16
 int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int K, int num_segments,
                                      const int* seg_n, const float* const* seg_bias, float* const* seg_out,
-                                     int max_order, racf_stream_t stream);
+                                     int max_order, int tiled, racf_stream_t stream);
 
 /*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over

@@ -38,14 +38,16 @@ SIGNATURES = {
     "racf_bev_pool_v2_backward": (_i, [_c_float_p] * 8 + [_i, _i, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_adaptive_mixing_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
     "racf_adaptive_mixing_forward_split": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, ctypes.c_void_p,
-                                                ctypes.c_void_p]),
+                                                _i, ctypes.c_void_p]),
+    "racf_linear_tiled_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _i]),
+    "racf_split_bf16x3_tiled": (_i, [_c_float_p, ctypes.c_longlong, _i, ctypes.c_void_p, ctypes.c_void_p]),
     "racf_split_bf16x3": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]),
-    "racf_split_bf16x3_chw_to_hwc": (_i, [_c_float_p, _c_float_p, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
+    "racf_split_bf16x3_chw_to_hwc": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
     "racf_linear_bf16x3_plan": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_longlong)]),
     "racf_linear_bf16x3_forward": (_i, [ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, _i, _c_float_p,
                                         _c_float_p, ctypes.c_void_p]),
     "racf_linear_bf16x3_multi_forward": (_i, [ctypes.c_void_p, ctypes.c_void_p, _i, _i, _i, ctypes.POINTER(_i),
-                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _i,
+                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _i, _i,
                                               ctypes.c_void_p]),
     "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bench_scatter_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),

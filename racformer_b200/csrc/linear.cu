@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "linear_tiled.cuh"
 #include "racformer_ops.h"
 
 namespace racf {
@@ -68,6 +69,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// 1-D bulk copy (TMA engine, no tensor map): `bytes` contiguous bytes, 16-byte aligned on both sides
+__device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -125,6 +131,8 @@ struct LinArgs {
     int num_kblocks;        // ceil(K / BK)
     int kblocks_per_split;
     int max_order;          // accumulate a_i * w_j for i + j <= max_order (4 = all nine terms)
+    const uint8_t* a_tiled; // operands in the pre-tiled format of linear_tiled.cuh (kTiled kernels), else nullptr
+    const uint8_t* w_tiled;
     // Several Linear layers that share the input (racf_linear_bf16x3_multi_forward): their weights are stacked along N,
     // each padded with zero rows to a multiple of 128, and every layer has its own dense output and bias.
     int num_segments;       // 0 = one layer (the fields above)
@@ -134,7 +142,7 @@ struct LinArgs {
     const float* seg_bias[RACF_LINEAR_MAX_SEGMENTS];
 };
 
-template <int kBK, int kStages>
+template <int kBK, int kStages, bool kTiled>
 __global__ void __launch_bounds__(kLinThreads, 2)
 linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const LinArgs args) {
     constexpr int kRowBytes = kBK * 2;
@@ -162,7 +170,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     auto empty_bar = [&](int s) { return smem_u32(&bars[kStages + s]); };
     const uint32_t tmem_full_bar = smem_u32(&bars[2 * kStages]);
 
-    if (warp == 0 && lane == 0) {
+    if (!kTiled && warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     }
@@ -188,9 +196,18 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             mbar_wait(empty_bar(s), ((i / kStages) & 1) ^ 1);
             mbar_arrive_expect_tx(full_bar(s), kStageBytes);
             const uint32_t dst = smem_base + s * kStageBytes;
-            const int k0 = (kb_begin + i) * kBK;
-            tma_load_3d(dst, &map_a, k0, m0, 0, full_bar(s));
-            tma_load_3d(dst + 3 * kPieceBytes, &map_w, k0, n0, 0, full_bar(s));
+            if constexpr (kTiled) {     // one contiguous 24 KB block per operand and stage
+                static_assert(!kTiled || (kBK == kTileK && 3 * kPieceBytes == kTileStageBytes), "tiled format is BK = 32");
+                const long long kb = kb_begin + i;
+                tma_load_bulk(dst, args.a_tiled + ((long long)m_tile * args.num_kblocks + kb) * kTileStageBytes,
+                              kTileStageBytes, full_bar(s));
+                tma_load_bulk(dst + 3 * kPieceBytes, args.w_tiled + ((long long)n_tile * args.num_kblocks + kb) * kTileStageBytes,
+                              kTileStageBytes, full_bar(s));
+            } else {
+                const int k0 = (kb_begin + i) * kBK;
+                tma_load_3d(dst, &map_a, k0, m0, 0, full_bar(s));
+                tma_load_3d(dst + 3 * kPieceBytes, &map_w, k0, n0, 0, full_bar(s));
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
@@ -353,12 +370,32 @@ split_bf16x3_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __r
     }
 }
 
+// x [rows][K] fp32 -> the pre-tiled pieces of linear_tiled.cuh; one thread per 16-byte chunk (8 k) of the padded domain
+__global__ void __launch_bounds__(256)
+split_bf16x3_tiled_kernel(const float* __restrict__ x, int rows, int K, int num_kblocks, long long num_chunks,
+                          __nv_bfloat16* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_chunks) return;
+    const int chunks_per_row = num_kblocks * 4;
+    const long long row = i / chunks_per_row;
+    const int k0 = (int)(i - row * chunks_per_row) * 8;
+    __align__(16) __nv_bfloat16 p[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v = (row < rows && k0 + j < K) ? x[row * K + k0 + j] : 0.f;
+        split3(v, p[0][j], p[1][j], p[2][j]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<uint4*>(out + tiled_offset(row, k0, num_kblocks, k)) = *reinterpret_cast<const uint4*>(p[k]);
+}
+
 // (in[bt][c][s] + pos[c][s]) -> bf16 pieces out3[piece][bt * S + s][c]: the channel-first BEV maps become the K-major A
 // operand of value_proj (models/bev_self_attention.py:162-174 does this with an add, a permute + copy and a GEMM whose
 // bias is added in a fourth pass). 64 channels x 32 positions per CTA through a padded shared-memory tile.
 __global__ void __launch_bounds__(256)
 split_bf16x3_chw_to_hwc_kernel(const float* __restrict__ in, const float* __restrict__ pos, int C, int S,
-                               long long piece_stride, __nv_bfloat16* __restrict__ out) {
+                               long long piece_stride, int tiled_kblocks, __nv_bfloat16* __restrict__ out) {
     __shared__ float tile[64][33];
     const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 64, bt = blockIdx.z;
     const int t = threadIdx.x;
@@ -377,13 +414,18 @@ split_bf16x3_chw_to_hwc_kernel(const float* __restrict__ in, const float* __rest
     }
     __syncthreads();
     const int sl = t >> 3, c8 = (t & 7) * 8, s = s0 + sl;
-    if (s >= S || c0 + c8 >= C) return;      // C % 8 == 0 is checked by the host
+    const int c_end = tiled_kblocks > 0 ? tiled_kblocks * kTileK : C;      // the tiled format zero-fills its K tail
+    if (s >= S || c0 + c8 >= c_end) return;                                // C % 8 == 0 is checked by the host
     __align__(16) __nv_bfloat16 p[3][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) split3(tile[c8 + j][sl], p[0][j], p[1][j], p[2][j]);
-    __nv_bfloat16* o = out + ((long long)bt * S + s) * C + c0 + c8;
+    const long long row = (long long)bt * S + s;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(o + k * piece_stride) = *reinterpret_cast<const uint4*>(p[k]);
+    for (int k = 0; k < 3; ++k) {
+        __nv_bfloat16* o = tiled_kblocks > 0 ? out + tiled_offset(row, c0 + c8, tiled_kblocks, k)
+                                             : out + row * C + c0 + c8 + k * piece_stride;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p[k]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -420,13 +462,13 @@ static int make_operand_map(CUtensorMap* map, const void* base, int rows, int K,
     return r == CUDA_SUCCESS ? 0 : RACF_ERR_BAD_SHAPE;
 }
 
-template <int kBK, int kStages>
+template <int kBK, int kStages, bool kTiled>
 static int launch_linear(const CUtensorMap& ma, const CUtensorMap& mw, const LinArgs& args, int num_splits, cudaStream_t st) {
     constexpr int smem = kStages * 6 * 128 * kBK * 2 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(linear_bf16x3_kernel<kBK, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(linear_bf16x3_kernel<kBK, kStages, kTiled>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     const unsigned grid = (unsigned)(args.m_tiles * args.n_tiles * num_splits);
-    linear_bf16x3_kernel<kBK, kStages><<<grid, kLinThreads, smem, st>>>(ma, mw, args);
+    linear_bf16x3_kernel<kBK, kStages, kTiled><<<grid, kLinThreads, smem, st>>>(ma, mw, args);
     return (int)cudaGetLastError();
 }
 
@@ -443,15 +485,36 @@ extern "C" int racf_split_bf16x3(const float* x, long long count, void* out3, ra
     return (int)cudaGetLastError();
 }
 
+extern "C" long long racf_linear_tiled_bytes(long long rows, int K) {
+    if (rows <= 0 || K <= 0) return 0;
+    return ((rows + racf::kTileRows - 1) / racf::kTileRows) * (long long)((K + racf::kTileK - 1) / racf::kTileK) * racf::kTileStageBytes;
+}
+
+extern "C" int racf_split_bf16x3_tiled(const float* x, long long rows, int K, void* out, racf_stream_t stream) {
+    using namespace racf;
+    if (!x || !out) return RACF_ERR_NULL_POINTER;
+    if (rows <= 0 || K <= 0) return RACF_ERR_BAD_SHAPE;
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return RACF_ERR_UNSUPPORTED;
+    const int num_kblocks = (K + kTileK - 1) / kTileK;
+    const long long rows_pad = (rows + kTileRows - 1) / kTileRows * kTileRows;
+    const long long chunks = rows_pad * num_kblocks * 4;
+    if ((chunks + 255) / 256 > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
+    split_bf16x3_tiled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, (int)rows, K, num_kblocks, chunks, static_cast<__nv_bfloat16*>(out));
+    return (int)cudaGetLastError();
+}
+
 extern "C" int racf_split_bf16x3_chw_to_hwc(const float* in, const float* pos, int batch, int channels, int positions,
-                                            void* out3, racf_stream_t stream) {
+                                            int tiled, void* out3, racf_stream_t stream) {
     using namespace racf;
     if (!in || !out3) return RACF_ERR_NULL_POINTER;
     if (batch <= 0 || channels <= 0 || positions <= 0 || batch > 65535) return RACF_ERR_BAD_SHAPE;
     if ((channels & 7) != 0 || (reinterpret_cast<uintptr_t>(out3) & 15u)) return RACF_ERR_UNSUPPORTED;
     const dim3 grid((unsigned)((positions + 31) / 32), (unsigned)((channels + 63) / 64), (unsigned)batch);
-    split_bf16x3_chw_to_hwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        in, pos, channels, positions, (long long)batch * positions * channels, static_cast<__nv_bfloat16*>(out3));
+    const int kblocks = tiled ? (channels + kTileK - 1) / kTileK : 0;
+    const dim3 grid_t((unsigned)((positions + 31) / 32), (unsigned)((kblocks * kTileK + 63) / 64), (unsigned)batch);
+    split_bf16x3_chw_to_hwc_kernel<<<tiled ? grid_t : grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, pos, channels, positions, (long long)batch * positions * channels, kblocks, static_cast<__nv_bfloat16*>(out3));
     return (int)cudaGetLastError();
 }
 
@@ -471,7 +534,8 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
     using namespace racf;
     if (!a3 || !w3 || !out) return RACF_ERR_NULL_POINTER;
     if (M <= 0 || N <= 0 || K <= 0 || split_k <= 0) return RACF_ERR_BAD_SHAPE;
-    if ((K & 7) != 0 || max_order < 0 || max_order > 4) return RACF_ERR_UNSUPPORTED;   // TMA: 16-byte global strides
+    if (variant < 0 || variant > 2 || max_order < 0 || max_order > 4) return RACF_ERR_UNSUPPORTED;
+    if (variant != 2 && (K & 7) != 0) return RACF_ERR_UNSUPPORTED;                     // tensor maps: 16-byte global strides
     if ((reinterpret_cast<uintptr_t>(a3) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(out)) & 15u)
         return RACF_ERR_UNSUPPORTED;
     if (split_k > 1 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15u))) return RACF_ERR_NULL_POINTER;
@@ -482,12 +546,17 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
     split_k = (num_kblocks + kbps - 1) / kbps;           // no empty splits
 
     CUtensorMap ma, mw;
-    int rc = make_operand_map(&ma, a3, M, K, bk);
-    if (rc != 0) return rc;
-    rc = make_operand_map(&mw, w3, N, K, bk);
-    if (rc != 0) return rc;
+    int rc = 0;
+    if (variant != 2) {
+        rc = make_operand_map(&ma, a3, M, K, bk);
+        if (rc != 0) return rc;
+        rc = make_operand_map(&mw, w3, N, K, bk);
+        if (rc != 0) return rc;
+    }
 
     LinArgs args;
+    args.a_tiled = static_cast<const uint8_t*>(a3);
+    args.w_tiled = static_cast<const uint8_t*>(w3);
     args.num_segments = 0;
     args.bias = bias;
     args.out = split_k > 1 ? workspace : out;
@@ -499,7 +568,9 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
     args.max_order = max_order;
     if ((long long)args.m_tiles * args.n_tiles * split_k > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = variant == 1 ? launch_linear<64, 1>(ma, mw, args, split_k, st) : launch_linear<32, 2>(ma, mw, args, split_k, st);
+    rc = variant == 2 ? launch_linear<32, 2, true>(ma, mw, args, split_k, st)
+       : variant == 1 ? launch_linear<64, 1, false>(ma, mw, args, split_k, st)
+                      : launch_linear<32, 2, false>(ma, mw, args, split_k, st);
     if (rc != 0) return rc;
     if (split_k > 1) {
         const long long mn = (long long)M * N;
@@ -512,14 +583,16 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
 
 extern "C" int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int K, int num_segments,
                                                 const int* seg_n, const float* const* seg_bias, float* const* seg_out,
-                                                int max_order, racf_stream_t stream) {
+                                                int max_order, int tiled, racf_stream_t stream) {
     using namespace racf;
     if (!a3 || !w3 || !seg_n || !seg_out) return RACF_ERR_NULL_POINTER;
     if (M <= 0 || K <= 0 || num_segments <= 0) return RACF_ERR_BAD_SHAPE;
-    if (num_segments > RACF_LINEAR_MAX_SEGMENTS || (K & 7) != 0 || K > 512 || max_order < 0 || max_order > 4)
+    if (num_segments > RACF_LINEAR_MAX_SEGMENTS || (!tiled && (K & 7) != 0) || K > 512 || max_order < 0 || max_order > 4)
         return RACF_ERR_UNSUPPORTED;    // K <= 512: one accumulator pass, no K split
     if ((reinterpret_cast<uintptr_t>(a3) | reinterpret_cast<uintptr_t>(w3)) & 15u) return RACF_ERR_UNSUPPORTED;
     LinArgs args;
+    args.a_tiled = static_cast<const uint8_t*>(a3);
+    args.w_tiled = static_cast<const uint8_t*>(w3);
     args.bias = nullptr;
     args.out = nullptr;
     args.M = M;
@@ -546,9 +619,10 @@ extern "C" int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, 
     args.kblocks_per_split = args.num_kblocks;
     args.max_order = max_order;
     CUtensorMap ma, mw;
+    if (tiled) return launch_linear<32, 2, true>(ma, mw, args, 1, static_cast<cudaStream_t>(stream));
     int rc = make_operand_map(&ma, a3, M, K, 32);
     if (rc != 0) return rc;
     rc = make_operand_map(&mw, w3, args.N, K, 32);
     if (rc != 0) return rc;
-    return launch_linear<32, 2>(ma, mw, args, 1, static_cast<cudaStream_t>(stream));
+    return launch_linear<32, 2, false>(ma, mw, args, 1, static_cast<cudaStream_t>(stream));
 }

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "linear_tiled.cuh"
 #include "racformer_ops.h"
 
 namespace racf {
@@ -56,7 +57,7 @@ __device__ __forceinline__ int swz64(int row, int chunk) { return row * kMixC + 
 template <bool kSplitOut>
 __global__ void __launch_bounds__(kMixThreads, 2)
 adaptive_mixing_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ out,
-                       __nv_bfloat16* __restrict__ out3, long long piece_stride, int p_in, float eps) {
+                       __nv_bfloat16* __restrict__ out3, long long piece_stride, int tiled_groups, int p_in, float eps) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                          // [p_in][64] swizzled; reused for the normalised intermediate
     float* ms = xs + 128 * kMixC;              // [64][64]
@@ -198,9 +199,19 @@ adaptive_mixing_kernel(const float* __restrict__ x, const float* __restrict__ pa
                     p[1][j] = __float2bfloat16_rn(r1);
                     p[2][j] = __float2bfloat16_rn(r1 - __bfloat162float(p[1][j]));
                 }
-                __nv_bfloat16* o3 = out3 + qg * (long long)(kMixPout * kMixC) + off;
+                if (tiled_groups > 0) {
+                    // the A operand of out_proj in the pre-tiled format: row = query, k = group * 8192 + point * 64 + channel
+                    const long long q = qg / tiled_groups;
+                    const int k0 = (int)(qg - q * tiled_groups) * (kMixPout * kMixC) + (int)off;
+                    const int kblocks = tiled_groups * (kMixPout * kMixC / kTileK);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(o3 + k * piece_stride) = *reinterpret_cast<const uint2*>(p[k]);
+                    for (int k = 0; k < 3; ++k)
+                        *reinterpret_cast<uint2*>(out3 + tiled_offset(q, k0, kblocks, k)) = *reinterpret_cast<const uint2*>(p[k]);
+                } else {
+                    __nv_bfloat16* o3 = out3 + qg * (long long)(kMixPout * kMixC) + off;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint2*>(o3 + k * piece_stride) = *reinterpret_cast<const uint2*>(p[k]);
+                }
             } else {
                 *reinterpret_cast<float4*>(og + off) = o;
             }
@@ -211,7 +222,7 @@ adaptive_mixing_kernel(const float* __restrict__ x, const float* __restrict__ pa
 }  // namespace racf
 
 static int mixing_launch(const float* x, const float* params, int num_query_groups, int in_points, int out_points,
-                         int channels, float eps, float* out, void* out3, racf_stream_t stream) {
+                         int channels, float eps, float* out, void* out3, int tiled_groups, racf_stream_t stream) {
     using namespace racf;
     if (!x || !params || (!out && !out3)) return RACF_ERR_NULL_POINTER;
     if (num_query_groups <= 0) return RACF_ERR_BAD_SHAPE;
@@ -229,20 +240,21 @@ static int mixing_launch(const float* x, const float* params, int num_query_grou
     const long long piece_stride = (long long)num_query_groups * kMixPout * kMixC;
     if (out3 != nullptr)
         adaptive_mixing_kernel<true><<<(unsigned)num_query_groups, kMixThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-            x, params, nullptr, static_cast<__nv_bfloat16*>(out3), piece_stride, in_points, eps);
+            x, params, nullptr, static_cast<__nv_bfloat16*>(out3), piece_stride, tiled_groups, in_points, eps);
     else
         adaptive_mixing_kernel<false><<<(unsigned)num_query_groups, kMixThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-            x, params, out, nullptr, 0, in_points, eps);
+            x, params, out, nullptr, 0, 0, in_points, eps);
     return (int)cudaGetLastError();
 }
 
 extern "C" int racf_adaptive_mixing_forward(const float* x, const float* params, int num_query_groups, int in_points,
                                             int out_points, int channels, float eps, float* out, racf_stream_t stream) {
-    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, out, nullptr, stream);
+    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, out, nullptr, 0, stream);
 }
 
 extern "C" int racf_adaptive_mixing_forward_split(const float* x, const float* params, int num_query_groups, int in_points,
                                                   int out_points, int channels, float eps, void* out3,
-                                                  racf_stream_t stream) {
-    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, nullptr, out3, stream);
+                                                  int tiled_groups, racf_stream_t stream) {
+    if (tiled_groups < 0 || (tiled_groups > 0 && num_query_groups % tiled_groups != 0)) return RACF_ERR_BAD_SHAPE;
+    return mixing_launch(x, params, num_query_groups, in_points, out_points, channels, eps, nullptr, out3, tiled_groups, stream);
 }

@@ -362,14 +362,14 @@ class BEVSelfAttention(nn.Module):
         projection (with its bias) runs on the tcgen05 Linear kernel; otherwise the PyTorch ops of the reference."""
         B, T, C = bev.shape[:3]
         if (self.tensor_core_value_proj and not torch.is_grad_enabled() and bev.is_cuda and bev.dtype == torch.float32
-                and C % 8 == 0 and (pos is None or pos.numel() == bev[0, 0].numel())):
+                and C % 8 == 0 and (pos is None or pos.numel() == bev[0, 0].numel())):   # C % 8: 16-byte chunks of the split
             from . import linear
             if getattr(self, "_split_value_proj", None) is None:
                 self._split_value_proj = linear.SplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
             x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(),
-                                                None if pos is None else pos.reshape(C, -1).contiguous())
+                                                None if pos is None else pos.reshape(C, -1).contiguous(), tiled=True)
             v = self._split_value_proj(x3=x3)
-            return v.reshape(B * T, x3.shape[1] // (B * T), self.num_heads, -1)
+            return v.reshape(B * T, x3.rows // (B * T), self.num_heads, -1)
         if pos is not None:
             bev = bev + pos.view(1, 1, C, *bev.shape[3:])
         v = self.value_proj(bev.reshape(B * T, C, -1).permute(0, 2, 1))
@@ -623,7 +623,7 @@ class AdaptiveMixing(nn.Module):
     def _tensor_core_linear(self, query):
         """True when the two large Linear layers run on csrc/linear.cu (tcgen05, exact bf16 operand splitting)."""
         return (self.gemm_precision in ("bf16x9", "bf16x6") and not torch.is_grad_enabled() and query.is_cuda
-                and query.dtype == torch.float32 and self.in_dim % 8 == 0 and self.out_proj.in_features % 8 == 0)
+                and query.dtype == torch.float32)
 
     def _split_linear(self, name):
         from . import linear
@@ -660,10 +660,11 @@ class AdaptiveMixing(nn.Module):
             from . import points   # one kernel for matmul-LN-ReLU-matmul-LN-ReLU
             split = self._tensor_core_linear(query)      # emit the bf16 pieces out_proj consumes, no fp32 round trip
             core = points.adaptive_mixing_core(x.reshape(B * Q * G, P, C).contiguous(),
-                                               params.reshape(B * Q * G, -1).contiguous(), self.out_points, split=split)
+                                               params.reshape(B * Q * G, -1).contiguous(), self.out_points, split=split,
+                                               tiled_groups=G if split else 0)
             if core is not None:
                 if split:
-                    return query + self._split_linear("out_proj")(x3=core.reshape(3, B * Q, -1), lead=(B, Q))
+                    return query + self._split_linear("out_proj")(x3=core, lead=(B, Q))
                 return query + self._project(core.reshape(B, Q, -1))
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)
@@ -742,7 +743,7 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         with separate bias kernels. Returns (radar 4, lss 4, image 3) or None when the fused point kernels are not in use."""
         radar, lss, img = self.sampling_radar_bev, self.sampling_lss_bev, self.sampling
         if (not self.stacked_heads or torch.is_grad_enabled() or not query_feat.is_cuda or query_feat.dtype != torch.float32
-                or self.embed_dims % 8 != 0 or self.embed_dims > 512 or radar.num_levels != 1 or lss.num_levels != 1
+                or self.embed_dims > 512 or radar.num_levels != 1 or lss.num_levels != 1
                 or not all(getattr(m, "fused_points", True) for m in (radar, lss, img))
                 or not (radar.attention.queue_weight and lss.attention.queue_weight)):
             return None

@@ -34,9 +34,55 @@ def split_bf16x3(x):
     return out
 
 
-def split_bf16x3_chw_to_hwc(x, pos=None):
-    """x [BT, C, S] fp32 (+ pos [C, S], broadcast over BT) -> bf16 pieces [3, BT * S, C] of the channel-last sum: the add,
-    permute and copy in front of BEVSelfAttention.value_proj fused with the operand split."""
+class TiledOperand:
+    """A [rows, K] fp32 matrix as its three bf16 pieces in the kernel's pre-tiled format (csrc/linear_tiled.cuh): an
+    opaque device buffer whose pipeline stages are contiguous 24 KB blocks."""
+    __slots__ = ("buf", "rows", "K")
+
+    def __init__(self, buf, rows, K):
+        self.buf, self.rows, self.K = buf, int(rows), int(K)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def tiled_bytes(rows, K):
+    return int(_lib.load().racf_linear_tiled_bytes(int(rows), int(K)))
+
+
+def empty_tiled(rows, K, device):
+    return TiledOperand(torch.empty(tiled_bytes(rows, K) // 2, dtype=torch.bfloat16, device=device), rows, K)
+
+
+def split_tiled(x):
+    """fp32 CUDA matrix [rows, K] -> TiledOperand (the K tail of the last 32-wide block is zero-filled)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.numel() > 0):
+        raise RuntimeError("split_tiled needs a contiguous fp32 CUDA matrix")
+    out = empty_tiled(x.shape[0], x.shape[1], x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_split_bf16x3_tiled(x.data_ptr(), x.shape[0], x.shape[1], out.buf.data_ptr(), _stream(x.device))
+    _lib.check(rc, "racf_split_bf16x3_tiled")
+    return out
+
+
+def untile(op):
+    """TiledOperand -> plain pieces [3, rows, K] bf16 (index arithmetic of csrc/linear_tiled.cuh in torch; used by tests)."""
+    dev = op.buf.device
+    kblocks = (op.K + 31) // 32
+    row = torch.arange(op.rows, device=dev)[:, None]
+    k = torch.arange(op.K, device=dev)[None, :]
+    rr, kk = row & 127, k & 31
+    chunk = (kk >> 3) ^ ((rr >> 1) & 3)
+    base = ((row >> 7) * kblocks + (k >> 5)) * 3
+    inner = rr * 32 + chunk * 8 + (kk & 7)
+    return torch.stack([op.buf[(base + p) * 4096 + inner] for p in range(3)])
+
+
+def split_bf16x3_chw_to_hwc(x, pos=None, tiled=False):
+    """x [BT, C, S] fp32 (+ pos [C, S], broadcast over BT) -> bf16 pieces [3, BT * S, C] of the channel-last sum (or the
+    same matrix as a TiledOperand): the add, permute and copy in front of BEVSelfAttention.value_proj fused with the
+    operand split."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3):
         raise RuntimeError("split_bf16x3_chw_to_hwc needs a contiguous fp32 CUDA tensor [BT, C, S]")
     BT, C, S = x.shape
@@ -45,10 +91,11 @@ def split_bf16x3_chw_to_hwc(x, pos=None):
         raise RuntimeError("split_bf16x3_chw_to_hwc: pos must be a contiguous fp32 CUDA tensor of C * S elements")
     if C % 8 != 0:
         raise RuntimeError("split_bf16x3_chw_to_hwc: channels must be a multiple of 8")
-    out = torch.empty((3, BT * S, C), dtype=torch.bfloat16, device=x.device)
+    out = empty_tiled(BT * S, C, x.device) if tiled else torch.empty((3, BT * S, C), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
         rc = _lib.load().racf_split_bf16x3_chw_to_hwc(x.data_ptr(), pos.data_ptr() if pos is not None else None, BT, C, S,
-                                                      out.data_ptr(), _stream(x.device))
+                                                      1 if tiled else 0, (out.buf if tiled else out).data_ptr(),
+                                                      _stream(x.device))
     _lib.check(rc, "racf_split_bf16x3_chw_to_hwc")
     return out
 
@@ -61,27 +108,37 @@ def plan(M, N, K):
 
 
 def linear_bf16x3(a3, w3, bias=None, max_order=ALL_TERMS, split_k=None, variant=0):
-    """a3 [3, M, K], w3 [3, N, K] (bf16 pieces from split_bf16x3), bias [N] fp32 or None -> [M, N] fp32."""
-    if not (a3.is_cuda and w3.is_cuda and a3.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16
-            and a3.is_contiguous() and w3.is_contiguous() and a3.device == w3.device):
-        raise RuntimeError("linear_bf16x3 needs contiguous bf16 CUDA piece tensors on one device")
-    if a3.dim() != 3 or w3.dim() != 3 or a3.shape[0] != 3 or w3.shape[0] != 3 or a3.shape[2] != w3.shape[2]:
-        raise RuntimeError("linear_bf16x3: a3 must be [3, M, K] and w3 [3, N, K]")
-    M, K = a3.shape[1], a3.shape[2]
-    N = w3.shape[1]
-    if K % 8 != 0:
-        raise RuntimeError("linear_bf16x3: K must be a multiple of 8")
+    """a3 [3, M, K], w3 [3, N, K] (bf16 pieces from split_bf16x3) or two TiledOperands, bias [N] fp32 or None
+    -> [M, N] fp32."""
+    if isinstance(a3, TiledOperand) or isinstance(w3, TiledOperand):
+        if not (isinstance(a3, TiledOperand) and isinstance(w3, TiledOperand)) or a3.K != w3.K or a3.device != w3.device:
+            raise RuntimeError("linear_bf16x3: both operands must be TiledOperands with the same K on one device")
+        M, K, N, variant = a3.rows, a3.K, w3.rows, 2
+        a_ptr, w_ptr, dev = a3.buf.data_ptr(), w3.buf.data_ptr(), a3.device
+    else:
+        if not (a3.is_cuda and w3.is_cuda and a3.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16
+                and a3.is_contiguous() and w3.is_contiguous() and a3.device == w3.device):
+            raise RuntimeError("linear_bf16x3 needs contiguous bf16 CUDA piece tensors on one device")
+        if a3.dim() != 3 or w3.dim() != 3 or a3.shape[0] != 3 or w3.shape[0] != 3 or a3.shape[2] != w3.shape[2]:
+            raise RuntimeError("linear_bf16x3: a3 must be [3, M, K] and w3 [3, N, K]")
+        M, K = a3.shape[1], a3.shape[2]
+        N = w3.shape[1]
+        if K % 8 != 0:
+            raise RuntimeError("linear_bf16x3: K must be a multiple of 8")
+        if variant not in (0, 1):
+            raise RuntimeError("linear_bf16x3: plain pieces run as variant 0 or 1")
+        a_ptr, w_ptr, dev = a3.data_ptr(), w3.data_ptr(), a3.device
     if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous()
-                                 and bias.numel() == N and bias.device == a3.device):
+                                 and bias.numel() == N and bias.device == dev):
         raise RuntimeError("linear_bf16x3: bias must be a contiguous fp32 CUDA tensor of N elements")
     if split_k is None:
         split_k, _ = plan(M, N, K)
-    out = torch.empty((M, N), dtype=torch.float32, device=a3.device)
-    ws = torch.empty((split_k, M, N), dtype=torch.float32, device=a3.device) if split_k > 1 else None
-    with torch.cuda.device(a3.device):
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    ws = torch.empty((split_k, M, N), dtype=torch.float32, device=dev) if split_k > 1 else None
+    with torch.cuda.device(dev):
         rc = _lib.load().racf_linear_bf16x3_forward(
-            a3.data_ptr(), w3.data_ptr(), bias.data_ptr() if bias is not None else None, M, N, K, int(max_order),
-            int(split_k), int(variant), ws.data_ptr() if ws is not None else None, out.data_ptr(), _stream(a3.device))
+            a_ptr, w_ptr, bias.data_ptr() if bias is not None else None, M, N, K, int(max_order),
+            int(split_k), int(variant), ws.data_ptr() if ws is not None else None, out.data_ptr(), _stream(dev))
     _lib.check(rc, "racf_linear_bf16x3_forward")
     return out
 
@@ -90,25 +147,30 @@ class SplitLinear:
     """Inference-time stand-in for an nn.Linear: caches the bf16 pieces of the weight (re-split when the parameter
     changes) and runs x @ W^T + b through racf_linear_bf16x3_forward."""
 
-    def __init__(self, linear, max_order=ALL_TERMS, variant=0):
+    def __init__(self, linear, max_order=ALL_TERMS, variant=2):
+        """variant 2 (default): operands in the pre-tiled format (bulk copies); 0 / 1: plain pieces through tensor maps."""
         self.linear, self.max_order, self.variant = linear, max_order, variant
         self._key, self._w3 = None, None
+
+    def _split(self, x2d):
+        return split_tiled(x2d) if self.variant == 2 else split_bf16x3(x2d)
 
     def weight_pieces(self):
         w = self.linear.weight
         key = (w.data_ptr(), w._version, w.device)
         if self._key != key:
-            self._w3 = split_bf16x3(w.detach().contiguous())
+            self._w3 = self._split(w.detach().contiguous())
             self._key = key
         return self._w3
 
     def __call__(self, x=None, x3=None, lead=None):
-        """x [..., K] fp32, or its pieces x3 [3, rows, K] with the leading shape `lead` of the result -> [..., N] fp32."""
+        """x [..., K] fp32, or its pieces x3 (TiledOperand, or [3, rows, K] for variants 0 / 1) with the leading shape
+        `lead` of the result -> [..., N] fp32."""
         if x3 is None:
             lead = x.shape[:-1]
-            x3 = split_bf16x3(x.reshape(-1, x.shape[-1]).contiguous())
+            x3 = self._split(x.reshape(-1, x.shape[-1]).contiguous())
         elif lead is None:
-            lead = (x3.shape[1],)
+            lead = (x3.rows if isinstance(x3, TiledOperand) else x3.shape[1],)
         bias = self.linear.bias.detach() if self.linear.bias is not None else None
         y = linear_bf16x3(x3, self.weight_pieces(), bias, self.max_order, variant=self.variant)
         return y.reshape(*lead, -1)
@@ -126,8 +188,8 @@ class MultiSplitLinear:
         if not 0 < len(self.linears) <= self.MAX_SEGMENTS:
             raise RuntimeError("MultiSplitLinear: 1..16 layers")
         k = {lin.in_features for lin in self.linears}
-        if len(k) != 1 or next(iter(k)) % 8 != 0 or next(iter(k)) > 512:
-            raise RuntimeError("MultiSplitLinear: the layers must share in_features (a multiple of 8, at most 512)")
+        if len(k) != 1 or next(iter(k)) > 512:
+            raise RuntimeError("MultiSplitLinear: the layers must share in_features (at most 512)")
         self._key, self._w3 = None, None
 
     def weight_pieces(self):
@@ -138,23 +200,23 @@ class MultiSplitLinear:
                 w = lin.weight.detach()
                 pad = (-w.shape[0]) % 128
                 rows.append(torch.cat([w, w.new_zeros(pad, w.shape[1])]) if pad else w)
-            self._w3 = split_bf16x3(torch.cat(rows).contiguous())
+            self._w3 = split_tiled(torch.cat(rows).contiguous())
             self._key = key
         return self._w3
 
     def __call__(self, x=None, x3=None):
-        """x [..., K] (or its pieces x3 [3, rows, K]) -> list of [rows, N_i] fp32 tensors, one per layer."""
+        """x [..., K] (or its TiledOperand x3) -> list of [rows, N_i] fp32 tensors, one per layer."""
         if x3 is None:
-            x3 = split_bf16x3(x.reshape(-1, x.shape[-1]).contiguous())
+            x3 = split_tiled(x.reshape(-1, x.shape[-1]).contiguous())
         w3 = self.weight_pieces()
-        M, K = x3.shape[1], x3.shape[2]
+        M, K = x3.rows, x3.K
         n = len(self.linears)
         outs = [torch.empty((M, lin.out_features), dtype=torch.float32, device=x3.device) for lin in self.linears]
         seg_n = (ctypes.c_int * n)(*[lin.out_features for lin in self.linears])
         seg_bias = (ctypes.c_void_p * n)(*[lin.bias.data_ptr() if lin.bias is not None else None for lin in self.linears])
         seg_out = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
         with torch.cuda.device(x3.device):
-            rc = _lib.load().racf_linear_bf16x3_multi_forward(x3.data_ptr(), w3.data_ptr(), M, K, n, seg_n, seg_bias, seg_out,
-                                                              int(self.max_order), _stream(x3.device))
+            rc = _lib.load().racf_linear_bf16x3_multi_forward(x3.buf.data_ptr(), w3.buf.data_ptr(), M, K, n, seg_n, seg_bias,
+                                                              seg_out, int(self.max_order), 1, _stream(x3.device))
         _lib.check(rc, "racf_linear_bf16x3_multi_forward")
         return outs

@@ -66,16 +66,17 @@ def test_split_is_exact_and_ordered():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(128, 128, 32), (77, 200, 40), (1, 8, 8), (300, 132, 264), (900, 256, 256), (257, 1030, 520)])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_linear_matches_fp64_like_sgemm(shape, variant):
-    """Ragged M / N / K (TMA zero-fills the tails), bias on, all nine terms and the six-term default."""
+    """Ragged M / N / K (TMA zero-fills the tails; the tiled format pads them), bias on, all nine terms and the six-term
+    default. Variant 2 = the pre-tiled operand format (bulk copies), 0 / 1 = plain pieces through tensor maps."""
     from racformer_b200 import linear
     M, N, K = shape
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
     a = torch.randn(M, K, device="cuda", generator=g)
     w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
     b = torch.randn(N, device="cuda", generator=g)
-    a3, w3 = linear.split_bf16x3(a), linear.split_bf16x3(w)
+    a3, w3 = (linear.split_tiled(a), linear.split_tiled(w)) if variant == 2 else (linear.split_bf16x3(a), linear.split_bf16x3(w))
     for order in (linear.ALL_TERMS, linear.SIX_TERMS):
         y = linear.linear_bf16x3(a3, w3, b, max_order=order, variant=variant)
         err = _normalised_error(y, a, w, b)
@@ -83,6 +84,27 @@ def test_linear_matches_fp64_like_sgemm(shape, variant):
         assert torch.equal(y, linear.linear_bf16x3(a3, w3, b, max_order=order, variant=variant)), "deterministic"
     y0 = linear.linear_bf16x3(a3, w3, None, variant=variant)
     assert _normalised_error(y0, a, w, None).max().item() < MAX_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(5, 12), (128, 32), (300, 100), (900, 256)])
+def test_tiled_format_holds_the_same_pieces(shape):
+    """split_tiled writes exactly the pieces of split_bf16x3, at the offsets csrc/linear_tiled.cuh defines (any K: the
+    tail of the last 32-wide K block is zero), and the tiled Linear works for a K that is not a multiple of 8."""
+    from racformer_b200 import linear
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(*shape, device="cuda", generator=g)
+    t = linear.split_tiled(x)
+    assert t.buf.numel() * 2 == linear.tiled_bytes(*shape) == -(-shape[0] // 128) * -(-shape[1] // 32) * 24576
+    assert torch.equal(linear.untile(t).double().sum(0), x.double())
+    if shape[1] % 4 == 0:
+        assert torch.equal(linear.untile(t), linear.split_bf16x3(x))
+    if shape[1] % 32:
+        padded = linear.untile(linear.TiledOperand(t.buf, shape[0], -(-shape[1] // 32) * 32))
+        assert bool((padded[:, :, shape[1]:] == 0).all())
+    w = torch.randn(40, shape[1], device="cuda", generator=g)
+    y = linear.linear_bf16x3(t, linear.split_tiled(w))
+    assert _normalised_error(y, x, w, None).max().item() < MAX_TOL
 
 
 @pytest.mark.gpu
@@ -130,6 +152,11 @@ def test_mixing_core_split_output_is_the_fp32_output():
     pieces = points.adaptive_mixing_core(x, params, P_out, split=True)
     assert pieces.shape == (3, QG, P_out, C) and pieces.dtype == torch.bfloat16
     assert torch.equal(pieces.double().sum(0), full.double())
+    # ... and as the pre-tiled A operand of out_proj: [QG / 4 queries, 4 groups * 128 points * 64 channels]
+    from racformer_b200 import linear
+    tiled = points.adaptive_mixing_core(x, params, P_out, split=True, tiled_groups=4)
+    assert (tiled.rows, tiled.K) == (QG // 4, 4 * P_out * C)
+    assert torch.equal(linear.untile(tiled), pieces.reshape(3, QG // 4, -1))
 
 
 @pytest.mark.gpu
@@ -160,6 +187,10 @@ def test_chw_to_hwc_split_and_tensor_core_value_proj():
     assert p.shape == (3, 150, 40)
     assert torch.equal(p.double().sum(0), (x + pos).permute(0, 2, 1).reshape(150, 40).double())
     assert torch.equal(linear.split_bf16x3_chw_to_hwc(x).double().sum(0), x.permute(0, 2, 1).reshape(150, 40).double())
+    tiled = linear.split_bf16x3_chw_to_hwc(x, pos, tiled=True)
+    assert (tiled.rows, tiled.K) == (150, 40) and torch.equal(linear.untile(tiled), p)
+    wide = linear.untile(linear.TiledOperand(tiled.buf, 150, 64))
+    assert bool((wide[:, :, 40:] == 0).all())                      # K tail of the tiled format is zero-filled
 
     attn = BEVSelfAttention(embed_dims=64, num_heads=4, num_levels=1, num_points=4, num_bev_queue=2).cuda().eval()
     bev = torch.randn(1, 2, 64, 9, 13, device="cuda", generator=g)

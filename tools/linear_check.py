@@ -26,7 +26,7 @@ def run_case(M, N, K, bias, variant, max_order, iters):
     a = torch.randn(M, K, device=dev)
     w = torch.randn(N, K, device=dev) / K ** 0.5
     b = torch.randn(N, device=dev) if bias else None
-    a3, w3 = linear.split_bf16x3(a), linear.split_bf16x3(w)
+    a3, w3 = (linear.split_tiled(a), linear.split_tiled(w)) if variant == 2 else (linear.split_bf16x3(a), linear.split_bf16x3(w))
     exact_split = bool((a3.double().sum(0) == a.double()).all()) and bool((w3.double().sum(0) == w.double()).all())
     y = linear.linear_bf16x3(a3, w3, b, max_order=max_order, variant=variant)
     torch.cuda.synchronize()
@@ -62,7 +62,7 @@ def run_case(M, N, K, bias, variant, max_order, iters):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / iters * 1e3
         res["us"] = timed(lambda: linear.linear_bf16x3(a3, w3, b, max_order=max_order, variant=variant))
-        res["us_split_a"] = timed(lambda: linear.split_bf16x3(a))
+        res["us_split_a"] = timed(lambda: linear.split_tiled(a) if variant == 2 else linear.split_bf16x3(a))
         torch.backends.cuda.matmul.allow_tf32 = False
         res["us_sgemm"] = timed(lambda: torch.nn.functional.linear(a, w, b))
         terms = {4: 9, 3: 8, 2: 6, 1: 3, 0: 1}[max_order]
@@ -77,7 +77,8 @@ if __name__ == "__main__":
         sys.exit(0)
     out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     results = []
-    for variant in (0, 1):
+    variants = [int(v) for v in sys.argv[sys.argv.index("--variants") + 1].split(",")] if "--variants" in sys.argv else (0, 1, 2)
+    for variant in variants:
         for (M, N, K, bias) in CASES:
             for max_order in ((4, 2, 0) if N * K >= 1 << 22 or (M, N, K) == (128, 128, 256) else (4,)):
                 iters = 20 if N * K >= 1 << 22 else 0
