@@ -215,6 +215,17 @@ int racf_adaptive_mixing_forward_split(const float* x, const float* params, int 
                                        racf_stream_t stream);
 
 /*
+ * The same AdaptiveMixing core on the tcgen05 tensor cores (csrc/mixing_tc.cu): both products as bf16x3 operand-split
+ * MMAs with fp32 accumulation in tensor memory (six piece products, large / cross terms in separate accumulators), the
+ * layer norms in fp32 straight from tensor memory. Exactly one of `out` (fp32 [QG, out_points, C]) and `out3` (the tiled
+ * A operand of out_proj, tiled_groups = n_groups, see racf_adaptive_mixing_forward_split) is non-NULL.
+ * Implemented for C == 64, out_points == 128, in_points % 16 == 0, 16 <= in_points <= 128 (else RACF_ERR_UNSUPPORTED).
+ */
+int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
+                                    int out_points, int channels, float eps, float* out, void* out3,
+                                    int tiled_groups, racf_stream_t stream);
+
+/*
  * "next" row: AdaptiveMixing's two large Linear layers (parameter_generator and out_proj,
  * models/racformer_transformer.py:560-566, F.linear in fp32) on the tcgen05 tensor cores at fp32-grade accuracy.
  *

@@ -1,0 +1,351 @@
+// AdaptiveMixing core on the 5th-generation tensor cores -- SURVEY.md 8f-4 ("fused grouped GEMM + LayerNorm").
+//
+// Same contract as csrc/mixing.cu (reference: AdaptiveMixing.inner_forward, models/racformer_transformer.py:592-604), per
+// (query, group):   t = relu(LN(x @ M));   out = relu(LN(S @ t))
+// x [P_in, 64], M [64, 64], S [128, P_in] fp32. Here both products run as tcgen05.mma on bf16 pieces produced ON THE FLY:
+// every fp32 value is split exactly into three bf16 pieces while it is copied from global to shared memory, the six
+// largest piece products are accumulated in fp32 in tensor memory (large term and cross terms in separate accumulators,
+// see csrc/linear.cu for why), so the products are fp32-grade; the layer norms stay in fp32 on the CUDA cores, fed
+// straight from tensor memory. One persistent CTA per SM walks over the (query, group) items:
+//
+//   P0  global fp32 -> split -> shared, in the layouts the MMA wants (manual 128-/64-byte swizzle):
+//         X3 [128 rows p][64 c]  A of product 1 (rows >= P_in stay zero)       M3 [64 rows c'][64 c]  B of product 1 (= M^T)
+//         S3 [128 rows o][P_in]  A of product 2, 32-wide K atoms
+//   P1  one thread issues product 1: D1[p, c'] (M = 128, N = 64, K = 64; 24 MMAs)
+//   P2  D1 -> registers (tcgen05.ld), LayerNorm over P_in x 64, ReLU, split -> T3 [64 rows c'][P_in] (= t^T, B of product 2)
+//   P3  product 2: D2[o, c'] (M = 128, N = 64, K = P_in; 36 MMAs at P_in = 96)
+//   P4  D2 -> registers, LayerNorm over 128 x 64, ReLU -> fp32 out, or bf16 pieces in the tiled format of out_proj's A operand
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "linear_tiled.cuh"
+#include "racformer_ops.h"
+
+namespace racf {
+namespace mixtc {
+
+constexpr int kC = 64, kPout = 128, kThreads = 256;
+constexpr int kX3 = 0;                          // 3 x 16 KB: [128][64] bf16, 128-byte rows, 128-byte swizzle
+constexpr int kM3 = kX3 + 3 * 16384;            // 3 x  8 KB: [64][64]
+constexpr int kS3 = kM3 + 3 * 8192;             // 3 x 4 atoms x 8 KB: [128][32] per atom, 64-byte rows, 64-byte swizzle
+constexpr int kT3 = kS3 + 3 * 4 * 8192;         // 3 x 4 atoms x 4 KB: [64][32] per atom
+constexpr int kSmemBytes = kT3 + 3 * 4 * 4096;  // 216 KB for P_in up to 128
+constexpr int kTmemCols = 256;                  // D1 main / cross: [0,64) [64,128); D2 main / cross: [128,192) [192,256)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {   // bounded: a bug must not hang the GPU
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+// K-major bf16 tile, rows one swizzle span wide (128 or 64 bytes); 8-row groups SBO = 8 rows apart
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+    constexpr uint64_t layout = kRowBytes == 128 ? 2 : 4;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8 * kRowBytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+    p0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p0);
+    p1 = __float2bfloat16_rn(r1);
+    p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+}
+// eight consecutive fp32 -> one 16-byte chunk per piece at byte offset `off` of each piece tile
+__device__ __forceinline__ void split_store8(const float (&f)[8], uint8_t* tile, int piece_bytes, int off) {
+    __align__(16) __nv_bfloat16 p[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3(f[j], p[0][j], p[1][j], p[2][j]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(tile + k * piece_bytes + off) = *reinterpret_cast<const uint4*>(p[k]);
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+template <bool kSplitOut>
+__global__ void __launch_bounds__(kThreads, 1)
+adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ out,
+                          __nv_bfloat16* __restrict__ out3, int tiled_groups, int num_items, int p_in, float eps) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red[kThreads / 32];
+
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sm_addr = smem_u32(sm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int natoms = (p_in + 31) >> 5;                     // 32-wide K atoms of product 2
+    const int s3_piece = natoms * 8192, t3_piece = natoms * 4096;
+    const uint32_t bar_addr = smem_u32(&bar);
+
+    // zero everything once: rows / K tails that are never written must read as 0
+    for (int i = tid; i < kSmemBytes / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar_addr, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+    // this thread's slice of an accumulator tile: TMEM lane quarter (warp % 4), 32 of the 64 columns (warp / 4)
+    const int row = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 32;
+    const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + col0;
+    const int m_elems = kC * kC, s_elems = kPout * p_in;
+
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const float* xg = x + (long long)item * p_in * kC;
+        const float* mg = params + (long long)item * (m_elems + s_elems);
+        const float* sg = mg + m_elems;
+
+        // ---- P0: split x, M^T and S into shared memory --------------------------------------------------------
+        for (int i = tid; i < p_in * 8; i += kThreads) {            // x: row p, 16-byte chunk ch (8 channels)
+            const int p = i >> 3, ch = i & 7;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(xg + p * kC + ch * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(xg + p * kC + ch * 8 + 4));
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            split_store8(f, sm + kX3, 16384, p * 128 + ((ch ^ (p & 7)) << 4));
+        }
+        for (int i = tid; i < kC * 8; i += kThreads) {              // M^T: row c' (lanes -> coalesced), chunk of 8 c
+            const int cp = i & 63, ch = i >> 6;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __ldg(mg + (ch * 8 + j) * kC + cp);
+            split_store8(f, sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
+        }
+        const int s_chunks = p_in >> 3;
+        for (int i = tid; i < kPout * s_chunks; i += kThreads) {    // S: row o, chunk j of 8 points
+            const int o = i / s_chunks, j = i - o * s_chunks;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(sg + o * p_in + j * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(sg + o * p_in + j * 8 + 4));
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            split_store8(f, sm + kS3, s3_piece, (j >> 2) * 8192 + o * 64 + (((j & 3) ^ ((o >> 1) & 3)) << 4));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+
+        // ---- P1: product 1 --------------------------------------------------------------------------------------
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc_cross = 0;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                for (int order = 2; order >= 1; --order)
+                    for (int pa = 0; pa <= order; ++pa) {
+                        umma_bf16(tmem + 64, umma_desc<128>(sm_addr + kX3 + pa * 16384 + ks * 32),
+                                  umma_desc<128>(sm_addr + kM3 + (order - pa) * 8192 + ks * 32), idesc, acc_cross);
+                        acc_cross = 1;
+                    }
+                umma_bf16(tmem, umma_desc<128>(sm_addr + kX3 + ks * 32), umma_desc<128>(sm_addr + kM3 + ks * 32), idesc, ks > 0);
+            }
+            umma_commit(bar_addr);
+        }
+        // prefetch the next item's inputs into L2 while the tensor core works
+        {
+            const int nxt = item + gridDim.x;
+            if (nxt < num_items) {
+                const char* nx = reinterpret_cast<const char*>(x + (long long)nxt * p_in * kC);
+                const char* np = reinterpret_cast<const char*>(params + (long long)nxt * (m_elems + s_elems));
+                for (int i = tid * 128; i < p_in * kC * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+                for (int i = tid * 128; i < (m_elems + s_elems) * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + i));
+            }
+        }
+        mbar_wait(bar_addr, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- P2: LayerNorm + ReLU of D1 (rows < P_in), split, store t^T as the B operand of product 2 ------------
+        {
+            uint32_t v[32], u[32];
+            tmem_ld32(tm_lane, v);
+            tmem_ld32(tm_lane + 64, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float f[32];
+            float s = 0.f;
+            const bool live = row < p_in;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                f[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                s += live ? f[j] : 0.f;
+            }
+            const float n = (float)(p_in * kC);
+            const float mean = block_sum(s, red) / n;
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = f[j] - mean;
+                q += live ? d * d : 0.f;
+            }
+            const float rstd = rsqrtf(block_sum(q, red) / n + eps);
+            if (live) {
+                // element (c', p) of t^T: atom p / 32, row c', 16-byte chunk (p % 32) / 8, 2-byte slot p % 8
+                const int atom = row >> 5, kk = row & 31;
+                uint8_t* base = sm + kT3 + atom * 4096 + (kk & 7) * 2;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int cp = col0 + j;
+                    __nv_bfloat16 p0, p1, p2;
+                    split3(fmaxf((f[j] - mean) * rstd, 0.f), p0, p1, p2);
+                    uint8_t* e = base + cp * 64 + (((kk >> 3) ^ ((cp >> 1) & 3)) << 4);
+                    *reinterpret_cast<__nv_bfloat16*>(e) = p0;
+                    *reinterpret_cast<__nv_bfloat16*>(e + t3_piece) = p1;
+                    *reinterpret_cast<__nv_bfloat16*>(e + 2 * t3_piece) = p2;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+
+        // ---- P3: product 2 --------------------------------------------------------------------------------------
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc_cross = 0;
+            const int ksteps = p_in >> 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t a_off = (ks >> 1) * 8192 + (ks & 1) * 32, b_off = (ks >> 1) * 4096 + (ks & 1) * 32;
+                for (int order = 2; order >= 1; --order)
+                    for (int pa = 0; pa <= order; ++pa) {
+                        umma_bf16(tmem + 192, umma_desc<64>(sm_addr + kS3 + pa * s3_piece + a_off),
+                                  umma_desc<64>(sm_addr + kT3 + (order - pa) * t3_piece + b_off), idesc, acc_cross);
+                        acc_cross = 1;
+                    }
+                umma_bf16(tmem + 128, umma_desc<64>(sm_addr + kS3 + a_off), umma_desc<64>(sm_addr + kT3 + b_off), idesc, ks > 0);
+            }
+            umma_commit(bar_addr);
+        }
+        mbar_wait(bar_addr, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- P4: LayerNorm + ReLU of D2 -> global ------------------------------------------------------------------
+        {
+            uint32_t v[32], u[32];
+            tmem_ld32(tm_lane + 128, v);
+            tmem_ld32(tm_lane + 192, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float f[32];
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                f[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                s += f[j];
+            }
+            const float n = (float)(kPout * kC);
+            const float mean = block_sum(s, red) / n;
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float d = f[j] - mean;
+                q += d * d;
+            }
+            const float rstd = rsqrtf(block_sum(q, red) / n + eps);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf((f[j] - mean) * rstd, 0.f);
+            if constexpr (kSplitOut) {
+                // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c' (this thread: one 32-wide K block)
+                const long long qi = item / tiled_groups;
+                const int k0 = (int)(item - qi * tiled_groups) * (kPout * kC) + row * kC + col0;
+                const int kblocks = tiled_groups * (kPout * kC / kTileK);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    __align__(16) __nv_bfloat16 p[3][8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split3(f[c * 8 + j], p[0][j], p[1][j], p[2][j]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        *reinterpret_cast<uint4*>(out3 + tiled_offset(qi, k0 + c * 8, kblocks, k)) = *reinterpret_cast<const uint4*>(p[k]);
+                }
+            } else {
+                float* og = out + (long long)item * (kPout * kC) + row * kC + col0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(og + c * 4) = make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();          // D1 / D2 and the operand tiles may be overwritten by the next item
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+}  // namespace mixtc
+}  // namespace racf
+
+// out (fp32 [QG, 128, 64]) or out3 (tiled pieces, tiled_groups = n_groups) -- exactly one of them non-NULL.
+extern "C" int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
+                                               int out_points, int channels, float eps, float* out, void* out3,
+                                               int tiled_groups, racf_stream_t stream) {
+    using namespace racf::mixtc;
+    if (!x || !params || (!out && !out3) || (out && out3)) return RACF_ERR_NULL_POINTER;
+    if (num_query_groups <= 0) return RACF_ERR_BAD_SHAPE;
+    if (channels != kC || out_points != kPout || in_points < 16 || in_points > 128 || (in_points & 15) != 0)
+        return RACF_ERR_UNSUPPORTED;
+    if (out3 && (tiled_groups <= 0 || num_query_groups % tiled_groups != 0)) return RACF_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(out3)) & 15u)
+        return RACF_ERR_UNSUPPORTED;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    const int smem = kSmemBytes + 1024;
+    const unsigned grid = (unsigned)(num_query_groups < sms ? num_query_groups : sms);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (out3) {
+        e = cudaFuncSetAttribute(adaptive_mixing_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        adaptive_mixing_tc_kernel<true><<<grid, kThreads, smem, st>>>(x, params, nullptr, static_cast<__nv_bfloat16*>(out3),
+                                                                      tiled_groups, num_query_groups, in_points, eps);
+    } else {
+        e = cudaFuncSetAttribute(adaptive_mixing_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        adaptive_mixing_tc_kernel<false><<<grid, kThreads, smem, st>>>(x, params, out, nullptr, 0, num_query_groups, in_points, eps);
+    }
+    return (int)cudaGetLastError();
+}

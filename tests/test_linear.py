@@ -154,9 +154,14 @@ def test_mixing_core_split_output_is_the_fp32_output():
     assert torch.equal(pieces.double().sum(0), full.double())
     # ... and as the pre-tiled A operand of out_proj: [QG / 4 queries, 4 groups * 128 points * 64 channels]
     from racformer_b200 import linear
-    tiled = points.adaptive_mixing_core(x, params, P_out, split=True, tiled_groups=4)
+    tiled = points.adaptive_mixing_core(x, params, P_out, split=True, tiled_groups=4, tensor_cores=False)
     assert (tiled.rows, tiled.K) == (QG // 4, 4 * P_out * C)
     assert torch.equal(linear.untile(tiled), pieces.reshape(3, QG // 4, -1))
+    # the tensor-core kernel (csrc/mixing_tc.cu): its tiled pieces are the split of its own fp32 result
+    full_tc = points.adaptive_mixing_core(x, params, P_out)
+    tiled_tc = points.adaptive_mixing_core(x, params, P_out, split=True, tiled_groups=4)
+    assert torch.equal(linear.untile(tiled_tc).double().sum(0), full_tc.reshape(QG // 4, -1).double())
+    assert float((full_tc - full).abs().max()) <= 2e-5
 
 
 @pytest.mark.gpu

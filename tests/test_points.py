@@ -142,10 +142,13 @@ def test_channel_last_relayout_kernel_equals_permute():
         assert torch.equal(points.to_sampling_layout(feat, N, G), want)
 
 
-@pytest.mark.parametrize("p_in", [96, 24, 128, 4])
-def test_fused_adaptive_mixing_core_equals_pytorch_chain(p_in):
-    """csrc/mixing.cu vs the op chain of AdaptiveMixing.inner_forward (racformer_transformer.py:592-604): both are fp32
-    FMA arithmetic, so they agree to rounding / summation order (outputs are layer-normalised, O(1))."""
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("p_in", [96, 24, 128, 4, 48, 16, 112])
+def test_fused_adaptive_mixing_core_equals_pytorch_chain(p_in, tensor_cores):
+    """csrc/mixing.cu (CUDA cores, fp32 FMA) and csrc/mixing_tc.cu (tcgen05, exact bf16x3 operand split, fp32 accumulation;
+    used when P_in % 16 == 0) vs the op chain of AdaptiveMixing.inner_forward (racformer_transformer.py:592-604): all are
+    fp32-grade evaluations, so they agree to rounding / summation order (outputs are layer-normalised, O(1)); against an
+    fp64 evaluation of the same chain the kernels must be as close as PyTorch's own fp32 chain is."""
     import torch.nn.functional as F
     from racformer_b200 import points
     g = torch.Generator().manual_seed(p_in)
@@ -157,10 +160,15 @@ def test_fused_adaptive_mixing_core_equals_pytorch_chain(p_in):
     t = F.relu(F.layer_norm(t, [p_in, C]))
     ref = torch.matmul(s.reshape(QG, P_out, p_in), t)
     ref = F.relu(F.layer_norm(ref, [P_out, C]))
-    got = points.adaptive_mixing_core(x, params, P_out)
+    got = points.adaptive_mixing_core(x, params, P_out, tensor_cores=tensor_cores)
     assert got is not None and got.shape == ref.shape
     assert float((got - ref).abs().max()) <= 2e-5
-    assert torch.equal(got, points.adaptive_mixing_core(x, params, P_out)), "deterministic"
+    assert torch.equal(got, points.adaptive_mixing_core(x, params, P_out, tensor_cores=tensor_cores)), "deterministic"
+    t64 = torch.matmul(x.double(), m.reshape(QG, C, C).double())
+    t64 = F.relu(F.layer_norm(t64, [p_in, C]))
+    ref64 = F.relu(F.layer_norm(torch.matmul(s.reshape(QG, P_out, p_in).double(), t64), [P_out, C]))
+    err_kernel, err_torch = float((got.double() - ref64).abs().max()), float((ref.double() - ref64).abs().max())
+    assert err_kernel <= max(2.0 * err_torch, 5e-6), (err_kernel, err_torch)
 
 
 def test_fused_adaptive_mixing_core_declines_unsupported_shapes():

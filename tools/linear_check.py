@@ -27,7 +27,9 @@ def run_case(M, N, K, bias, variant, max_order, iters):
     w = torch.randn(N, K, device=dev) / K ** 0.5
     b = torch.randn(N, device=dev) if bias else None
     a3, w3 = (linear.split_tiled(a), linear.split_tiled(w)) if variant == 2 else (linear.split_bf16x3(a), linear.split_bf16x3(w))
-    exact_split = bool((a3.double().sum(0) == a.double()).all()) and bool((w3.double().sum(0) == w.double()).all())
+    pa, pw = (linear.untile(a3), linear.untile(w3)) if variant == 2 else (a3, w3)
+    exact_split = bool((pa.double().sum(0) == a.double()).all()) and bool((pw.double().sum(0) == w.double()).all())
+    del pa, pw
     y = linear.linear_bf16x3(a3, w3, b, max_order=max_order, variant=variant)
     torch.cuda.synchronize()
     rows = slice(0, min(M, 256))
