@@ -141,28 +141,55 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
         const float* mg = params + (long long)item * (m_elems + s_elems);
         const float* sg = mg + m_elems;
 
-        // ---- P0: split x, M^T and S into shared memory --------------------------------------------------------
-        for (int i = tid; i < p_in * 8; i += kThreads) {            // x: row p, 16-byte chunk ch (8 channels)
-            const int p = i >> 3, ch = i & 7;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(xg + p * kC + ch * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(xg + p * kC + ch * 8 + 4));
-            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            split_store8(f, sm + kX3, 16384, p * 128 + ((ch ^ (p & 7)) << 4));
-        }
-        for (int i = tid; i < kC * 8; i += kThreads) {              // M^T: row c' (lanes -> coalesced), chunk of 8 c
-            const int cp = i & 63, ch = i >> 6;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __ldg(mg + (ch * 8 + j) * kC + cp);
-            split_store8(f, sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
-        }
+        // ---- P0: split x, M^T and S into shared memory. All global loads are issued before the first use so that
+        //      their latency is paid once per item (fixed trip counts for P_in <= 128, predicated) ------------------
         const int s_chunks = p_in >> 3;
-        for (int i = tid; i < kPout * s_chunks; i += kThreads) {    // S: row o, chunk j of 8 points
-            const int o = i / s_chunks, j = i - o * s_chunks;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(sg + o * p_in + j * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(sg + o * p_in + j * 8 + 4));
-            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            split_store8(f, sm + kS3, s3_piece, (j >> 2) * 8192 + o * 64 + (((j & 3) ^ ((o >> 1) & 3)) << 4));
+        float4 xa[4][2], sa[8][2];
+        float mv[2][8];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {                            // x: row p, 16-byte chunk ch (8 channels)
+            const int i = tid + it * kThreads;
+            if (i < p_in * 8) {
+                xa[it][0] = __ldg(reinterpret_cast<const float4*>(xg + i * 8));
+                xa[it][1] = __ldg(reinterpret_cast<const float4*>(xg + i * 8 + 4));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {                            // M^T: row c' (lanes -> coalesced), chunk of 8 c
+            const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mv[it][j] = __ldg(mg + (ch * 8 + j) * kC + cp);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {                            // S: row o, chunk j of 8 points (rows are P_in long)
+            const int i = tid + it * kThreads;
+            if (i < kPout * s_chunks) {
+                sa[it][0] = __ldg(reinterpret_cast<const float4*>(sg + i * 8));
+                sa[it][1] = __ldg(reinterpret_cast<const float4*>(sg + i * 8 + 4));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = tid + it * kThreads;
+            if (i < p_in * 8) {
+                const int p = i >> 3, ch = i & 7;
+                const float f[8] = {xa[it][0].x, xa[it][0].y, xa[it][0].z, xa[it][0].w, xa[it][1].x, xa[it][1].y, xa[it][1].z, xa[it][1].w};
+                split_store8(f, sm + kX3, 16384, p * 128 + ((ch ^ (p & 7)) << 4));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
+            split_store8(mv[it], sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = tid + it * kThreads;
+            if (i < kPout * s_chunks) {
+                const int o = i / s_chunks, j = i - o * s_chunks;
+                const float f[8] = {sa[it][0].x, sa[it][0].y, sa[it][0].z, sa[it][0].w, sa[it][1].x, sa[it][1].y, sa[it][1].z, sa[it][1].w};
+                split_store8(f, sm + kS3, s3_piece, (j >> 2) * 8192 + o * 64 + (((j & 3) ^ ((o >> 1) & 3)) << 4));
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -284,11 +311,15 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             const float rstd = rsqrtf(block_sum(q, red) / n + eps);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf((f[j] - mean) * rstd, 0.f);
+            // Stage the tile in the S3 / T3 region (dead once product 2 has completed) and write it out in full rows:
+            // a thread owns half a row of the accumulator, but neighbouring bytes of the destination belong to other threads.
+            uint8_t* stg = sm + kS3;
             if constexpr (kSplitOut) {
-                // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c' (this thread: one 32-wide K block)
+                // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c'. This thread's 32 values
+                // are one 64-byte row of a piece tile; chunks go to their swizzled position, which is the same for the whole
+                // item (it depends on the query only). Staging rows: [piece][o][half] 64 B, o-stride 144 B (bank spread).
                 const long long qi = item / tiled_groups;
-                const int k0 = (int)(item - qi * tiled_groups) * (kPout * kC) + row * kC + col0;
-                const int kblocks = tiled_groups * (kPout * kC / kTileK);
+                const int sw = (int)((qi & 127) >> 1) & 3;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     __align__(16) __nv_bfloat16 p[3][8];
@@ -296,13 +327,37 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                     for (int j = 0; j < 8; ++j) split3(f[c * 8 + j], p[0][j], p[1][j], p[2][j]);
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
-                        *reinterpret_cast<uint4*>(out3 + tiled_offset(qi, k0 + c * 8, kblocks, k)) = *reinterpret_cast<const uint4*>(p[k]);
+                        *reinterpret_cast<uint4*>(stg + k * (kPout * 144) + row * 144 + (col0 >> 5) * 64 + ((c ^ sw) << 4)) =
+                            *reinterpret_cast<const uint4*>(p[k]);
+                }
+                __syncthreads();
+                const int g = (int)(item - qi * tiled_groups);
+                const int kblocks = tiled_groups * (kPout * kC / kTileK);
+                // 3 pieces x 128 rows x 2 halves x 4 chunks = 3072 16-byte chunks; 4 consecutive lanes write one 64-byte row
+                for (int i = tid; i < 3 * kPout * 8; i += kThreads) {
+                    const int pos = i & 3, h = (i >> 2) & 1, o = (i >> 3) & 127, k = i >> 10;
+                    const uint4 v4 = *reinterpret_cast<const uint4*>(stg + k * (kPout * 144) + o * 144 + h * 64 + (pos << 4));
+                    const long long kb = (long long)g * (kPout * kC / kTileK) + o * 2 + h;      // 32-wide K block of this row
+                    __nv_bfloat16* dst = out3 + (((qi >> 7) * kblocks + kb) * 3 + k) * (long long)kTilePieceElems
+                                       + (qi & 127) * kTileK + pos * 8;
+                    *reinterpret_cast<uint4*>(dst) = v4;
                 }
             } else {
-                float* og = out + (long long)item * (kPout * kC) + row * kC + col0;
+                // fp32 rows of 256 B, staged with a 272-byte stride
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4*>(og + c * 4) = make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+                    *reinterpret_cast<float4*>(stg + row * 272 + col0 * 4 + c * 16) =
+                        make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+                __syncthreads();
+                float* og = out + (long long)item * (kPout * kC);
+                for (int i = tid; i < kPout * 16; i += kThreads) {
+                    const int o = i >> 4, c = i & 15;
+                    *reinterpret_cast<float4*>(og + o * kC + c * 4) = *reinterpret_cast<const float4*>(stg + o * 272 + c * 16);
+                }
+            }
+            if ((p_in & 31) != 0) {      // the staging area overlaps K tails that must read as zero: restore them
+                __syncthreads();
+                for (int i = tid; i < (kSmemBytes - kS3) / 16; i += kThreads) reinterpret_cast<uint4*>(stg)[i] = make_uint4(0, 0, 0, 0);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
