@@ -18,6 +18,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef RACF_MIXTC_PROFILE
+#include <cstdio>
+#endif
 
 #include "linear_tiled.cuh"
 #include "racformer_ops.h"
@@ -73,19 +76,32 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
     constexpr uint64_t layout = kRowBytes == 128 ? 2 : 4;
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((8 * kRowBytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
-    p0 = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(p0);
-    p1 = __float2bfloat16_rn(r1);
-    p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+// Exact three-way split of two floats at once: x = p0 + p1 + p2 with bf16 pieces, round to nearest at each step (the
+// residuals are exact in fp32). q[k] holds piece k of (a, b) as a bf16x2 (a in the low half). The packed conversion
+// (F2FP) is used on purpose: single cvt.rn.bf16.f32 compiles to F2F, which runs at a quarter of the rate.
+__device__ __forceinline__ void split3x2(float a, float b, uint32_t (&q)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        q[k] = *reinterpret_cast<const uint32_t*>(&h);
+        if (k < 2) {
+            a -= __uint_as_float(q[k] << 16);
+            b -= __uint_as_float(q[k] & 0xffff0000u);
+        }
+    }
 }
 // eight consecutive fp32 -> one 16-byte chunk per piece at byte offset `off` of each piece tile
 __device__ __forceinline__ void split_store8(const float (&f)[8], uint8_t* tile, int piece_bytes, int off) {
-    __align__(16) __nv_bfloat16 p[3][8];
+    uint32_t p[3][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split3(f[j], p[0][j], p[1][j], p[2][j]);
+    for (int j = 0; j < 4; ++j) {
+        uint32_t q[3];
+        split3x2(f[2 * j], f[2 * j + 1], q);
+        p[0][j] = q[0]; p[1][j] = q[1]; p[2][j] = q[2];
+    }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) *reinterpret_cast<uint4*>(tile + k * piece_bytes + off) = *reinterpret_cast<const uint4*>(p[k]);
+    for (int k = 0; k < 3; ++k)
+        *reinterpret_cast<uint4*>(tile + k * piece_bytes + off) = make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
 }
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
@@ -98,6 +114,70 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     for (int w = 0; w < kThreads / 32; ++w) t += red[w];
     return t;
 }
+
+// x [P_in][64] -> X3 (A of product 1), M [64 c][64 c'] -> M3 = M^T (B of product 1). All global loads are issued before
+// the first use, so their latency is paid once (fixed trip counts for P_in <= 128, predicated).
+__device__ __forceinline__ void load_split_xm(const float* __restrict__ xg, const float* __restrict__ mg, uint8_t* sm, int p_in, int tid) {
+    float4 xa[4][2];
+    float mv[2][8];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {                            // x: row p, 16-byte chunk ch (8 channels)
+        const int i = tid + it * kThreads;
+        if (i < p_in * 8) {
+            xa[it][0] = __ldg(reinterpret_cast<const float4*>(xg + i * 8));
+            xa[it][1] = __ldg(reinterpret_cast<const float4*>(xg + i * 8 + 4));
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {                            // M^T: row c' (lanes -> coalesced), chunk of 8 c
+        const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mv[it][j] = __ldg(mg + (ch * 8 + j) * kC + cp);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int i = tid + it * kThreads;
+        if (i < p_in * 8) {
+            const int p = i >> 3, ch = i & 7;
+            const float f[8] = {xa[it][0].x, xa[it][0].y, xa[it][0].z, xa[it][0].w, xa[it][1].x, xa[it][1].y, xa[it][1].z, xa[it][1].w};
+            split_store8(f, sm + kX3, 16384, p * 128 + ((ch ^ (p & 7)) << 4));
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
+        split_store8(mv[it], sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
+    }
+}
+
+// S [128 o][P_in] -> S3 (A of product 2): 32-wide K atoms of [128 rows][64 B], 64-byte swizzle
+__device__ __forceinline__ void load_split_s(const float* __restrict__ sg, uint8_t* sm, int p_in, int s3_piece, int tid) {
+    const int s_chunks = p_in >> 3;
+    float4 sa[8][2];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = tid + it * kThreads;
+        if (i < kPout * s_chunks) {
+            sa[it][0] = __ldg(reinterpret_cast<const float4*>(sg + i * 8));
+            sa[it][1] = __ldg(reinterpret_cast<const float4*>(sg + i * 8 + 4));
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = tid + it * kThreads;
+        if (i < kPout * s_chunks) {
+            const int o = i / s_chunks, j = i - o * s_chunks;
+            const float f[8] = {sa[it][0].x, sa[it][0].y, sa[it][0].z, sa[it][0].w, sa[it][1].x, sa[it][1].y, sa[it][1].z, sa[it][1].w};
+            split_store8(f, sm + kS3, s3_piece, (j >> 2) * 8192 + o * 64 + (((j & 3) ^ ((o >> 1) & 3)) << 4));
+        }
+    }
+}
+
+#ifdef RACF_MIXTC_PROFILE      // tuning aid: per-phase cycle counts of CTA 0 (build with RACF_NVCC_DEFINES=-DRACF_MIXTC_PROFILE)
+#define MIXTC_TICK(slot) do { if (tid == 0) { const long long now_ = clock64(); prof[slot] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define MIXTC_TICK(slot) do { } while (0)
+#endif
 
 template <bool kSplitOut>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -135,67 +215,24 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
     const int row = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 32;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + col0;
     const int m_elems = kC * kC, s_elems = kPout * p_in;
+    const long long per_item = m_elems + s_elems;
+
+#ifdef RACF_MIXTC_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    // Software pipeline over this CTA's items: x / M of item i+1 are split while product 2 of item i runs (X3 / M3 are free
+    // once product 1 has completed), S of item i while product 1 of item i runs (S3 is free once product 2 of item i-1 has).
+    if ((int)blockIdx.x < num_items)
+        load_split_xm(x + (long long)blockIdx.x * p_in * kC, params + (long long)blockIdx.x * per_item, sm, p_in, tid);
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const float* xg = x + (long long)item * p_in * kC;
-        const float* mg = params + (long long)item * (m_elems + s_elems);
-        const float* sg = mg + m_elems;
-
-        // ---- P0: split x, M^T and S into shared memory. All global loads are issued before the first use so that
-        //      their latency is paid once per item (fixed trip counts for P_in <= 128, predicated) ------------------
-        const int s_chunks = p_in >> 3;
-        float4 xa[4][2], sa[8][2];
-        float mv[2][8];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {                            // x: row p, 16-byte chunk ch (8 channels)
-            const int i = tid + it * kThreads;
-            if (i < p_in * 8) {
-                xa[it][0] = __ldg(reinterpret_cast<const float4*>(xg + i * 8));
-                xa[it][1] = __ldg(reinterpret_cast<const float4*>(xg + i * 8 + 4));
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {                            // M^T: row c' (lanes -> coalesced), chunk of 8 c
-            const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mv[it][j] = __ldg(mg + (ch * 8 + j) * kC + cp);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {                            // S: row o, chunk j of 8 points (rows are P_in long)
-            const int i = tid + it * kThreads;
-            if (i < kPout * s_chunks) {
-                sa[it][0] = __ldg(reinterpret_cast<const float4*>(sg + i * 8));
-                sa[it][1] = __ldg(reinterpret_cast<const float4*>(sg + i * 8 + 4));
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int i = tid + it * kThreads;
-            if (i < p_in * 8) {
-                const int p = i >> 3, ch = i & 7;
-                const float f[8] = {xa[it][0].x, xa[it][0].y, xa[it][0].z, xa[it][0].w, xa[it][1].x, xa[it][1].y, xa[it][1].z, xa[it][1].w};
-                split_store8(f, sm + kX3, 16384, p * 128 + ((ch ^ (p & 7)) << 4));
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
-            split_store8(mv[it], sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int i = tid + it * kThreads;
-            if (i < kPout * s_chunks) {
-                const int o = i / s_chunks, j = i - o * s_chunks;
-                const float f[8] = {sa[it][0].x, sa[it][0].y, sa[it][0].z, sa[it][0].w, sa[it][1].x, sa[it][1].y, sa[it][1].z, sa[it][1].w};
-                split_store8(f, sm + kS3, s3_piece, (j >> 2) * 8192 + o * 64 + (((j & 3) ^ ((o >> 1) & 3)) << 4));
-            }
-        }
+        const int nxt = item + gridDim.x;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        MIXTC_TICK(0);
 
-        // ---- P1: product 1 --------------------------------------------------------------------------------------
+        // ---- product 1: D1[p, c'] = x @ M -----------------------------------------------------------------------
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc_cross = 0;
@@ -211,20 +248,18 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             }
             umma_commit(bar_addr);
         }
-        // prefetch the next item's inputs into L2 while the tensor core works
-        {
-            const int nxt = item + gridDim.x;
-            if (nxt < num_items) {
-                const char* nx = reinterpret_cast<const char*>(x + (long long)nxt * p_in * kC);
-                const char* np = reinterpret_cast<const char*>(params + (long long)nxt * (m_elems + s_elems));
-                for (int i = tid * 128; i < p_in * kC * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
-                for (int i = tid * 128; i < (m_elems + s_elems) * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + i));
-            }
+        if (nxt < num_items) {      // pull the next item's inputs into L2 well before they are needed
+            const char* nx = reinterpret_cast<const char*>(x + (long long)nxt * p_in * kC);
+            const char* np = reinterpret_cast<const char*>(params + (long long)nxt * per_item);
+            for (int i = tid * 128; i < p_in * kC * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+            for (int i = tid * 128; i < (int)per_item * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(np + i));
         }
+        load_split_s(params + (long long)item * per_item + m_elems, sm, p_in, s3_piece, tid);   // overlaps product 1
         mbar_wait(bar_addr, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        MIXTC_TICK(1);
 
-        // ---- P2: LayerNorm + ReLU of D1 (rows < P_in), split, store t^T as the B operand of product 2 ------------
+        // ---- LayerNorm + ReLU of D1 (rows < P_in), split, store t^T as the B operand of product 2 -----------------
         {
             uint32_t v[32], u[32];
             tmem_ld32(tm_lane, v);
@@ -252,22 +287,26 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                 const int atom = row >> 5, kk = row & 31;
                 uint8_t* base = sm + kT3 + atom * 4096 + (kk & 7) * 2;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int cp = col0 + j;
-                    __nv_bfloat16 p0, p1, p2;
-                    split3(fmaxf((f[j] - mean) * rstd, 0.f), p0, p1, p2);
-                    uint8_t* e = base + cp * 64 + (((kk >> 3) ^ ((cp >> 1) & 3)) << 4);
-                    *reinterpret_cast<__nv_bfloat16*>(e) = p0;
-                    *reinterpret_cast<__nv_bfloat16*>(e + t3_piece) = p1;
-                    *reinterpret_cast<__nv_bfloat16*>(e + 2 * t3_piece) = p2;
+                for (int j = 0; j < 32; j += 2) {
+                    uint32_t pc[3];
+                    split3x2(fmaxf((f[j] - mean) * rstd, 0.f), fmaxf((f[j + 1] - mean) * rstd, 0.f), pc);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cp = col0 + j + h;
+                        uint8_t* e = base + cp * 64 + (((kk >> 3) ^ ((cp >> 1) & 3)) << 4);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            *reinterpret_cast<uint16_t*>(e + k * t3_piece) = (uint16_t)(h ? (pc[k] >> 16) : (pc[k] & 0xffffu));
+                    }
                 }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        MIXTC_TICK(2);
 
-        // ---- P3: product 2 --------------------------------------------------------------------------------------
+        // ---- product 2: D2[o, c'] = S @ t -----------------------------------------------------------------------
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc_cross = 0;
@@ -284,10 +323,13 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             }
             umma_commit(bar_addr);
         }
+        if (nxt < num_items)        // overlaps product 2: X3 / M3 are no longer read
+            load_split_xm(x + (long long)nxt * p_in * kC, params + (long long)nxt * per_item, sm, p_in, tid);
         mbar_wait(bar_addr, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        MIXTC_TICK(3);
 
-        // ---- P4: LayerNorm + ReLU of D2 -> global ------------------------------------------------------------------
+        // ---- LayerNorm + ReLU of D2 -> global ----------------------------------------------------------------------
         {
             uint32_t v[32], u[32];
             tmem_ld32(tm_lane + 128, v);
@@ -311,8 +353,8 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             const float rstd = rsqrtf(block_sum(q, red) / n + eps);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf((f[j] - mean) * rstd, 0.f);
-            // Stage the tile in the S3 / T3 region (dead once product 2 has completed) and write it out in full rows:
-            // a thread owns half a row of the accumulator, but neighbouring bytes of the destination belong to other threads.
+            // Stage the tile in the S3 region (dead once product 2 has completed) and write it out in full rows: a thread
+            // owns half a row of the accumulator, but neighbouring bytes of the destination belong to other threads.
             uint8_t* stg = sm + kS3;
             if constexpr (kSplitOut) {
                 // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c'. This thread's 32 values
@@ -322,13 +364,17 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                 const int sw = (int)((qi & 127) >> 1) & 3;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    __align__(16) __nv_bfloat16 p[3][8];
+                    uint32_t p[3][4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) split3(f[c * 8 + j], p[0][j], p[1][j], p[2][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t pc[3];
+                        split3x2(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1], pc);
+                        p[0][j] = pc[0]; p[1][j] = pc[1]; p[2][j] = pc[2];
+                    }
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         *reinterpret_cast<uint4*>(stg + k * (kPout * 144) + row * 144 + (col0 >> 5) * 64 + ((c ^ sw) << 4)) =
-                            *reinterpret_cast<const uint4*>(p[k]);
+                            make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
                 }
                 __syncthreads();
                 const int g = (int)(item - qi * tiled_groups);
@@ -355,16 +401,21 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                     *reinterpret_cast<float4*>(og + o * kC + c * 4) = *reinterpret_cast<const float4*>(stg + o * 272 + c * 16);
                 }
             }
-            if ((p_in & 31) != 0) {      // the staging area overlaps K tails that must read as zero: restore them
+            if ((p_in & 31) != 0) {      // the staging area overlaps K tails of S3 that must read as zero: restore them
                 __syncthreads();
-                for (int i = tid; i < (kSmemBytes - kS3) / 16; i += kThreads) reinterpret_cast<uint4*>(stg)[i] = make_uint4(0, 0, 0, 0);
+                for (int i = tid; i < (kT3 - kS3) / 16; i += kThreads) reinterpret_cast<uint4*>(stg)[i] = make_uint4(0, 0, 0, 0);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();          // D1 / D2 and the operand tiles may be overwritten by the next item
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        MIXTC_TICK(4);
+        // the loop-top barrier orders these reads of the staging area / TMEM before the next item's writes
     }
-
+#ifdef RACF_MIXTC_PROFILE
+    if (tid == 0 && blockIdx.x == 0)
+        printf("mixtc cycles (CTA 0): sync %lld mma1|S-split %lld ln1 %lld mma2|xM-split %lld ln2+out %lld\n", prof[0], prof[1],
+               prof[2], prof[3], prof[4]);
+#endif
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
