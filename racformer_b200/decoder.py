@@ -661,7 +661,7 @@ class AdaptiveMixing(nn.Module):
             split = self._tensor_core_linear(query)      # emit the bf16 pieces out_proj consumes, no fp32 round trip
             core = points.adaptive_mixing_core(x.reshape(B * Q * G, P, C).contiguous(),
                                                params.reshape(B * Q * G, -1).contiguous(), self.out_points, split=split,
-                                               tiled_groups=G if split else 0)
+                                               tiled_groups=G if split else 0, tensor_cores=split)
             if core is not None:
                 if split:
                     return query + self._split_linear("out_proj")(x3=core, lead=(B, Q))
