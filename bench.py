@@ -45,6 +45,27 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_roofline(kernels):
+    """Secondary roofline entry for the tcgen05 Linear kernel (the largest kernel of the step after the sampling ops moved
+    out of the way): issued bf16 MMA throughput against the measured dense bf16 peak. It is a fp32-grade GEMM evaluated
+    as six exact bf16 piece products per fp32 product, so the fp32-equivalent rate is one sixth of the issued rate."""
+    k = (kernels or {}).get("linear_parameter_generator")
+    if not k:
+        return None
+    peak, src = 1600.0, "fallback (B200_PROFILING.md)"
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        peak, src = float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", peak))), "measured, sustained (MEASURED_PEAKS.json)"
+    return {"kernel": "linear_bf16x3_kernel (AdaptiveMixing.parameter_generator, %dx%dx%d)" % tuple(k["shape"]), "bound": "tensor",
+            "achieved": k["issued_bf16_mma_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": k["issued_bf16_mma_tflops"] / peak,
+            "fp32_equivalent_tflops": k["fp32_equivalent_tflops"], "bf16_terms_per_product": k["bf16_terms_per_product"],
+            "avg_launch_us": k["avg_us"], "peak_source": src, "timing": "CUDA events, eager pass after the timed region",
+            "note": "limited by L2->SM operand traffic (1.6 GB per launch at 128x128 tiles), not by the tensor pipe: "
+                    "profiles/r01c_linear_ncu_summary.json"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -246,6 +267,7 @@ def _main():
                     "d2h_bytes_per_step": wl.d2h_bytes_per_step, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": roof,
+            "roofline_tensor": tensor_roofline(kernels),
             "cpu_baseline": cpu_baseline,
             "kernels": kernels,
         }

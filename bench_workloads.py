@@ -287,6 +287,7 @@ class DecoderWorkload:
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None
+        self.tensor_shapes = {}
 
     def config(self):
         return {"workload": self.name, "shapes": "racformer_r50_nuimg_704x256_f8", "batch_per_gpu": 1, "num_query": 900,
@@ -339,9 +340,51 @@ class DecoderWorkload:
                 self._collect_graph_events = False
             return self._graphed()
         self._time_kernels = time_kernels
-        out = self._forward(self.inp)
+        if time_kernels:
+            with self._timed_tensor_core_kernels():
+                out = self._forward(self.inp)
+        else:
+            out = self._forward(self.inp)
         self._time_kernels = False
         return out
+
+    def _timed_tensor_core_kernels(self):
+        """Eager timing pass only: CUDA events around the tcgen05 Linear and AdaptiveMixing launches (module-level
+        functions of racformer_b200.linear / .points, looked up at call time by the decoder)."""
+        import contextlib
+        from racformer_b200 import linear, points
+        wl = self
+
+        @contextlib.contextmanager
+        def ctx():
+            lin, mix = linear.linear_bf16x3, points.adaptive_mixing_core
+
+            def timed_linear(a3, w3, bias=None, *args, **kw):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = lin(a3, w3, bias, *args, **kw)
+                b.record()
+                M, K, N = (a3.rows, a3.K, w3.rows) if isinstance(a3, linear.TiledOperand) else (a3.shape[1], a3.shape[2], w3.shape[1])
+                name = {(256, 65536): "linear_parameter_generator", (32768, 256): "linear_out_proj"}.get((K, N), "linear_value_proj")
+                wl.timers.setdefault(name, []).append((a, b))
+                wl.tensor_shapes[name] = (M, N, K)
+                return out
+
+            def timed_mixing(x, params, out_points, *args, **kw):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = mix(x, params, out_points, *args, **kw)
+                b.record()
+                wl.timers.setdefault("adaptive_mixing_core", []).append((a, b))
+                wl.tensor_shapes["adaptive_mixing_core"] = tuple(x.shape) + (out_points,)
+                return out
+
+            linear.linear_bf16x3, points.adaptive_mixing_core = timed_linear, timed_mixing
+            try:
+                yield
+            finally:
+                linear.linear_bf16x3, points.adaptive_mixing_core = lin, mix
+        return ctx()
 
     def kernel_report(self, hbm_peak):
         from racformer_b200 import wrapper
@@ -368,9 +411,22 @@ class DecoderWorkload:
             except Exception:
                 pass
         rep["kernel_timing"] = timing
+        passes = max(1, len(sources.get("msda_fwd", [])) // (2 * self.layers)) if "msda_fwd" in sources else 1
         for key, pairs in sources.items():
             ms = [a.elapsed_time(b) for a, b in pairs]
             avg = sum(ms) / len(ms)
+            if key in self.tensor_shapes:      # tcgen05 kernels (eager pass): fp32-equivalent and issued bf16 MMA throughput
+                shp = self.tensor_shapes[key]
+                if key == "adaptive_mixing_core":
+                    qg, p_in, c, p_out = shp
+                    flops = 2.0 * qg * (p_in * c * c + p_out * p_in * c)
+                else:
+                    flops = 2.0 * shp[0] * shp[1] * shp[2]
+                terms = 9 if self.mixing_precision == "bf16x9" and key != "adaptive_mixing_core" else 6
+                rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / passes, "shape": list(shp),
+                            "fp32_equivalent_tflops": flops / (avg * 1e-3) / 1e12,
+                            "issued_bf16_mma_tflops": terms * flops / (avg * 1e-3) / 1e12, "bf16_terms_per_product": terms}
+                continue
             rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / max(1, len(ms) // (
                 self.layers * (2 if key == "msda_fwd" else 1)))}
             if key in algo:
