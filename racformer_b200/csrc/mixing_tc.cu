@@ -28,7 +28,7 @@
 namespace racf {
 namespace mixtc {
 
-constexpr int kC = 64, kPout = 128, kThreads = 256;
+constexpr int kC = 64, kPout = 128, kThreads = 512;   // 16 warps: 4 per TMEM lane quarter, 16 accumulator columns each
 constexpr int kX3 = 0;                          // 3 x 16 KB: [128][64] bf16, 128-byte rows, 128-byte swizzle
 constexpr int kM3 = kX3 + 3 * 16384;            // 3 x  8 KB: [64][64]
 constexpr int kS3 = kM3 + 3 * 8192;             // 3 x 4 atoms x 8 KB: [128][32] per atom, 64-byte rows, 64-byte swizzle
@@ -68,6 +68,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
 // K-major bf16 tile, rows one swizzle span wide (128 or 64 bytes); 8-row groups SBO = 8 rows apart
@@ -118,10 +126,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // x [P_in][64] -> X3 (A of product 1), M [64 c][64 c'] -> M3 = M^T (B of product 1). All global loads are issued before
 // the first use, so their latency is paid once (fixed trip counts for P_in <= 128, predicated).
 __device__ __forceinline__ void load_split_xm(const float* __restrict__ xg, const float* __restrict__ mg, uint8_t* sm, int p_in, int tid) {
-    float4 xa[4][2];
-    float mv[2][8];
+    constexpr int kXIt = 128 * 8 / kThreads, kMIt = kC * 8 / kThreads;
+    float4 xa[kXIt][2];
+    float mv[kMIt][8];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {                            // x: row p, 16-byte chunk ch (8 channels)
+    for (int it = 0; it < kXIt; ++it) {                         // x: row p, 16-byte chunk ch (8 channels)
         const int i = tid + it * kThreads;
         if (i < p_in * 8) {
             xa[it][0] = __ldg(reinterpret_cast<const float4*>(xg + i * 8));
@@ -129,13 +138,13 @@ __device__ __forceinline__ void load_split_xm(const float* __restrict__ xg, cons
         }
     }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {                            // M^T: row c' (lanes -> coalesced), chunk of 8 c
+    for (int it = 0; it < kMIt; ++it) {                         // M^T: row c' (lanes -> coalesced), chunk of 8 c
         const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
 #pragma unroll
         for (int j = 0; j < 8; ++j) mv[it][j] = __ldg(mg + (ch * 8 + j) * kC + cp);
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < kXIt; ++it) {
         const int i = tid + it * kThreads;
         if (i < p_in * 8) {
             const int p = i >> 3, ch = i & 7;
@@ -144,7 +153,7 @@ __device__ __forceinline__ void load_split_xm(const float* __restrict__ xg, cons
         }
     }
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < kMIt; ++it) {
         const int i = tid + it * kThreads, cp = i & 63, ch = i >> 6;
         split_store8(mv[it], sm + kM3, 8192, cp * 128 + ((ch ^ (cp & 7)) << 4));
     }
@@ -153,9 +162,10 @@ __device__ __forceinline__ void load_split_xm(const float* __restrict__ xg, cons
 // S [128 o][P_in] -> S3 (A of product 2): 32-wide K atoms of [128 rows][64 B], 64-byte swizzle
 __device__ __forceinline__ void load_split_s(const float* __restrict__ sg, uint8_t* sm, int p_in, int s3_piece, int tid) {
     const int s_chunks = p_in >> 3;
-    float4 sa[8][2];
+    constexpr int kSIt = kPout * 16 / kThreads;
+    float4 sa[kSIt][2];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < kSIt; ++it) {
         const int i = tid + it * kThreads;
         if (i < kPout * s_chunks) {
             sa[it][0] = __ldg(reinterpret_cast<const float4*>(sg + i * 8));
@@ -163,7 +173,7 @@ __device__ __forceinline__ void load_split_s(const float* __restrict__ sg, uint8
         }
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < kSIt; ++it) {
         const int i = tid + it * kThreads;
         if (i < kPout * s_chunks) {
             const int o = i / s_chunks, j = i - o * s_chunks;
@@ -211,8 +221,8 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
     const uint32_t tmem = tmem_slot;
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-    // this thread's slice of an accumulator tile: TMEM lane quarter (warp % 4), 32 of the 64 columns (warp / 4)
-    const int row = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 32;
+    // this thread's slice of an accumulator tile: TMEM lane quarter (warp % 4), 16 of the 64 columns (warp / 4)
+    const int row = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 16;
     const uint32_t tm_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + col0;
     const int m_elems = kC * kC, s_elems = kPout * p_in;
     const long long per_item = m_elems + s_elems;
@@ -261,15 +271,15 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
 
         // ---- LayerNorm + ReLU of D1 (rows < P_in), split, store t^T as the B operand of product 2 -----------------
         {
-            uint32_t v[32], u[32];
-            tmem_ld32(tm_lane, v);
-            tmem_ld32(tm_lane + 64, u);
+            uint32_t v[16], u[16];
+            tmem_ld16(tm_lane, v);
+            tmem_ld16(tm_lane + 64, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float f[32];
+            float f[16];
             float s = 0.f;
             const bool live = row < p_in;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 f[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
                 s += live ? f[j] : 0.f;
             }
@@ -277,7 +287,7 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             const float mean = block_sum(s, red) / n;
             float q = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float d = f[j] - mean;
                 q += live ? d * d : 0.f;
             }
@@ -287,7 +297,7 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                 const int atom = row >> 5, kk = row & 31;
                 uint8_t* base = sm + kT3 + atom * 4096 + (kk & 7) * 2;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < 16; j += 2) {
                     uint32_t pc[3];
                     split3x2(fmaxf((f[j] - mean) * rstd, 0.f), fmaxf((f[j + 1] - mean) * rstd, 0.f), pc);
 #pragma unroll
@@ -331,14 +341,14 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
 
         // ---- LayerNorm + ReLU of D2 -> global ----------------------------------------------------------------------
         {
-            uint32_t v[32], u[32];
-            tmem_ld32(tm_lane + 128, v);
-            tmem_ld32(tm_lane + 192, u);
+            uint32_t v[16], u[16];
+            tmem_ld16(tm_lane + 128, v);
+            tmem_ld16(tm_lane + 192, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float f[32];
+            float f[16];
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 f[j] = __uint_as_float(v[j]) + __uint_as_float(u[j]);
                 s += f[j];
             }
@@ -346,24 +356,25 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             const float mean = block_sum(s, red) / n;
             float q = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float d = f[j] - mean;
                 q += d * d;
             }
             const float rstd = rsqrtf(block_sum(q, red) / n + eps);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf((f[j] - mean) * rstd, 0.f);
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf((f[j] - mean) * rstd, 0.f);
             // Stage the tile in the S3 region (dead once product 2 has completed) and write it out in full rows: a thread
             // owns half a row of the accumulator, but neighbouring bytes of the destination belong to other threads.
             uint8_t* stg = sm + kS3;
             if constexpr (kSplitOut) {
-                // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c'. This thread's 32 values
-                // are one 64-byte row of a piece tile; chunks go to their swizzled position, which is the same for the whole
-                // item (it depends on the query only). Staging rows: [piece][o][half] 64 B, o-stride 144 B (bank spread).
+                // A operand of out_proj, tiled format: row = query, k = group * 8192 + o * 64 + c'. This thread's 16 values
+                // are half of one 64-byte row of a piece tile; chunks go to their swizzled position, which is the same for the
+                // whole item (it depends on the query only). Staging rows: [piece][o][half] 64 B, o-stride 144 B (bank spread).
                 const long long qi = item / tiled_groups;
                 const int sw = (int)((qi & 127) >> 1) & 3;
+                const int c_base = (col0 & 31) >> 3;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t p[3][4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -373,7 +384,7 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
                     }
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
-                        *reinterpret_cast<uint4*>(stg + k * (kPout * 144) + row * 144 + (col0 >> 5) * 64 + ((c ^ sw) << 4)) =
+                        *reinterpret_cast<uint4*>(stg + k * (kPout * 144) + row * 144 + (col0 >> 5) * 64 + (((c_base + c) ^ sw) << 4)) =
                             make_uint4(p[k][0], p[k][1], p[k][2], p[k][3]);
                 }
                 __syncthreads();
@@ -391,7 +402,7 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
             } else {
                 // fp32 rows of 256 B, staged with a 272-byte stride
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<float4*>(stg + row * 272 + col0 * 4 + c * 16) =
                         make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
                 __syncthreads();
