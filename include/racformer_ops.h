@@ -273,6 +273,72 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
                                      int max_order, int tiled, racf_stream_t stream);
 
 /*
+ * Call-site row: box refinement at the end of a decoder iteration
+ * (models/racformer_transformer.py:255-259,264-279 and theta_d2xy_coods, models/bbox/utils.py:82-90) as one launch.
+ *   proposal, delta : [batch * num_query, code_size]  the iteration's input rays and the reg branch output
+ *   time_diff       : [batch, num_frames] or NULL; with num_frames > 1 the velocity columns (>= 8) are divided by
+ *                     time_diff[b, 1] (1 where it is < 1e-5)
+ *   pred            : (theta + (2 sigmoid(delta_0) - 1) / num_ray, sigmoid(delta_1:3 + inverse_sigmoid(proposal_1:3)),
+ *                     delta_3:)                                              -- the next iteration's query rays
+ *   pred_xy         : pred with (theta, d) mapped to clamped normalised (x, y)  -- the iteration's box output
+ */
+int racf_refine_bbox_forward(const float* proposal, const float* delta, const float* time_diff, int batch,
+                             int num_query, int num_frames, int code_size, float num_ray, float* pred,
+                             float* pred_xy, racf_stream_t stream);
+
+/*
+ * Call-site row: the row-wise operators between the sampling ops of one decoder iteration
+ * (models/racformer_transformer.py:204-262: position_encoder, norm1..3, fusion, FFN, cls / reg branches; the softmax
+ * queue fusion + output_proj of models/bev_self_attention.py:206-225) as ONE launch. Rows (queries) never interact, so
+ * each CTA carries rows_per_cta rows through the whole chain in shared memory, interpreting a short program.
+ *
+ * A program works on `num_bufs` shared-memory buffers of [rows_per_cta][width] floats. Operators (kind):
+ *   LOAD           buf[dst][r][dst_col + c] = p0[row * ld + c],                               c < n
+ *   LOAD_QUEUE     buf[dst][r][dst_col + c] = sum_t softmax_t(p1[row * aux + t]) * p0[((b * aux + t) * k + q) * ld + c]
+ *                  with row = b * k + q (k = rows per batch element, aux = queue length <= RACF_ROW_MAX_QUEUE;
+ *                  p1 == NULL: plain mean over the queue)
+ *   STORE          out[row * ld + c] = buf[src][r][src_col + c],                              c < n
+ *   ADD            buf[dst][.. dst_col + c] += buf[src][.. src_col + c],                      c < n
+ *   LINEAR         buf[dst][.. dst_col + j] = act(p1[j] + sum_{i<k} buf[src][.. src_col + i] * p0[i * n + j]),  j < n
+ *                  p0 = the nn.Linear weight W [n][k] as its chunked transpose [ceil(n / 256)][k][256]
+ *                  (element [c][i][jj] = W[c * 256 + jj][i], zero for c * 256 + jj >= n; 16-byte aligned),
+ *                  p1 = bias or NULL; dst != src, src_col % 4 == 0
+ *   LINEAR_NARROW  the same for a few output columns with p0 = the weight in nn.Linear's own layout [n][k]
+ *                  (n * k <= 8192, a multiple of 4, 16-byte aligned)
+ *   LAYERNORM      in place over buf[dst][.. dst_col .. dst_col + n), gamma p0 / beta p1 (either may be NULL), eps
+ * flags & RACF_ROWOP_RELU applies max(., 0) to the operator's result (LINEAR*, LAYERNORM).
+ * LOAD_QUEUE needs n, ld, dst_col multiples of 4 and a 16-byte aligned p0.
+ * fp32 FMA on the CUDA cores, bias added last. `ops` is a HOST array, copied into the kernel parameters
+ * (capture-safe). rows_per_cta is 4 or 8; 128 KB (weight tiles) + num_bufs * rows_per_cta * width * 4 bytes <= 226 KB.
+ */
+#define RACF_ROW_MAX_OPS        40
+#define RACF_ROW_MAX_QUEUE      16
+#define RACF_ROW_CHUNK_COLS    256
+#define RACF_ROWOP_LOAD          1
+#define RACF_ROWOP_LOAD_QUEUE    2
+#define RACF_ROWOP_STORE         3
+#define RACF_ROWOP_ADD           4
+#define RACF_ROWOP_LINEAR        5
+#define RACF_ROWOP_LINEAR_NARROW 6
+#define RACF_ROWOP_LAYERNORM     7
+#define RACF_ROWOP_RELU          1   /* flags bit */
+typedef struct racf_row_op {
+    int kind;
+    int dst, dst_col;
+    int src, src_col;
+    int n, k;
+    int flags;
+    int ld;
+    int aux;
+    float eps;
+    const float* p0;
+    const float* p1;
+    float* out;
+} racf_row_op_t;
+int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, int rows, int rows_per_cta, int num_bufs,
+                             int width, racf_stream_t stream);
+
+/*
  * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
  * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
  * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.

@@ -276,3 +276,63 @@ extern "C" int racf_bev_points_forward(const float* query_ray, const float* offs
     bev_points_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Box refinement at the end of a decoder iteration (models/racformer_transformer.py:264-279 refine_bbox + the
+// relative -> absolute velocity scaling :255-259 + theta_d2xy_coods of the prediction, models/bbox/utils.py:82-90):
+// ~25 PyTorch elementwise launches per iteration as one. One thread per query; separate multiplies / adds where PyTorch
+// runs separate kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace racf {
+
+__device__ __forceinline__ float torch_sigmoid(float x) { return fdiv(1.f, fadd(1.f, expf(-x))); }
+
+__device__ __forceinline__ float torch_inverse_sigmoid(float x, float eps) {
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    return logf(fdiv(fmaxf(x, eps), fmaxf(fsub(1.f, x), eps)));
+}
+
+__global__ void __launch_bounds__(128)
+refine_bbox_kernel(const float* __restrict__ proposal, const float* __restrict__ delta, const float* __restrict__ time_diff,
+                   int rows, int num_query, int num_frames, int code, float num_ray, float* __restrict__ pred,
+                   float* __restrict__ pred_xy) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const float* p = proposal + (size_t)row * code;
+    const float* d = delta + (size_t)row * code;
+    float* o = pred + (size_t)row * code;
+    float* oxy = pred_xy + (size_t)row * code;
+    const float theta = fadd(p[0], fdiv(fsub(fmul(torch_sigmoid(d[0]), 2.f), 1.f), num_ray));
+    const float dist = torch_sigmoid(fadd(d[1], torch_inverse_sigmoid(p[1], 1e-5f)));
+    const float z = torch_sigmoid(fadd(d[2], torch_inverse_sigmoid(p[2], 1e-5f)));
+    o[0] = theta; o[1] = dist; o[2] = z;
+    float x, y;
+    polar_to_xy(theta, dist, x, y);
+    oxy[0] = x; oxy[1] = y; oxy[2] = z;
+    float td = 1.f;
+    if (time_diff != nullptr && num_frames > 1) {      // relative -> absolute velocity
+        td = time_diff[(size_t)(row / num_query) * num_frames + 1];
+        if (td < 1e-5f) td = 1.f;
+    }
+    for (int c = 3; c < code; ++c) {
+        float v = d[c];
+        if (c >= 8 && time_diff != nullptr && num_frames > 1) v = fdiv(v, td);
+        o[c] = v;
+        oxy[c] = v;
+    }
+}
+
+}  // namespace racf
+
+extern "C" int racf_refine_bbox_forward(const float* proposal, const float* delta, const float* time_diff, int batch,
+                                        int num_query, int num_frames, int code_size, float num_ray, float* pred,
+                                        float* pred_xy, racf_stream_t stream) {
+    using namespace racf;
+    if (!proposal || !delta || !pred || !pred_xy) return RACF_ERR_NULL_POINTER;
+    if (batch <= 0 || num_query <= 0 || num_frames <= 0 || code_size < 3 || !(num_ray > 0.f)) return RACF_ERR_BAD_SHAPE;
+    const long long rows = (long long)batch * num_query;
+    if (rows > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
+    refine_bbox_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        proposal, delta, time_diff, (int)rows, num_query, num_frames, code_size, num_ray, pred, pred_xy);
+    return (int)cudaGetLastError();
+}

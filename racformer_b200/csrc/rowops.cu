@@ -1,0 +1,509 @@
+// Row programs: the per-query "glue" of a decoder iteration in ONE launch (sm_100a).
+//
+// Between the sampling ops, the decoder layer (models/racformer_transformer.py:239-262) is a chain of row-wise
+// operators on the [B*Q, 256] query matrix: Linear, LayerNorm, ReLU, residual adds, concatenation
+// (position_encoder :204-211, norm1..3, fusion :231, FFN, cls/reg branches :214-226; the softmax queue fusion and
+// output_proj of models/bev_self_attention.py:206-225). PyTorch runs them as ~150 launches of 2-12 us per iteration.
+// Rows never interact, so a CTA can carry a tile of kRows rows through the WHOLE chain in shared memory: the host
+// describes the chain as a short program of racf_row_op_t records (passed by value in the kernel parameters, so a
+// CUDA graph captures it), every CTA interprets the same program on its own rows.
+//
+// Arithmetic is fp32 FMA on the CUDA cores; a dot product is two ascending-k partial sums (the 16-wide k halves of
+// every 32-wide tile) added at the end, the bias last (the order of a GEMM epilogue). Weights are kept by the host as
+// chunked transposes W^T [N/256][K][256]; a [32 k][256 column] tile is one contiguous 32 KB block that ONE thread moves
+// into shared memory with cp.async.bulk (TMA engine) behind an mbarrier, four tiles deep and across operator
+// boundaries. Every CTA reads the same <= 0.8 MB per Linear from L2: L2 -> SM bandwidth and the FMA pipe bound the
+// kernel, not HBM (a first version with per-thread LDG weight loads was latency-bound at 40 us per 256x256 layer).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "racformer_ops.h"
+
+namespace racf {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kChunkCols = RACF_ROW_CHUNK_COLS;           // 256 output columns per weight chunk
+constexpr int kTileK = 32;                                // k rows per weight tile
+constexpr int kTileFloats = kTileK * kChunkCols;          // 32 KB
+constexpr int kStages = 4;                                // weight tiles in flight (3 ahead of the one being used)
+
+struct RowProgram {
+    racf_row_op_t ops[RACF_ROW_MAX_OPS];
+    int num_ops;
+    int rows;        // total rows
+    int width;       // floats per buffer row (multiple of 4)
+    int num_bufs;
+};
+
+// ---- PTX wrappers (mbarrier + 1-D bulk copy on the TMA engine)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// The weight-tile stream: every LINEAR operator of the program, in program order, contributes its tiles
+// [chunk][k block] (each a contiguous <= 32 KB block of the chunked transposed weight). One thread walks this
+// cursor and keeps kStages tiles in flight across operator boundaries, so the next Linear's weights are already
+// arriving while the CTA is still in a LayerNorm.
+struct TileCursor {
+    int op, chunk, kb;
+};
+
+__device__ __forceinline__ bool next_tile(const RowProgram& prog, TileCursor& cur, const float*& src, uint32_t& bytes) {
+    while (cur.op < prog.num_ops) {
+        const racf_row_op_t& op = prog.ops[cur.op];
+        if (op.kind == RACF_ROWOP_LINEAR) {
+            const int kblocks = (op.k + kTileK - 1) / kTileK, chunks = (op.n + kChunkCols - 1) / kChunkCols;
+            if (cur.chunk < chunks) {
+                const int k0 = cur.kb * kTileK;
+                const int kn = min(kTileK, op.k - k0);
+                src = op.p0 + ((size_t)cur.chunk * op.k + k0) * kChunkCols;
+                bytes = (uint32_t)kn * kChunkCols * 4u;
+                if (++cur.kb == kblocks) { cur.kb = 0; ++cur.chunk; }
+                return true;
+            }
+        } else if (op.kind == RACF_ROWOP_LINEAR_NARROW && cur.chunk == 0) {   // the whole [n][k] weight is one tile
+            src = op.p0;
+            bytes = (uint32_t)(op.n * op.k) * 4u;
+            cur.chunk = 1;
+            return true;
+        }
+        ++cur.op; cur.chunk = 0; cur.kb = 0;
+    }
+    return false;
+}
+
+// dst[r][j] = act(bias[j] + sum_k src[r][k] * W[j][k]); the weight arrives as tiles of W^T through shared memory.
+// Thread = (column pair, k half): it owns 2 columns x kRows rows and the upper or lower 16 k of every tile, so each
+// weight element is read from shared memory once (LDS.64) and each input once per warp (LDS.128 broadcast): 4 + kRows
+// shared-memory wavefronts per 8 * kRows FMAs -- the shared-memory pipe and the FMA pipe are equally loaded. The two k
+// halves are added at the end of a chunk through the destination buffer.
+template <int kRows>
+__device__ __forceinline__ void op_linear(const RowProgram& prog, const racf_row_op_t& op, float* bufs, const float* wtiles,
+                                          uint32_t full_bar, int width, int tid, unsigned& consumed, TileCursor& cursor) {
+    constexpr int kHalf = kTileK / 2;
+    const int jp = tid & 127, h = tid >> 7;
+    const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
+    float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+    const int N = op.n, K = op.k;
+    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
+    const int kblocks = (K + kTileK - 1) / kTileK, chunks = (N + kChunkCols - 1) / kChunkCols;
+    for (int c = 0; c < chunks; ++c) {
+        float acc[kRows][2];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r][0] = acc[r][1] = 0.f;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int stage = consumed % kStages;
+            mbar_wait(full_bar + 8u * stage, (consumed / kStages) & 1u);
+            const float* ws = wtiles + (size_t)stage * kTileFloats + 2 * jp;
+            const float* xs = src + kb * kTileK;
+            const int kn = min(kTileK, K - kb * kTileK);
+            if (kn == kTileK) {
+                const float* wh = ws + h * kHalf * kChunkCols;
+                const float* xh = xs + h * kHalf;
+#pragma unroll
+                for (int kk = 0; kk < kHalf; kk += 4) {
+                    const float2 w0 = *reinterpret_cast<const float2*>(wh + (kk + 0) * kChunkCols);
+                    const float2 w1 = *reinterpret_cast<const float2*>(wh + (kk + 1) * kChunkCols);
+                    const float2 w2 = *reinterpret_cast<const float2*>(wh + (kk + 2) * kChunkCols);
+                    const float2 w3 = *reinterpret_cast<const float2*>(wh + (kk + 3) * kChunkCols);
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const float4 x = *reinterpret_cast<const float4*>(xh + r * width + kk);
+                        acc[r][0] = fmaf(x.x, w0.x, acc[r][0]); acc[r][1] = fmaf(x.x, w0.y, acc[r][1]);
+                        acc[r][0] = fmaf(x.y, w1.x, acc[r][0]); acc[r][1] = fmaf(x.y, w1.y, acc[r][1]);
+                        acc[r][0] = fmaf(x.z, w2.x, acc[r][0]); acc[r][1] = fmaf(x.z, w2.y, acc[r][1]);
+                        acc[r][0] = fmaf(x.w, w3.x, acc[r][0]); acc[r][1] = fmaf(x.w, w3.y, acc[r][1]);
+                    }
+                }
+            } else {                               // K tail (or a tiny K): the halves take alternate k
+                for (int kk = h; kk < kn; kk += 2) {
+                    const float2 w = *reinterpret_cast<const float2*>(ws + kk * kChunkCols);
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        const float x = xs[r * width + kk];
+                        acc[r][0] = fmaf(x, w.x, acc[r][0]); acc[r][1] = fmaf(x, w.y, acc[r][1]);
+                    }
+                }
+            }
+            __syncthreads();                       // every thread is done with this stage
+            ++consumed;
+            if (tid == 0) {                        // refill it with the tile kStages ahead
+                const float* g; uint32_t bytes;
+                if (next_tile(prog, cursor, g, bytes)) {
+                    mbar_arrive_expect_tx(full_bar + 8u * stage, bytes);
+                    tma_load_bulk(smem_u32(wtiles + (size_t)stage * kTileFloats), g, bytes, full_bar + 8u * stage);
+                }
+            }
+        }
+        const int j = c * kChunkCols + 2 * jp;
+        if (h == 1) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (j + e < N) {
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) dst[r * width + j + e] = acc[r][e];
+                }
+        }
+        __syncthreads();
+        if (h == 0) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (j + e < N) {
+                    const float b = op.p1 != nullptr ? __ldg(op.p1 + j + e) : 0.f;
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        float v = (acc[r][e] + dst[r * width + j + e]) + b;
+                        if (relu) v = fmaxf(v, 0.f);
+                        dst[r * width + j + e] = v;
+                    }
+                }
+        }
+    }
+}
+
+// Narrow outputs (a few columns, n * k <= 8192): the weight W [n][k] (nn.Linear's own layout) arrives as ONE tile of the
+// stream; one warp per row, lanes split k, warp-shuffle reduction per output column.
+template <int kRows>
+__device__ __forceinline__ void op_linear_narrow(const RowProgram& prog, const racf_row_op_t& op, float* bufs,
+                                                 const float* wtiles, uint32_t full_bar, int width, int tid,
+                                                 unsigned& consumed, TileCursor& cursor) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int N = op.n, K = op.k;
+    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
+    const int stage = consumed % kStages;
+    mbar_wait(full_bar + 8u * stage, (consumed / kStages) & 1u);
+    const float* w = wtiles + (size_t)stage * kTileFloats;
+    for (int r = warp; r < kRows; r += kRowWarps) {
+        const float* src = bufs + ((size_t)op.src * kRows + r) * width + op.src_col;
+        float* dst = bufs + ((size_t)op.dst * kRows + r) * width + op.dst_col;
+        for (int j0 = 0; j0 < N; j0 += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = lane; k < K; k += 32) {
+                const float x = src[k];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j0 + e < N) acc[e] = fmaf(x, w[(j0 + e) * K + k], acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float s = warp_sum(acc[e]);
+                if (lane == 0 && j0 + e < N) {
+                    float v = s + (op.p1 != nullptr ? __ldg(op.p1 + j0 + e) : 0.f);
+                    if (relu) v = fmaxf(v, 0.f);
+                    dst[j0 + e] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    ++consumed;
+    if (tid == 0) {
+        const float* g; uint32_t bytes;
+        if (next_tile(prog, cursor, g, bytes)) {
+            mbar_arrive_expect_tx(full_bar + 8u * stage, bytes);
+            tma_load_bulk(smem_u32(wtiles + (size_t)stage * kTileFloats), g, bytes, full_bar + 8u * stage);
+        }
+    }
+}
+
+// In-place LayerNorm over n columns (two-pass mean / variance, biased variance, rsqrtf as PyTorch), optional ReLU.
+// Vector path (n, dst_col multiples of 4, n <= 1024, 16-byte aligned gamma / beta): the row lives in registers and the
+// gamma / beta loads are issued before the reductions, so their latency is hidden.
+template <int kRows>
+__device__ __forceinline__ void op_layernorm(const racf_row_op_t& op, float* bufs, int width, int warp, int lane) {
+    const int n = op.n;
+    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
+    const bool vec = ((n | op.dst_col) & 3) == 0 && n <= 1024 &&
+                     ((reinterpret_cast<uintptr_t>(op.p0) | reinterpret_cast<uintptr_t>(op.p1)) & 15u) == 0;
+    for (int r = warp; r < kRows; r += kRowWarps) {
+        float* x = bufs + ((size_t)op.dst * kRows + r) * width + op.dst_col;
+        if (vec) {
+            constexpr int kV = 8;                 // float4 per lane: n <= 1024
+            const int n4 = n >> 2;
+            float4 v[kV], g[kV], b[kV];
+#pragma unroll
+            for (int i = 0; i < kV; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 < n4) {
+                    g[i] = op.p0 != nullptr ? __ldg(reinterpret_cast<const float4*>(op.p0) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    b[i] = op.p1 != nullptr ? __ldg(reinterpret_cast<const float4*>(op.p1) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = *reinterpret_cast<const float4*>(x + 4 * c4);
+                }
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < kV; ++i)
+                if (lane + 32 * i < n4) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            const float mean = warp_sum(s) / (float)n;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < kV; ++i)
+                if (lane + 32 * i < n4) {
+                    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+                    q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q);
+                    q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
+                }
+            const float rstd = rsqrtf(warp_sum(q) / (float)n + op.eps);
+#pragma unroll
+            for (int i = 0; i < kV; ++i) {
+                const int c4 = lane + 32 * i;
+                if (c4 < n4) {
+                    float4 o;
+                    o.x = v[i].x * rstd * g[i].x + b[i].x; o.y = v[i].y * rstd * g[i].y + b[i].y;
+                    o.z = v[i].z * rstd * g[i].z + b[i].z; o.w = v[i].w * rstd * g[i].w + b[i].w;
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(x + 4 * c4) = o;
+                }
+            }
+            continue;
+        }
+        float s = 0.f;
+        for (int c = lane; c < n; c += 32) s += x[c];
+        const float mean = warp_sum(s) / (float)n;
+        float q = 0.f;
+        for (int c = lane; c < n; c += 32) {
+            const float d = x[c] - mean;
+            q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)n + op.eps);
+        for (int c = lane; c < n; c += 32) {
+            float v = (x[c] - mean) * rstd;
+            if (op.p0 != nullptr) v = v * __ldg(op.p0 + c);
+            if (op.p1 != nullptr) v = v + __ldg(op.p1 + c);
+            if (relu) v = fmaxf(v, 0.f);
+            x[c] = v;
+        }
+    }
+}
+
+template <int kRows>
+__global__ void __launch_bounds__(kRowThreads, 1)
+row_program_kernel(const __grid_constant__ RowProgram prog) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ float queue_w[kRows][RACF_ROW_MAX_QUEUE];
+    __shared__ __align__(8) unsigned long long full_bars[kStages];
+    float* wtiles = smem;                                  // [kStages][32][256]
+    float* bufs = smem + (size_t)kStages * kTileFloats;    // [num_bufs][kRows][width]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int width = prog.width;
+    const long long row0 = (long long)blockIdx.x * kRows;
+    const int valid = (int)min((long long)kRows, (long long)prog.rows - row0);
+    const uint32_t full_bar = smem_u32(full_bars);
+
+    TileCursor cursor = {0, 0, 0};
+    unsigned consumed = 0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(full_bar + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < kStages; ++s) {
+            const float* g; uint32_t bytes;
+            if (!next_tile(prog, cursor, g, bytes)) break;
+            mbar_arrive_expect_tx(full_bar + 8u * s, bytes);
+            tma_load_bulk(smem_u32(wtiles + (size_t)s * kTileFloats), g, bytes, full_bar + 8u * s);
+        }
+    }
+    __syncthreads();
+
+    for (int i = 0; i < prog.num_ops; ++i) {
+        const racf_row_op_t& op = prog.ops[i];
+        switch (op.kind) {
+        case RACF_ROWOP_LOAD: {      // dst[r][c] = p0[row * ld + c]; rows past the end read as 0
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            if (((op.n | op.ld | op.dst_col) & 3) == 0 && (reinterpret_cast<uintptr_t>(op.p0) & 15u) == 0) {
+                const int n4 = op.n >> 2;
+                for (int e = tid; e < kRows * n4; e += kRowThreads) {
+                    const int r = e / n4, c = (e - r * n4) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < valid) v = __ldg(reinterpret_cast<const float4*>(op.p0 + (row0 + r) * op.ld + c));
+                    *reinterpret_cast<float4*>(dst + r * width + c) = v;
+                }
+            } else {
+                for (int e = tid; e < kRows * op.n; e += kRowThreads) {
+                    const int r = e / op.n, c = e - r * op.n;
+                    dst[r * width + c] = r < valid ? __ldg(op.p0 + (row0 + r) * op.ld + c) : 0.f;
+                }
+            }
+            break;
+        }
+        case RACF_ROWOP_LOAD_QUEUE: {   // w = softmax over the T queue logits p1[row][T] (NULL: 1/T); dst = sum_t w_t * p0[b*T + t][q][c]
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            const int T = op.aux, Q = op.k;
+            if (tid < kRows) {
+                const long long row = row0 + tid;
+                if (tid < valid && op.p1 != nullptr) {
+                    const float* lg = op.p1 + row * T;
+                    float m = -INFINITY;
+                    for (int t = 0; t < T; ++t) m = fmaxf(m, __ldg(lg + t));
+                    float den = 0.f;
+                    for (int t = 0; t < T; ++t) den += expf(__ldg(lg + t) - m);
+                    for (int t = 0; t < T; ++t) queue_w[tid][t] = expf(__ldg(lg + t) - m) / den;
+                } else {
+                    for (int t = 0; t < T; ++t) queue_w[tid][t] = 1.f / (float)T;
+                }
+            }
+            __syncthreads();
+            const int n4 = op.n >> 2;      // validated: n, ld, dst_col multiples of 4, p0 16-byte aligned
+            for (int e = tid; e < kRows * n4; e += kRowThreads) {
+                const int r = e / n4, c = (e - r * n4) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < valid) {
+                    const long long row = row0 + r;
+                    const long long b = row / Q, q = row - b * Q;
+                    const float* base = op.p0 + ((b * T) * Q + q) * op.ld + c;
+                    const long long tstride = (long long)Q * op.ld;
+                    for (int t0 = 0; t0 < T; t0 += 8) {
+                        float4 x[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (t0 + t < T) x[t] = __ldg(reinterpret_cast<const float4*>(base + (t0 + t) * tstride));
+#pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (t0 + t < T) {
+                                const float wq = queue_w[r][t0 + t];
+                                v.x = fmaf(x[t].x, wq, v.x); v.y = fmaf(x[t].y, wq, v.y);
+                                v.z = fmaf(x[t].z, wq, v.z); v.w = fmaf(x[t].w, wq, v.w);
+                            }
+                    }
+                }
+                *reinterpret_cast<float4*>(dst + r * width + c) = v;
+            }
+            break;
+        }
+        case RACF_ROWOP_STORE: {
+            const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
+            for (int e = tid; e < valid * op.n; e += kRowThreads) {
+                const int r = e / op.n, c = e - r * op.n;
+                op.out[(row0 + r) * op.ld + c] = src[r * width + c];
+            }
+            break;
+        }
+        case RACF_ROWOP_ADD: {
+            const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            for (int e = tid; e < kRows * op.n; e += kRowThreads) {
+                const int r = e / op.n, c = e - r * op.n;
+                dst[r * width + c] += src[r * width + c];
+            }
+            break;
+        }
+        case RACF_ROWOP_LINEAR: op_linear<kRows>(prog, op, bufs, wtiles, full_bar, width, tid, consumed, cursor); break;
+        case RACF_ROWOP_LINEAR_NARROW:
+            op_linear_narrow<kRows>(prog, op, bufs, wtiles, full_bar, width, tid, consumed, cursor);
+            break;
+        case RACF_ROWOP_LAYERNORM: op_layernorm<kRows>(op, bufs, width, warp, lane); break;
+        default: break;
+        }
+        __syncthreads();
+    }
+}
+
+static int validate(const racf_row_op_t& op, int width, int num_bufs) {
+    const bool reads_buf = op.kind == RACF_ROWOP_STORE || op.kind == RACF_ROWOP_ADD || op.kind == RACF_ROWOP_LINEAR ||
+                           op.kind == RACF_ROWOP_LINEAR_NARROW;
+    const bool writes_buf = op.kind != RACF_ROWOP_STORE;
+    if (op.kind < RACF_ROWOP_LOAD || op.kind > RACF_ROWOP_LAYERNORM) return RACF_ERR_UNSUPPORTED;
+    if (op.n <= 0) return RACF_ERR_BAD_SHAPE;
+    const bool is_linear = op.kind == RACF_ROWOP_LINEAR || op.kind == RACF_ROWOP_LINEAR_NARROW;
+    const int in_w = is_linear ? op.k : op.n;
+    if (is_linear && op.k <= 0) return RACF_ERR_BAD_SHAPE;
+    if (reads_buf && (op.src < 0 || op.src >= num_bufs || op.src_col < 0 || op.src_col + in_w > width)) return RACF_ERR_BAD_SHAPE;
+    if (writes_buf && (op.dst < 0 || op.dst >= num_bufs || op.dst_col < 0 || op.dst_col + op.n > width)) return RACF_ERR_BAD_SHAPE;
+    switch (op.kind) {
+    case RACF_ROWOP_LOAD:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_LOAD_QUEUE:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n || op.aux <= 0 || op.aux > RACF_ROW_MAX_QUEUE || op.k <= 0) return RACF_ERR_BAD_SHAPE;
+        if (((op.n | op.ld | op.dst_col) & 3) != 0 || (reinterpret_cast<uintptr_t>(op.p0) & 15u)) return RACF_ERR_UNSUPPORTED;
+        break;
+    case RACF_ROWOP_STORE:
+        if (!op.out) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_LINEAR:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.src == op.dst) return RACF_ERR_UNSUPPORTED;          // not in place
+        if ((op.src_col & 3) != 0) return RACF_ERR_UNSUPPORTED;     // 128-bit shared-memory reads
+        if (reinterpret_cast<uintptr_t>(op.p0) & 15u) return RACF_ERR_UNSUPPORTED;   // bulk copies of the weight tiles
+        break;
+    case RACF_ROWOP_LINEAR_NARROW:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.src == op.dst) return RACF_ERR_UNSUPPORTED;
+        if ((long long)op.n * op.k > 8192 || ((op.n * op.k) & 3) != 0 || (reinterpret_cast<uintptr_t>(op.p0) & 15u))
+            return RACF_ERR_UNSUPPORTED;                                // one weight tile, moved by one bulk copy
+        break;
+    default: break;
+    }
+    return RACF_OK;
+}
+
+template <int kRows>
+static int launch(const RowProgram& prog, cudaStream_t st) {
+    const size_t smem = ((size_t)kStages * kTileFloats + (size_t)prog.num_bufs * kRows * prog.width) * sizeof(float);
+    if (smem > 227u * 1024u - 1024u) return RACF_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(row_program_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long grid = ((long long)prog.rows + kRows - 1) / kRows;
+    if (grid > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
+    row_program_kernel<kRows><<<(unsigned)grid, kRowThreads, smem, st>>>(prog);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace racf
+
+extern "C" int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, int rows, int rows_per_cta, int num_bufs,
+                                        int width, racf_stream_t stream) {
+    using namespace racf;
+    if (!ops) return RACF_ERR_NULL_POINTER;
+    if (num_ops <= 0 || num_ops > RACF_ROW_MAX_OPS || rows <= 0 || num_bufs <= 0 || width <= 0) return RACF_ERR_BAD_SHAPE;
+    if ((width & 3) != 0 || (rows_per_cta != 4 && rows_per_cta != 8)) return RACF_ERR_UNSUPPORTED;
+    RowProgram prog;
+    for (int i = 0; i < num_ops; ++i) {
+        const int rc = validate(ops[i], width, num_bufs);
+        if (rc != RACF_OK) return rc;
+        prog.ops[i] = ops[i];
+    }
+    prog.num_ops = num_ops;
+    prog.rows = rows;
+    prog.width = width;
+    prog.num_bufs = num_bufs;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return rows_per_cta == 4 ? launch<4>(prog, st) : launch<8>(prog, st);
+}

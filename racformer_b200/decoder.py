@@ -375,21 +375,27 @@ class BEVSelfAttention(nn.Module):
         v = self.value_proj(bev.reshape(B * T, C, -1).permute(0, 2, 1))
         return v.reshape(B * T, v.shape[1], self.num_heads, -1)
 
-    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes):
+    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False):
         B, Q, C = query.shape
         T, M, L, P = self.num_bev_queue, self.num_heads, self.num_levels, self.num_points
         loc = sampling_locations.view(B, Q, M, T, L, P, 2).permute(3, 0, 1, 2, 4, 5, 6).reshape(B * T, Q, M, L, P, 2)
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
-        return self.attend(ops, query, value, loc, aw, spatial_shapes)
+        return self.attend(ops, query, value, loc, aw, spatial_shapes, raw=raw)
 
-    def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None):
+    def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None, raw=False):
         """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing; queue_logits: bev_queue_weight(query)
-        when the caller has already computed it (the decoder layer's stacked head launch)."""
+        when the caller has already computed it (the decoder layer's stacked head launch). raw: return the MSDA output
+        [B*T,Q,C] and the queue logits (None: plain mean) -- the caller's row program (csrc/rowops.cu) does the queue
+        fusion, output_proj and residual."""
         B, Q, C = query.shape
         T = self.num_bev_queue
         shapes = _const_long((tuple(int(v) for v in spatial_shapes),), value.device)
         lsi = _const_long((0,), value.device)
         out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
+        if raw:
+            if not self.queue_weight:
+                return out, None
+            return out, (queue_logits if queue_logits is not None else self.bev_queue_weight(query))
         out = out.permute(1, 2, 0).reshape(Q, C, B, T)
         if self.queue_weight:
             logits = queue_logits if queue_logits is not None else self.bev_queue_weight(query)
@@ -502,7 +508,7 @@ class BEVSampling(nn.Module):
             return self.attention.project_value(bev_feats, pos.reshape(C, H, W)), (H, W)
         return self.attention.project_value(bev_feats + pos.view(B, 1, C, H, W)), (H, W)
 
-    def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region, heads=None):
+    def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region, heads=None, raw=False):
         B, Q, _ = query_ray.shape
         T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
         if self.num_levels == 1 and _use_fused_points(self, query_ray, query_feat, value):
@@ -512,7 +518,7 @@ class BEVSampling(nn.Module):
                                                                 self.scale_weights(query_feat), None)
             loc, aw = points.bev_points(query_ray.contiguous(), off, ray, sw, meta["time_diff"],
                                         _depth_base(d_region, D, query_feat.device), pr, d_region, T, M, Pn, D)
-            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw)
+            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw)
         query_bbox = theta_d2xy_coods(query_ray)
         offset = self.sampling_offset(query_feat).view(B, Q, M * Pn * D, 2)
         offset = torch.cat([offset, torch.zeros_like(offset[..., 0:1])], dim=-1)
@@ -526,12 +532,12 @@ class BEVSampling(nn.Module):
         loc = theta_d2xy_coods(polar).permute(0, 1, 3, 2, 4, 5).contiguous()               # [B,Q,M,T,P,2]
         w = self.scale_weights(query_feat).view(B, Q, M, 1, self.num_levels, D * Pn)
         w = torch.softmax(w, dim=-1).expand(B, Q, M, T, self.num_levels, D * Pn).contiguous()
-        return self.attention(ops, query_feat, value, loc, w, hw)
+        return self.attention(ops, query_feat, value, loc, w, hw, raw=raw)
 
-    def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None, heads=None):
+    def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None, heads=None, raw=False):
         def fn(qr, qf, bev):
             value, hw = prepared if prepared is not None else self.prepare_value(bev)
-            return self.sample(ops, qr, qf, value, hw, meta, d_region, heads)
+            return self.sample(ops, qr, qf, value, hw, meta, d_region, heads, raw=raw)
         return _maybe_checkpoint(self, fn, query_ray, query_feat, bev_feats)
 
 
@@ -762,28 +768,113 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         theta = proposal[..., 0:1] + (torch.sigmoid(delta[..., 0:1]) * 2 - 1) / self.num_ray
         return torch.cat([theta, dz, delta[..., 3:]], dim=-1)
 
+    row_programs = True     # inference on CUDA: the row-wise operator chains run as row programs (csrc/rowops.cu)
+
+    def _rows_ok(self, query_feat):
+        """The row programs are forward-only fp32 CUDA kernels (dropout must be the identity)."""
+        return (self.row_programs and not torch.is_grad_enabled() and not self.training and query_feat.is_cuda
+                and query_feat.dtype == torch.float32 and self.embed_dims % 4 == 0)
+
+    def _pos_encode_rows(self, query_bbox, query_feat):
+        """query_feat + position_encoder(query_bbox[..., :3]) as one launch (Linear-LN-ReLU-Linear-LN-ReLU + add)."""
+        from . import rowops
+        B, Q, E = query_feat.shape
+        pe = self.position_encoder
+        p = rowops.RowProgram(B * Q, width=E, num_bufs=3)
+        p.load(0, query_bbox.contiguous(), n=3)
+        p.linear(1, 0, pe[0])
+        p.layernorm(1, pe[1], relu=True)
+        p.linear(2, 1, pe[3])
+        p.layernorm(2, pe[4], relu=True)
+        p.load(0, query_feat.contiguous())
+        p.add(0, 2, E)
+        out = p.store(0, E)
+        p.run()
+        return out.view(B, Q, E)
+
+    def _tail_rows(self, mixed, query_feat, radar, lss):
+        """Everything after the sampling ops of an iteration as ONE launch: norm2(mixed); per BEV branch the softmax queue
+        fusion, output_proj, residual and norm; cat + fusion + norm_fusion; FFN + norm3; cls and reg branches.
+        radar / lss = (MSDA output [B*T,Q,C], queue logits [B,Q,T]). -> (query_feat, cls_score, reg delta)."""
+        from . import rowops
+        B, Q, E = query_feat.shape
+        p = rowops.RowProgram(B * Q, width=3 * E, num_bufs=3)
+        p.load(0, mixed.contiguous())
+        p.layernorm(0, self.norm2)
+        p.load(1, query_feat.contiguous())
+        for i, (branch, norm, (values, logits)) in enumerate(((self.sampling_radar_bev, self.norm_radar_bev, radar),
+                                                               (self.sampling_lss_bev, self.norm_lss_bev, lss))):
+            col = (i + 1) * E
+            p.load_queue(2, values, logits, Q, branch.attention.num_bev_queue)
+            p.linear(0, 2, branch.attention.output_proj, dst_col=col)
+            p.add(0, 1, E, dst_col=col)
+            p.layernorm(0, norm, col=col)
+        p.linear(1, 0, self.fusion)
+        p.layernorm(1, self.norm_fusion)
+        p.linear(2, 1, self.ffn.layers[0][0], relu=True)
+        p.linear(0, 2, self.ffn.layers[1])
+        p.add(0, 1, E)
+        p.layernorm(0, self.norm3)
+        out_feat = p.store(0, E)
+        outs = []
+        for branch in (self.cls_branch, self.reg_branch):
+            mods = list(branch)
+            src, i = 0, 0
+            free = [1, 2]
+            while i < len(mods):
+                lin = mods[i]
+                i += 1
+                dst = free[0] if src != free[0] else free[1]
+                relu_now = i < len(mods) and isinstance(mods[i], nn.ReLU)
+                p.linear(dst, src, lin, relu=relu_now)
+                if relu_now:
+                    i += 1
+                elif i < len(mods) and isinstance(mods[i], nn.LayerNorm):
+                    relu_after = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                    p.layernorm(dst, mods[i], relu=relu_after)
+                    i += 2 if relu_after else 1
+                src = dst
+            outs.append(p.store(src, mods[-1].out_features))
+        p.run()
+        return out_feat.view(B, Q, E), outs[0].view(B, Q, -1), outs[1].view(B, Q, -1)
+
     def forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer=0,
                 prepared=None):
         d_region = self.d_region_list[layer]
-        query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
+        rows = self._rows_ok(query_feat)
+        if rows:
+            query_feat = self._pos_encode_rows(query_bbox, query_feat)
+        else:
+            query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
         query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
         heads = self._sampling_heads(query_feat) or (None, None, None)
-        radar = self.norm_radar_bev(self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta,
-                                                            d_region=d_region, prepared=prep_radar, heads=heads[0]))
-        lss = self.norm_lss_bev(self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta,
-                                                      d_region=d_region, prepared=prep_lss, heads=heads[1]))
+        radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,
+                                        prepared=prep_radar, heads=heads[0], raw=rows)
+        lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,
+                                    prepared=prep_lss, heads=heads[1], raw=rows)
         sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region, heads=heads[2])
-        query_feat = self.norm2(self.mixing(sampled, query_feat))
-        query_feat = self.norm_fusion(self.fusion(torch.cat((query_feat, radar, lss), dim=-1)))
-        query_feat = self.norm3(self.ffn(query_feat))
-        cls_score = self.cls_branch(query_feat)
-        bbox_pred = self.refine_bbox(query_bbox, self.reg_branch(query_feat))
+        mixed = self.mixing(sampled, query_feat)
+        if rows:
+            query_feat, cls_score, delta = self._tail_rows(mixed, query_feat, radar, lss)
+        else:
+            radar, lss = self.norm_radar_bev(radar), self.norm_lss_bev(lss)
+            query_feat = self.norm2(mixed)
+            query_feat = self.norm_fusion(self.fusion(torch.cat((query_feat, radar, lss), dim=-1)))
+            query_feat = self.norm3(self.ffn(query_feat))
+            cls_score = self.cls_branch(query_feat)
+            delta = self.reg_branch(query_feat)
         time_diff = meta["time_diff"]
+        if rows and self.code_size >= 8:
+            from . import points   # refine + velocity scaling + output transform: one launch
+            bbox_pred, bbox_xy = points.refine_bbox(query_bbox.contiguous(), delta.contiguous(), time_diff.contiguous(),
+                                                    self.num_ray)
+            return query_feat, cls_score, bbox_pred, bbox_xy
+        bbox_pred = self.refine_bbox(query_bbox, delta)
         if time_diff.shape[1] > 1:   # relative -> absolute velocity
             td = torch.where(time_diff < 1e-5, torch.ones_like(time_diff), time_diff)
             bbox_pred = torch.cat([bbox_pred[..., :8], bbox_pred[..., 8:] / td[:, 1:2, None]], dim=-1)
-        return query_feat, cls_score, bbox_pred
+        return query_feat, cls_score, bbox_pred, None
 
 
 def to_sampling_layout(feat, num_cams, num_groups=4):
@@ -832,11 +923,11 @@ class RaCFormerTransformerDecoder(nn.Module):
                         layer.sampling_lss_bev.prepare_value(lss_bev_feats))
         cls_scores, bbox_preds = [], []
         for i in range(self.num_layers):
-            query_feat, cls_score, bbox_pred = layer(ops, query_bbox, query_feat, feats, lss_bev_feats, radar_bev_feats,
-                                                     attn_mask, meta, layer=i, prepared=prepared)
-            query_bbox = bbox_pred.clone().detach()
+            query_feat, cls_score, bbox_pred, bbox_xy = layer(ops, query_bbox, query_feat, feats, lss_bev_feats,
+                                                              radar_bev_feats, attn_mask, meta, layer=i, prepared=prepared)
+            query_bbox = bbox_pred.clone().detach() if bbox_xy is None else bbox_pred   # fused: a fresh no-grad tensor
             cls_scores.append(cls_score)
-            bbox_preds.append(theta_d2xy_coods(bbox_pred))
+            bbox_preds.append(bbox_xy if bbox_xy is not None else theta_d2xy_coods(bbox_pred))
         return torch.stack(cls_scores), torch.stack(bbox_preds)
 
 

@@ -121,3 +121,26 @@ def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_gro
         return None
     _lib.check(rc, "racf_adaptive_mixing_forward")
     return out
+
+
+def refine_bbox(proposal, delta, time_diff, num_ray):
+    """(query rays [B,Q,code], reg branch output [B,Q,code], time_diff [B,T] or None) -> (bbox_pred, theta_d2xy(bbox_pred)):
+    refine_bbox, the velocity scaling and the polar -> cartesian output transform of a decoder iteration
+    (models/racformer_transformer.py:255-279) in one launch."""
+    _check(proposal, delta)
+    if proposal.shape != delta.shape or proposal.dim() != 3:
+        raise RuntimeError("refine_bbox: proposal and delta must both be [B, Q, code]")
+    B, Q, code = proposal.shape
+    T = 1
+    if time_diff is not None:
+        _check(proposal, time_diff)
+        if time_diff.dim() != 2 or time_diff.shape[0] != B:
+            raise RuntimeError("refine_bbox: time_diff must be [B, T]")
+        T = time_diff.shape[1]
+    pred, pred_xy = torch.empty_like(proposal), torch.empty_like(proposal)
+    with torch.cuda.device(proposal.device):
+        rc = _lib.load().racf_refine_bbox_forward(proposal.data_ptr(), delta.data_ptr(),
+                                                  time_diff.data_ptr() if time_diff is not None else None, B, Q, T, code,
+                                                  float(num_ray), pred.data_ptr(), pred_xy.data_ptr(), _stream(proposal.device))
+    _lib.check(rc, "racf_refine_bbox_forward")
+    return pred, pred_xy
