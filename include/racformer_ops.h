@@ -273,6 +273,21 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
                                      int max_order, int tiled, racf_stream_t stream);
 
 /*
+ * Call-site row: the attention core of ScaleAdaptiveSelfAttention
+ * (models/racformer_transformer.py:283-336: pairwise centre distances, dist * tau as the additive mask of mmcv's
+ * MultiheadAttention, softmax, weighted sum) as one launch, without materialising the [B, H, Q, Q] mask.
+ *   qkv       : [batch * num_query, 3 * H * head_dim]  in_proj output (q | k | v), head h at columns h * head_dim
+ *   tau       : [batch * num_query, H]                  gen_tau output
+ *   query_ray : [batch * num_query, code_size]          (theta, d, ...): centre = decode_bbox(theta_d2xy_coods(.))[:2]
+ *   pc_range  : 6 host doubles
+ *   out       : [batch * num_query, H * head_dim]       heads merged, ready for out_proj
+ * score = q.k / sqrt(head_dim) - tau[i, h] * |centre_i - centre_j|. head_dim must be 32. Inference only (no extra mask).
+ */
+int racf_sasa_attention_forward(const float* qkv, const float* tau, const float* query_ray, const double* pc_range,
+                                int batch, int num_query, int num_heads, int head_dim, int code_size,
+                                float* out, racf_stream_t stream);
+
+/*
  * Call-site row: box refinement at the end of a decoder iteration
  * (models/racformer_transformer.py:255-259,264-279 and theta_d2xy_coods, models/bbox/utils.py:82-90) as one launch.
  *   proposal, delta : [batch * num_query, code_size]  the iteration's input rays and the reg branch output

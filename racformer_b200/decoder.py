@@ -792,6 +792,46 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         p.run()
         return out.view(B, Q, E)
 
+    fused_self_attention = True     # with row_programs: csrc/sasa.cu instead of the [B,8,Q,Q] mask + generic attention
+
+    def _self_attn_rows(self, query_bbox, query_feat):
+        """norm1(self_attn(query_bbox, query_feat + position_encoder(query_bbox[..., :3]))) in three launches: a row
+        program (position encoder, add, in_proj, gen_tau), the scale-adaptive attention core, a row program (out_proj,
+        residual, norm1). None when the attention module is not the plain 32-wide-head configuration."""
+        mha = self.self_attn.attention.attn
+        E, H = self.embed_dims, mha.num_heads
+        if (not self.fused_self_attention or not mha._qkv_same_embed_dim or mha.in_proj_bias is None or E != H * 32
+                or mha.bias_k is not None or mha.add_zero_attn or query_bbox.shape[-1] < 2):
+            return None
+        from . import points, rowops
+        B, Q, _ = query_feat.shape
+        pe = self.position_encoder
+        query_bbox = query_bbox.contiguous()
+        p = rowops.RowProgram(B * Q, width=3 * E, num_bufs=3)
+        p.load(0, query_bbox, n=3)
+        p.linear(1, 0, pe[0])
+        p.layernorm(1, pe[1], relu=True)
+        p.linear(2, 1, pe[3])
+        p.layernorm(2, pe[4], relu=True)
+        p.load(0, query_feat.contiguous())
+        p.add(0, 2, E)
+        qpos = p.store(0, E)
+        p.linear(1, 0, mha, weight=mha.in_proj_weight, bias=mha.in_proj_bias)
+        qkv = p.store(1, 3 * E)
+        p.linear(2, 0, self.self_attn.gen_tau)
+        tau = p.store(2, H)
+        p.run()
+        att = points.sasa_attention(qkv.view(B, Q, 3 * E), tau.view(B, Q, H), query_bbox, self.pc_range, H)
+        p = rowops.RowProgram(B * Q, width=E, num_bufs=2)
+        p.load(0, att)
+        p.linear(1, 0, mha.out_proj)
+        p.load(0, qpos)
+        p.add(1, 0, E)
+        p.layernorm(1, self.norm1)
+        out = p.store(1, E)
+        p.run()
+        return out.view(B, Q, E)
+
     def _tail_rows(self, mixed, query_feat, radar, lss):
         """Everything after the sampling ops of an iteration as ONE launch: norm2(mixed); per BEV branch the softmax queue
         fusion, output_proj, residual and norm; cat + fusion + norm_fusion; FFN + norm3; cls and reg branches.
@@ -842,11 +882,15 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
                 prepared=None):
         d_region = self.d_region_list[layer]
         rows = self._rows_ok(query_feat)
-        if rows:
-            query_feat = self._pos_encode_rows(query_bbox, query_feat)
+        attended = self._self_attn_rows(query_bbox, query_feat) if rows and attn_mask is None else None
+        if attended is not None:
+            query_feat = attended
         else:
-            query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
-        query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
+            if rows:
+                query_feat = self._pos_encode_rows(query_bbox, query_feat)
+            else:
+                query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
+            query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
         heads = self._sampling_heads(query_feat) or (None, None, None)
         radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,

@@ -144,3 +144,21 @@ def refine_bbox(proposal, delta, time_diff, num_ray):
                                                   float(num_ray), pred.data_ptr(), pred_xy.data_ptr(), _stream(proposal.device))
     _lib.check(rc, "racf_refine_bbox_forward")
     return pred, pred_xy
+
+
+def sasa_attention(qkv, tau, query_ray, pc_range, num_heads):
+    """Attention core of ScaleAdaptiveSelfAttention (models/racformer_transformer.py:283-336) in one launch:
+    qkv [B,Q,3E] (in_proj output), tau [B,Q,H] (gen_tau output), query_ray [B,Q,code] -> [B,Q,E] (heads merged, before
+    out_proj). The [B,H,Q,Q] distance mask is never materialised."""
+    _check(qkv, tau, query_ray)
+    B, Q, E3 = qkv.shape
+    E = E3 // 3
+    if E3 != 3 * E or E % num_heads != 0 or tau.shape != (B, Q, num_heads) or query_ray.shape[:2] != (B, Q):
+        raise RuntimeError("sasa_attention: inconsistent input shapes")
+    out = torch.empty((B, Q, E), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        rc = _lib.load().racf_sasa_attention_forward(qkv.data_ptr(), tau.data_ptr(), query_ray.data_ptr(), _pc(pc_range),
+                                                     B, Q, num_heads, E // num_heads, query_ray.shape[2], out.data_ptr(),
+                                                     _stream(qkv.device))
+    _lib.check(rc, "racf_sasa_attention_forward")
+    return out

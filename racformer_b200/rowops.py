@@ -44,13 +44,14 @@ def chunked_transpose(w):
     return out.view(chunks, CHUNK_COLS, K).transpose(1, 2).contiguous()
 
 
-def weight_t(linear):
-    """nn.Linear weight [N, K] -> its cached chunked transpose (rebuilt when the parameter changes)."""
-    w = linear.weight
+def weight_t(owner, w=None):
+    """Weight [N, K] of `owner` (an nn.Linear, or any module holding the parameter `w`) -> its cached chunked transpose
+    (rebuilt when the parameter changes)."""
+    w = owner.weight if w is None else w
     key = (w.data_ptr(), w._version, w.device)
-    hit = _transposed.get(linear)
+    hit = _transposed.get(owner)
     if hit is None or hit[0] != key:
-        hit = _transposed[linear] = (key, chunked_transpose(w.detach()))
+        hit = _transposed[owner] = (key, chunked_transpose(w.detach()))
     return hit[1]
 
 
@@ -133,13 +134,17 @@ class RowProgram:
     def add(self, dst, src, n, dst_col=0, src_col=0):
         self._push(kind=ADD, dst=dst, dst_col=dst_col, src=src, src_col=src_col, n=n)
 
-    def linear(self, dst, src, lin, relu=False, dst_col=0, src_col=0):
-        """buf[dst] = act(lin(buf[src])); wide outputs read the cached transposed weight, narrow ones (< 32) the weight."""
-        N, K = lin.weight.shape
-        narrow = N < 32
-        w = self._param(lin.weight if narrow else weight_t(lin))
+    def linear(self, dst, src, lin, relu=False, dst_col=0, src_col=0, weight=None, bias=None):
+        """buf[dst] = act(lin(buf[src])); wide outputs read the cached chunked transpose of the weight, narrow ones (< 32
+        columns) the weight itself. `weight` / `bias`: parameters held by `lin` under other names (e.g. the in_proj of an
+        nn.MultiheadAttention); `lin` is then only the cache key."""
+        weight = lin.weight if weight is None else weight
+        bias = (lin.bias if hasattr(lin, "bias") else None) if bias is None else bias
+        N, K = weight.shape
+        narrow = N < 32 and N * K <= 8192 and (N * K) % 4 == 0
+        w = self._param(weight if narrow else weight_t(lin, weight))
         self._push(kind=LINEAR_NARROW if narrow else LINEAR, dst=dst, dst_col=dst_col, src=src, src_col=src_col, n=N, k=K,
-                   flags=RELU if relu else 0, p0=w, p1=self._param(lin.bias))
+                   flags=RELU if relu else 0, p0=w, p1=self._param(bias))
 
     def layernorm(self, buf, ln, col=0, relu=False):
         n = ln.normalized_shape[-1]

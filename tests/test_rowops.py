@@ -170,3 +170,56 @@ def test_refine_bbox_matches_the_pytorch_chain(batch, frames):
     torch.cuda.synchronize()
     assert torch.allclose(pred, ref, rtol=1e-6, atol=1e-6), float((pred - ref).abs().max())
     assert torch.allclose(pred_xy, ref_xy, rtol=1e-6, atol=1e-6), float((pred_xy - ref_xy).abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,num_query", [(1, 900), (2, 77), (1, 5)])
+def test_sasa_attention_core_matches_the_masked_attention(batch, num_query):
+    """racf_sasa_attention_forward vs the reference construction: dist * tau as additive mask of scaled dot-product
+    attention (models/racformer_transformer.py:308-336)."""
+    from racformer_b200 import points
+    from racformer_b200.decoder import decode_bbox, theta_d2xy_coods
+    from racformer_b200.synthetic import PC_RANGE
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(num_query)
+    H, D = 8, 32
+    E = H * D
+    qkv = torch.randn(batch, num_query, 3 * E, device=dev, generator=g)
+    tau = torch.rand(batch, num_query, H, device=dev, generator=g) * 2
+    ray = torch.rand(batch, num_query, 10, device=dev, generator=g)
+    centres = decode_bbox(theta_d2xy_coods(ray), PC_RANGE)[..., :2]
+    dist = -torch.norm(centres[:, :, None, :] - centres[:, None, :, :], dim=-1)
+    mask = dist[:, None] * tau.permute(0, 2, 1)[..., None]                                   # [B,H,Q,Q]
+    q, k, v = (t.view(batch, num_query, H, D).transpose(1, 2) for t in qkv.split(E, dim=-1))
+    ref = F.scaled_dot_product_attention(q.double(), k.double(), v.double(), attn_mask=mask.double())
+    ref = ref.transpose(1, 2).reshape(batch, num_query, E)
+    ref32 = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(batch, num_query, E)
+    got = points.sasa_attention(qkv, tau, ray, PC_RANGE, H)
+    torch.cuda.synchronize()
+    err, err32 = float((got.double() - ref).abs().max()), float((ref32.double() - ref).abs().max())
+    # the kernel recomputes the bias (up to ~200 in magnitude here, ulp 1.5e-5) instead of reading the fp32 mask the fp64
+    # evaluation was given: a last-ulp difference in a distance moves a softmax weight by ~1e-5
+    print("sasa err vs fp64", err, "torch fp32 SDPA err", err32)
+    assert err <= max(2 * err32, 3e-5), (err, err32)
+    assert torch.allclose(got, ref32, rtol=1e-4, atol=5e-5), float((got - ref32).abs().max())
+
+
+@pytest.mark.gpu
+def test_decoder_layer_fused_self_attention_matches_the_pytorch_chain():
+    from racformer_b200.decoder import RaCFormerTransformer
+    from racformer_b200.synthetic import fill_parameters_by_name
+    from tests.decoder_cases import SMALL, small_inputs
+    dev = torch.device("cuda", 0)
+    model = RaCFormerTransformer(**SMALL).to(dev).eval()
+    fill_parameters_by_name(model)
+    inp = small_inputs(batch=2)
+    args = [inp["query_bbox"].to(dev), inp["query_feat"].to(dev), [f.to(dev) for f in inp["mlvl_feats"]],
+            inp["lss_bev"].to(dev), inp["radar_bev"].to(dev), None, inp["img_metas"]]
+    layer = model.decoder.decoder_layer
+    with torch.no_grad():
+        layer.fused_self_attention = True
+        cls_a, box_a = model(*args)
+        layer.fused_self_attention = False
+        cls_b, box_b = model(*args)
+    assert torch.allclose(cls_a, cls_b, rtol=1e-4, atol=2e-4), float((cls_a - cls_b).abs().max())
+    assert torch.allclose(box_a, box_b, rtol=1e-4, atol=2e-4), float((box_a - box_b).abs().max())

@@ -85,6 +85,25 @@ def main():
             with torch.cuda.graph(g, stream=s):
                 out = layer._tail_rows(mixed, qf, radar, lss)
         res["tail_rows_graph_us"] = timed(g.replay)
+        # scale-adaptive self-attention: fused path (2 row programs + csrc/sasa.cu) vs the PyTorch chain, both under a graph
+        from racformer_b200 import points
+
+        def graph_time(fn):
+            g2, s2 = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+            with torch.cuda.stream(s2):
+                fn()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g2, stream=s2):
+                    keep = fn()
+            return timed(g2.replay), keep
+
+        qkv = torch.randn(B, Q, 3 * E, device=dev)
+        tau = torch.rand(B, Q, 8, device=dev)
+        res["sasa_core_graph_us"], _ = graph_time(lambda: points.sasa_attention(qkv, tau, qb, PC_RANGE, 8))
+        res["self_attn_fused_graph_us"], _ = graph_time(lambda: layer._self_attn_rows(qb, qf))
+        res["self_attn_torch_graph_us"], _ = graph_time(
+            lambda: layer.norm1(layer.self_attn(qb, qf + layer.position_encoder(qb[..., :3]), None)))
+        res["tail_torch_graph_us"], _ = graph_time(torch_tail)
     print(json.dumps(res, indent=1))
 
 
