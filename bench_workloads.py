@@ -283,7 +283,8 @@ class DecoderWorkload:
         # with the tcgen05 Linear layers also, per iteration: 1 operand split + 1 GEMM (parameter_generator), 1 GEMM + 1
         # split-K reduce (out_proj), 1 operand split + 1 stacked-heads GEMM; per sample: 2 x (split + GEMM) for value_proj
         tc = mixing_precision.startswith("bf16")
-        self.launches_per_step = (13 if tc else 7) * num_layers + (8 if tc else 4)
+        # and, per iteration, 3 row programs (csrc/rowops.cu), the self-attention core (csrc/sasa.cu) and the box refinement
+        self.launches_per_step = (18 if tc else 12) * num_layers + (8 if tc else 4)
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
         self._captured = None

@@ -254,6 +254,11 @@ int racf_split_bf16x3_chw_to_hwc(const float* in, const float* pos, int batch, i
  */
 long long racf_linear_tiled_bytes(long long rows, int K);
 int racf_split_bf16x3_tiled(const float* x, long long rows, int K, void* out, racf_stream_t stream);
+/* The same with a row-periodic fp32 addend: splits x[row][k] + addend[row % addend_rows][k] (addend may be NULL). Used
+ * for value_proj when the BEV maps are channel-last: x = the [B*T*H*W, C] pixel matrix, addend = the [H*W, C] positional
+ * encoding (models/bev_self_attention.py:162-174 adds it with a separate pass). */
+int racf_split_bf16x3_tiled_add(const float* x, long long rows, int K, const float* addend, long long addend_rows,
+                                void* out, racf_stream_t stream);
 int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long long* workspace_bytes);
 int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
                                int max_order, int split_k, int variant, float* workspace, float* out,

@@ -372,8 +372,8 @@ split_bf16x3_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __r
 
 // x [rows][K] fp32 -> the pre-tiled pieces of linear_tiled.cuh; one thread per 16-byte chunk (8 k) of the padded domain
 __global__ void __launch_bounds__(256)
-split_bf16x3_tiled_kernel(const float* __restrict__ x, int rows, int K, int num_kblocks, long long num_chunks,
-                          __nv_bfloat16* __restrict__ out) {
+split_bf16x3_tiled_kernel(const float* __restrict__ x, const float* __restrict__ addend, int addend_rows, int rows, int K,
+                          int num_kblocks, long long num_chunks, __nv_bfloat16* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_chunks) return;
     const int chunks_per_row = num_kblocks * 4;
@@ -382,7 +382,8 @@ split_bf16x3_tiled_kernel(const float* __restrict__ x, int rows, int K, int num_
     __align__(16) __nv_bfloat16 p[3][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float v = (row < rows && k0 + j < K) ? x[row * K + k0 + j] : 0.f;
+        float v = (row < rows && k0 + j < K) ? x[row * K + k0 + j] : 0.f;
+        if (addend != nullptr && row < rows && k0 + j < K) v += __ldg(addend + (row % addend_rows) * K + k0 + j);
         split3(v, p[0][j], p[1][j], p[2][j]);
     }
 #pragma unroll
@@ -491,16 +492,21 @@ extern "C" long long racf_linear_tiled_bytes(long long rows, int K) {
 }
 
 extern "C" int racf_split_bf16x3_tiled(const float* x, long long rows, int K, void* out, racf_stream_t stream) {
+    return racf_split_bf16x3_tiled_add(x, rows, K, nullptr, 1, out, stream);
+}
+
+extern "C" int racf_split_bf16x3_tiled_add(const float* x, long long rows, int K, const float* addend, long long addend_rows,
+                                           void* out, racf_stream_t stream) {
     using namespace racf;
     if (!x || !out) return RACF_ERR_NULL_POINTER;
-    if (rows <= 0 || K <= 0) return RACF_ERR_BAD_SHAPE;
+    if (rows <= 0 || K <= 0 || addend_rows <= 0 || addend_rows > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
     if (reinterpret_cast<uintptr_t>(out) & 15u) return RACF_ERR_UNSUPPORTED;
     const int num_kblocks = (K + kTileK - 1) / kTileK;
     const long long rows_pad = (rows + kTileRows - 1) / kTileRows * kTileRows;
     const long long chunks = rows_pad * num_kblocks * 4;
     if ((chunks + 255) / 256 > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
     split_bf16x3_tiled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, (int)rows, K, num_kblocks, chunks, static_cast<__nv_bfloat16*>(out));
+        x, addend, (int)addend_rows, (int)rows, K, num_kblocks, chunks, static_cast<__nv_bfloat16*>(out));
     return (int)cudaGetLastError();
 }
 

@@ -182,41 +182,49 @@ struct BevPointArgs {
     int B, Q, T, M, Pn, D;
 };
 
+// One thread per (b, q, head, point): the box decode, the box-relative point and the attention softmax do not depend on
+// the frame, so they are done once and only the velocity warp / polar jitter runs per frame (the first version spent
+// 22 us per launch redoing them for each of the T frames; same arithmetic per output element).
 __global__ void __launch_bounds__(256) bev_points_kernel(const BevPointArgs a) {
     const int P = a.Pn * a.D;
-    const long long total = (long long)a.T * a.B * a.Q * a.M * P;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+    const long long per_frame = (long long)a.B * a.Q * a.M * P;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < per_frame;
          idx += (long long)gridDim.x * blockDim.x) {
-        // idx enumerates the OUTPUT order: (t*B + b, q, m, p)   (queue-major, bev_self_attention.py:185-188)
+        // idx enumerates (b, q, m, p); outputs are queue-major: (t*B + b, q, m, p)   (bev_self_attention.py:185-188)
         long long r = idx;
         const int p = (int)(r % P); r /= P;
         const int m = (int)(r % a.M); r /= a.M;
-        const int q = (int)(r % a.Q); r /= a.Q;
-        const int b = (int)(r % a.B);
-        const int t = (int)(r / a.B);
+        const int q = (int)(r % a.Q);
+        const int b = (int)(r / a.Q);
         const int d = p % a.D;
 
         const long long bq = (long long)b * a.Q + q;
         const BoxFrame f = decode_query(a.ray + bq * 10, a.pc, a.span);
         const float* off = a.offset + (bq * (a.M * P) + (long long)m * P + p) * 2;
-        float x, y, z;
-        box_point(f, off[0], off[1], 0.f, x, y, z);
-        const float td = a.time_diff[b * a.T + t];
-        x = fdiv(fsub(fsub(x, fmul(f.vx, td)), a.pc[0]), a.span[0]);
-        y = fdiv(fsub(fsub(y, fmul(f.vy, td)), a.pc[1]), a.span[1]);
-        float theta, dist;
-        xy_to_polar(x, y, theta, dist);
-        dist = fadd(dist, depth_offset(a.depth_base[d], a.ray_logit[bq * a.D + d], a.d_region, a.D));
-        polar_to_xy(theta, dist, x, y);
-        a.loc[idx * 2] = x;
-        a.loc[idx * 2 + 1] = y;
+        float px, py, pz;
+        box_point(f, off[0], off[1], 0.f, px, py, pz);
+        const float jitter = depth_offset(a.depth_base[d], a.ray_logit[bq * a.D + d], a.d_region, a.D);
 
         const float* ar = a.attn_raw + (bq * a.M + m) * P;
         float mx = ar[0];
         for (int k = 1; k < P; ++k) mx = fmaxf(mx, ar[k]);
         float sum = 0.f;
         for (int k = 0; k < P; ++k) sum = fadd(sum, expf(fsub(ar[k], mx)));
-        a.attn[idx] = fdiv(expf(fsub(ar[p], mx)), sum);
+        const float weight = fdiv(expf(fsub(ar[p], mx)), sum);
+
+        const long long within = ((long long)q * a.M + m) * P + p;
+        for (int t = 0; t < a.T; ++t) {
+            const float td = a.time_diff[b * a.T + t];
+            float x = fdiv(fsub(fsub(px, fmul(f.vx, td)), a.pc[0]), a.span[0]);
+            float y = fdiv(fsub(fsub(py, fmul(f.vy, td)), a.pc[1]), a.span[1]);
+            float theta, dist;
+            xy_to_polar(x, y, theta, dist);
+            dist = fadd(dist, jitter);
+            polar_to_xy(theta, dist, x, y);
+            const long long o = ((long long)t * a.B + b) * ((long long)a.Q * a.M * P) + within;
+            *reinterpret_cast<float2*>(a.loc + o * 2) = make_float2(x, y);
+            a.attn[o] = weight;
+        }
     }
 }
 
@@ -272,7 +280,7 @@ extern "C" int racf_bev_points_forward(const float* query_ray, const float* offs
     for (int i = 0; i < 3; ++i) a.span[i] = (float)(pc_range[3 + i] - pc_range[i]);
     a.d_region = d_region;
     a.B = batch; a.Q = num_query; a.T = num_frames; a.M = num_heads; a.Pn = num_points; a.D = depth_num;
-    const long long total = (long long)num_frames * batch * num_query * num_heads * num_points * depth_num;
+    const long long total = (long long)batch * num_query * num_heads * num_points * depth_num;   // one thread per (b,q,m,p)
     bev_points_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }

@@ -11,8 +11,8 @@
 // Arithmetic is fp32 FMA on the CUDA cores; a dot product is two ascending-k partial sums (the 16-wide k halves of
 // every 32-wide tile) added at the end, the bias last (the order of a GEMM epilogue). Weights are kept by the host as
 // chunked transposes W^T [N/256][K][256]; a [32 k][256 column] tile is one contiguous 32 KB block that ONE thread moves
-// into shared memory with cp.async.bulk (TMA engine) behind an mbarrier, four tiles deep and across operator
-// boundaries. Every CTA reads the same <= 0.8 MB per Linear from L2: L2 -> SM bandwidth and the FMA pipe bound the
+// into shared memory with cp.async.bulk (TMA engine) behind full / empty mbarriers -- a dedicated producer warp runs
+// the whole program's tile stream through a four-deep ring, across operator boundaries, while 16 consumer warps compute. Every CTA reads the same <= 0.8 MB per Linear from L2: L2 -> SM bandwidth and the FMA pipe bound the
 // kernel, not HBM (a first version with per-thread LDG weight loads was latency-bound at 40 us per 256x256 layer).
 #include <cuda_runtime.h>
 #include <math.h>
@@ -22,12 +22,14 @@
 
 namespace racf {
 
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 256;                          // consumer threads (8 warps); one more warp only moves weights
 constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kLaunchThreads = kRowThreads + 32;
 constexpr int kChunkCols = RACF_ROW_CHUNK_COLS;           // 256 output columns per weight chunk
 constexpr int kTileK = 32;                                // k rows per weight tile
 constexpr int kTileFloats = kTileK * kChunkCols;          // 32 KB
-constexpr int kStages = 4;                                // weight tiles in flight (3 ahead of the one being used)
+constexpr int kStages = 4;                                // weight tile ring
+constexpr int kSplitK = kRowThreads / 64;                 // a tile's 32 k are split over 4 thread groups of 64
 
 struct RowProgram {
     racf_row_op_t ops[RACF_ROW_MAX_OPS];
@@ -62,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 2000000000LL) __trap();
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// barrier of the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory"); }
 __device__ __forceinline__ void tma_load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -106,90 +113,109 @@ __device__ __forceinline__ bool next_tile(const RowProgram& prog, TileCursor& cu
 }
 
 // dst[r][j] = act(bias[j] + sum_k src[r][k] * W[j][k]); the weight arrives as tiles of W^T through shared memory.
-// Thread = (column pair, k half): it owns 2 columns x kRows rows and the upper or lower 16 k of every tile, so each
-// weight element is read from shared memory once (LDS.64) and each input once per warp (LDS.128 broadcast): 4 + kRows
-// shared-memory wavefronts per 8 * kRows FMAs -- the shared-memory pipe and the FMA pipe are equally loaded. The two k
-// halves are added at the end of a chunk through the destination buffer.
+// Thread = (column quad, k group): it owns 4 columns x kRows rows (4 * kRows independent accumulators) and 8 of the 32 k
+// of every tile, so each weight element is read from shared memory once (LDS.128) and each input once per warp
+// (LDS.128 broadcast): 4 + kRows shared-memory instructions per 16 * kRows FMAs. A warp releases a stage by arriving on
+// its "empty" barrier -- the consumer warps never wait for each other inside a Linear. The four k groups are added at
+// the end of a chunk through the destination buffer, in a fixed order.
 template <int kRows>
-__device__ __forceinline__ void op_linear(const RowProgram& prog, const racf_row_op_t& op, float* bufs, const float* wtiles,
-                                          uint32_t full_bar, int width, int tid, unsigned& consumed, TileCursor& cursor) {
-    constexpr int kHalf = kTileK / 2;
-    const int jp = tid & 127, h = tid >> 7;
+__device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, const float* wtiles, uint32_t full_bar,
+                                          uint32_t empty_bar, int width, int tid, unsigned& consumed) {
+    constexpr int kGroupK = kTileK / kSplitK;   // 8
+    const int jq = tid & 63, h = tid >> 6, lane = tid & 31;
     const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
     float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
     const int N = op.n, K = op.k;
     const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
     const int kblocks = (K + kTileK - 1) / kTileK, chunks = (N + kChunkCols - 1) / kChunkCols;
     for (int c = 0; c < chunks; ++c) {
-        float acc[kRows][2];
+        float acc[kRows][4];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r][0] = acc[r][1] = 0.f;
+        for (int r = 0; r < kRows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
         for (int kb = 0; kb < kblocks; ++kb) {
             const int stage = consumed % kStages;
             mbar_wait(full_bar + 8u * stage, (consumed / kStages) & 1u);
-            const float* ws = wtiles + (size_t)stage * kTileFloats + 2 * jp;
+            const float* ws = wtiles + (size_t)stage * kTileFloats + 4 * jq;
             const float* xs = src + kb * kTileK;
             const int kn = min(kTileK, K - kb * kTileK);
             if (kn == kTileK) {
-                const float* wh = ws + h * kHalf * kChunkCols;
-                const float* xh = xs + h * kHalf;
+                const float* wh = ws + h * kGroupK * kChunkCols;
+                const float* xh = xs + h * kGroupK;
 #pragma unroll
-                for (int kk = 0; kk < kHalf; kk += 4) {
-                    const float2 w0 = *reinterpret_cast<const float2*>(wh + (kk + 0) * kChunkCols);
-                    const float2 w1 = *reinterpret_cast<const float2*>(wh + (kk + 1) * kChunkCols);
-                    const float2 w2 = *reinterpret_cast<const float2*>(wh + (kk + 2) * kChunkCols);
-                    const float2 w3 = *reinterpret_cast<const float2*>(wh + (kk + 3) * kChunkCols);
+                for (int kk = 0; kk < kGroupK; kk += 4) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wh + (kk + 0) * kChunkCols);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wh + (kk + 1) * kChunkCols);
+                    const float4 w2 = *reinterpret_cast<const float4*>(wh + (kk + 2) * kChunkCols);
+                    const float4 w3 = *reinterpret_cast<const float4*>(wh + (kk + 3) * kChunkCols);
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
                         const float4 x = *reinterpret_cast<const float4*>(xh + r * width + kk);
                         acc[r][0] = fmaf(x.x, w0.x, acc[r][0]); acc[r][1] = fmaf(x.x, w0.y, acc[r][1]);
+                        acc[r][2] = fmaf(x.x, w0.z, acc[r][2]); acc[r][3] = fmaf(x.x, w0.w, acc[r][3]);
                         acc[r][0] = fmaf(x.y, w1.x, acc[r][0]); acc[r][1] = fmaf(x.y, w1.y, acc[r][1]);
+                        acc[r][2] = fmaf(x.y, w1.z, acc[r][2]); acc[r][3] = fmaf(x.y, w1.w, acc[r][3]);
                         acc[r][0] = fmaf(x.z, w2.x, acc[r][0]); acc[r][1] = fmaf(x.z, w2.y, acc[r][1]);
+                        acc[r][2] = fmaf(x.z, w2.z, acc[r][2]); acc[r][3] = fmaf(x.z, w2.w, acc[r][3]);
                         acc[r][0] = fmaf(x.w, w3.x, acc[r][0]); acc[r][1] = fmaf(x.w, w3.y, acc[r][1]);
+                        acc[r][2] = fmaf(x.w, w3.z, acc[r][2]); acc[r][3] = fmaf(x.w, w3.w, acc[r][3]);
                     }
                 }
-            } else {                               // K tail (or a tiny K): the halves take alternate k
-                for (int kk = h; kk < kn; kk += 2) {
-                    const float2 w = *reinterpret_cast<const float2*>(ws + kk * kChunkCols);
+            } else {                               // K tail (or a tiny K): the groups take every fourth k
+                for (int kk = h; kk < kn; kk += kSplitK) {
+                    const float4 w = *reinterpret_cast<const float4*>(ws + kk * kChunkCols);
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
                         const float x = xs[r * width + kk];
                         acc[r][0] = fmaf(x, w.x, acc[r][0]); acc[r][1] = fmaf(x, w.y, acc[r][1]);
+                        acc[r][2] = fmaf(x, w.z, acc[r][2]); acc[r][3] = fmaf(x, w.w, acc[r][3]);
                     }
                 }
             }
-            __syncthreads();                       // every thread is done with this stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + 8u * stage);   // this warp is done with the stage
             ++consumed;
-            if (tid == 0) {                        // refill it with the tile kStages ahead
-                const float* g; uint32_t bytes;
-                if (next_tile(prog, cursor, g, bytes)) {
-                    mbar_arrive_expect_tx(full_bar + 8u * stage, bytes);
-                    tma_load_bulk(smem_u32(wtiles + (size_t)stage * kTileFloats), g, bytes, full_bar + 8u * stage);
-                }
-            }
         }
-        const int j = c * kChunkCols + 2 * jp;
-        if (h == 1) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (j + e < N) {
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) dst[r * width + j + e] = acc[r][e];
+        // dst = ((p3 + p2) + p1) + p0, then bias and activation
+        const int j = c * kChunkCols + 4 * jq;
+        const bool vec = (j + 3 < N) && ((op.dst_col & 3) == 0);
+        for (int g = kSplitK - 1; g >= 0; --g) {
+            if (h == g && vec) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g == 0 && op.p1 != nullptr) {
+                    b.x = __ldg(op.p1 + j); b.y = __ldg(op.p1 + j + 1); b.z = __ldg(op.p1 + j + 2); b.w = __ldg(op.p1 + j + 3);
                 }
-        }
-        __syncthreads();
-        if (h == 0) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (j + e < N) {
-                    const float b = op.p1 != nullptr ? __ldg(op.p1 + j + e) : 0.f;
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) {
-                        float v = (acc[r][e] + dst[r * width + j + e]) + b;
-                        if (relu) v = fmaxf(v, 0.f);
-                        dst[r * width + j + e] = v;
+                for (int r = 0; r < kRows; ++r) {
+                    float4* d4 = reinterpret_cast<float4*>(dst + r * width + j);
+                    float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    if (g != kSplitK - 1) {
+                        const float4 p = *d4;
+                        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
                     }
+                    if (g == 0) {
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    }
+                    *d4 = v;
                 }
+            } else if (h == g) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j + e < N) {
+                        const float b = (g == 0 && op.p1 != nullptr) ? __ldg(op.p1 + j + e) : 0.f;
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) {
+                            float v = acc[r][e];
+                            if (g != kSplitK - 1) v += dst[r * width + j + e];
+                            if (g == 0) {
+                                v += b;
+                                if (relu) v = fmaxf(v, 0.f);
+                            }
+                            dst[r * width + j + e] = v;
+                        }
+                    }
+            }
+            if (g != 0) consumer_sync();
         }
     }
 }
@@ -197,9 +223,8 @@ __device__ __forceinline__ void op_linear(const RowProgram& prog, const racf_row
 // Narrow outputs (a few columns, n * k <= 8192): the weight W [n][k] (nn.Linear's own layout) arrives as ONE tile of the
 // stream; one warp per row, lanes split k, warp-shuffle reduction per output column.
 template <int kRows>
-__device__ __forceinline__ void op_linear_narrow(const RowProgram& prog, const racf_row_op_t& op, float* bufs,
-                                                 const float* wtiles, uint32_t full_bar, int width, int tid,
-                                                 unsigned& consumed, TileCursor& cursor) {
+__device__ __forceinline__ void op_linear_narrow(const racf_row_op_t& op, float* bufs, const float* wtiles, uint32_t full_bar,
+                                                 uint32_t empty_bar, int width, int tid, unsigned& consumed) {
     const int warp = tid >> 5, lane = tid & 31;
     const int N = op.n, K = op.k;
     const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
@@ -228,30 +253,24 @@ __device__ __forceinline__ void op_linear_narrow(const RowProgram& prog, const r
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + 8u * stage);
     ++consumed;
-    if (tid == 0) {
-        const float* g; uint32_t bytes;
-        if (next_tile(prog, cursor, g, bytes)) {
-            mbar_arrive_expect_tx(full_bar + 8u * stage, bytes);
-            tma_load_bulk(smem_u32(wtiles + (size_t)stage * kTileFloats), g, bytes, full_bar + 8u * stage);
-        }
-    }
 }
 
 // In-place LayerNorm over n columns (two-pass mean / variance, biased variance, rsqrtf as PyTorch), optional ReLU.
-// Vector path (n, dst_col multiples of 4, n <= 1024, 16-byte aligned gamma / beta): the row lives in registers and the
+// Vector path (n, dst_col multiples of 4, n <= 256, 16-byte aligned gamma / beta): the row lives in registers and the
 // gamma / beta loads are issued before the reductions, so their latency is hidden.
 template <int kRows>
 __device__ __forceinline__ void op_layernorm(const racf_row_op_t& op, float* bufs, int width, int warp, int lane) {
+    constexpr int kV = 2;                     // float4 per lane on the vector path
     const int n = op.n;
     const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
-    const bool vec = ((n | op.dst_col) & 3) == 0 && n <= 1024 &&
+    const bool vec = ((n | op.dst_col) & 3) == 0 && n <= 128 * kV &&
                      ((reinterpret_cast<uintptr_t>(op.p0) | reinterpret_cast<uintptr_t>(op.p1)) & 15u) == 0;
     for (int r = warp; r < kRows; r += kRowWarps) {
         float* x = bufs + ((size_t)op.dst * kRows + r) * width + op.dst_col;
         if (vec) {
-            constexpr int kV = 8;                 // float4 per lane: n <= 1024
             const int n4 = n >> 2;
             float4 v[kV], g[kV], b[kV];
 #pragma unroll
@@ -310,35 +329,48 @@ __device__ __forceinline__ void op_layernorm(const racf_row_op_t& op, float* buf
 }
 
 template <int kRows>
-__global__ void __launch_bounds__(kRowThreads, 1)
+__global__ void __launch_bounds__(kLaunchThreads, 1)
 row_program_kernel(const __grid_constant__ RowProgram prog) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float queue_w[kRows][RACF_ROW_MAX_QUEUE];
-    __shared__ __align__(8) unsigned long long full_bars[kStages];
+    __shared__ __align__(8) unsigned long long bars[2 * kStages];
     float* wtiles = smem;                                  // [kStages][32][256]
     float* bufs = smem + (size_t)kStages * kTileFloats;    // [num_bufs][kRows][width]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int width = prog.width;
     const long long row0 = (long long)blockIdx.x * kRows;
     const int valid = (int)min((long long)kRows, (long long)prog.rows - row0);
-    const uint32_t full_bar = smem_u32(full_bars);
+    const uint32_t full_bar = smem_u32(bars), empty_bar = full_bar + 8u * kStages;
 
-    TileCursor cursor = {0, 0, 0};
-    unsigned consumed = 0;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(full_bar + 8u * s, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar + 8u * s, 1);
+            mbar_init(empty_bar + 8u * s, kRowWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < kStages; ++s) {
-            const float* g; uint32_t bytes;
-            if (!next_tile(prog, cursor, g, bytes)) break;
-            mbar_arrive_expect_tx(full_bar + 8u * s, bytes);
-            tma_load_bulk(smem_u32(wtiles + (size_t)s * kTileFloats), g, bytes, full_bar + 8u * s);
-        }
     }
     __syncthreads();
 
+    if (warp == kRowWarps) {
+        // Producer warp: one thread walks the weight-tile stream of the whole program and keeps the ring full, waiting
+        // only for the consumers to release a stage.
+        if (lane == 0) {
+            TileCursor cursor = {0, 0, 0};
+            const float* g;
+            uint32_t bytes;
+            for (unsigned issued = 0; next_tile(prog, cursor, g, bytes); ++issued) {
+                const unsigned s = issued % kStages;
+                if (issued >= kStages) mbar_wait(empty_bar + 8u * s, ((issued / kStages) - 1u) & 1u);
+                mbar_arrive_expect_tx(full_bar + 8u * s, bytes);
+                tma_load_bulk(smem_u32(wtiles + (size_t)s * kTileFloats), g, bytes, full_bar + 8u * s);
+            }
+        }
+        return;
+    }
+
+    unsigned consumed = 0;
     for (int i = 0; i < prog.num_ops; ++i) {
         const racf_row_op_t& op = prog.ops[i];
         switch (op.kind) {
@@ -376,7 +408,7 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
                     for (int t = 0; t < T; ++t) queue_w[tid][t] = 1.f / (float)T;
                 }
             }
-            __syncthreads();
+            consumer_sync();
             const int n4 = op.n >> 2;      // validated: n, ld, dst_col multiples of 4, p0 16-byte aligned
             for (int e = tid; e < kRows * n4; e += kRowThreads) {
                 const int r = e / n4, c = (e - r * n4) * 4;
@@ -421,14 +453,14 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
             }
             break;
         }
-        case RACF_ROWOP_LINEAR: op_linear<kRows>(prog, op, bufs, wtiles, full_bar, width, tid, consumed, cursor); break;
+        case RACF_ROWOP_LINEAR: op_linear<kRows>(op, bufs, wtiles, full_bar, empty_bar, width, tid, consumed); break;
         case RACF_ROWOP_LINEAR_NARROW:
-            op_linear_narrow<kRows>(prog, op, bufs, wtiles, full_bar, width, tid, consumed, cursor);
+            op_linear_narrow<kRows>(op, bufs, wtiles, full_bar, empty_bar, width, tid, consumed);
             break;
         case RACF_ROWOP_LAYERNORM: op_layernorm<kRows>(op, bufs, width, warp, lane); break;
         default: break;
         }
-        __syncthreads();
+        consumer_sync();
     }
 }
 
@@ -482,7 +514,7 @@ static int launch(const RowProgram& prog, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     const long long grid = ((long long)prog.rows + kRows - 1) / kRows;
     if (grid > 0x7fffffffLL) return RACF_ERR_BAD_SHAPE;
-    row_program_kernel<kRows><<<(unsigned)grid, kRowThreads, smem, st>>>(prog);
+    row_program_kernel<kRows><<<(unsigned)grid, kLaunchThreads, smem, st>>>(prog);
     return (int)cudaGetLastError();
 }
 

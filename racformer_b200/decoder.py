@@ -366,8 +366,14 @@ class BEVSelfAttention(nn.Module):
             from . import linear
             if getattr(self, "_split_value_proj", None) is None:
                 self._split_value_proj = linear.SplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
-            x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(),
-                                                None if pos is None else pos.reshape(C, -1).contiguous(), tiled=True)
+            pixels = bev.permute(0, 1, 3, 4, 2)
+            if pixels.is_contiguous():      # channel-last maps (the radar temporal encoder's output): already [B*T*S, C]
+                # [C, S] -> [S, C]: a view of LearnedPositionalEncoding's own [H, W, C] layout (no copy)
+                addend = None if pos is None else pos.reshape(C, -1).t().contiguous()
+                x3 = linear.split_tiled(pixels.reshape(-1, C), addend)
+            else:
+                x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(),
+                                                    None if pos is None else pos.reshape(C, -1).contiguous(), tiled=True)
             v = self._split_value_proj(x3=x3)
             return v.reshape(B * T, x3.rows // (B * T), self.num_heads, -1)
         if pos is not None:
@@ -462,9 +468,23 @@ class RadarBEVTemporalEncoder(nn.Module):
         self.upsample = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
                                       nn.Conv2d(hidden_dims, hidden_dims, kernel_size=3, padding=1))
 
+    channels_last = True    # inference on CUDA: run the convolutions on channel-last tensors (no cuDNN layout round trips)
+
     def inner_forward(self, bev):
         B, T, C, H, W = bev.shape
         r = self.downsample_ratio
+        if self.channels_last and not torch.is_grad_enabled() and bev.is_cuda:
+            # Same operators on NHWC memory: cuDNN's fp32 / TF32 kernels are NHWC kernels, so NCHW tensors are converted
+            # in and out around every convolution (0.27 ms per forward at f8). The result stays channel-last -- it is
+            # exactly the [B*T*H*W, C] pixel matrix value_proj consumes (BEVSelfAttention.project_value).
+            x = bev.flatten(0, 1).contiguous(memory_format=torch.channels_last)
+            down = self.downsample(x).unflatten(0, (B, T))
+            hid = self.upsample(self.convGRU(down).flatten(0, 1).contiguous(memory_format=torch.channels_last))
+            both = torch.empty((B * T, C + self.hidden_dims, H, W), dtype=bev.dtype, device=bev.device,
+                               memory_format=torch.channels_last)
+            both[:, :C].copy_(x)
+            both[:, C:].copy_(hid)
+            return self.temporal_fusion(both).unflatten(0, (B, T))
         down = self.downsample(bev.flatten(0, 1)).reshape(B, T, self.hidden_dims, H // r, W // r)
         hid = self.upsample(self.convGRU(down).flatten(0, 1)).reshape(B, T, self.hidden_dims, H, W)
         return self.temporal_fusion(torch.cat([bev, hid], dim=2).flatten(0, 1)).reshape(B, T, C, H, W)

@@ -55,14 +55,22 @@ def empty_tiled(rows, K, device):
     return TiledOperand(torch.empty(tiled_bytes(rows, K) // 2, dtype=torch.bfloat16, device=device), rows, K)
 
 
-def split_tiled(x):
-    """fp32 CUDA matrix [rows, K] -> TiledOperand (the K tail of the last 32-wide block is zero-filled)."""
+def split_tiled(x, addend=None):
+    """fp32 CUDA matrix [rows, K] (+ addend [rows_a, K], broadcast with period rows_a over the rows) -> TiledOperand
+    (the K tail of the last 32-wide block is zero-filled)."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.numel() > 0):
         raise RuntimeError("split_tiled needs a contiguous fp32 CUDA matrix")
+    if addend is not None and not (addend.is_cuda and addend.dtype == torch.float32 and addend.is_contiguous()
+                                   and addend.dim() == 2 and addend.shape[1] == x.shape[1] and addend.device == x.device
+                                   and x.shape[0] % addend.shape[0] == 0):
+        raise RuntimeError("split_tiled: addend must be a contiguous fp32 CUDA matrix [rows / n, K] on the same device")
     out = empty_tiled(x.shape[0], x.shape[1], x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.load().racf_split_bf16x3_tiled(x.data_ptr(), x.shape[0], x.shape[1], out.buf.data_ptr(), _stream(x.device))
-    _lib.check(rc, "racf_split_bf16x3_tiled")
+        rc = _lib.load().racf_split_bf16x3_tiled_add(x.data_ptr(), x.shape[0], x.shape[1],
+                                                     addend.data_ptr() if addend is not None else None,
+                                                     addend.shape[0] if addend is not None else 1, out.buf.data_ptr(),
+                                                     _stream(x.device))
+    _lib.check(rc, "racf_split_bf16x3_tiled_add")
     return out
 
 

@@ -231,3 +231,16 @@ def test_multi_linear_equals_the_separate_layers():
         torch.testing.assert_close(multi(x)[1], lins[1](x).reshape(900, -1), rtol=1e-5, atol=2e-5)
     with pytest.raises(RuntimeError):
         linear.MultiSplitLinear([torch.nn.Linear(256, 8), torch.nn.Linear(128, 8)])
+
+
+@pytest.mark.gpu
+def test_split_tiled_with_row_periodic_addend_is_the_split_of_the_sum():
+    """racf_split_bf16x3_tiled_add == racf_split_bf16x3_tiled of (x + addend broadcast over row blocks), bit for bit."""
+    from racformer_b200 import linear
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(3 * 70, 40, device=dev, generator=g)
+    add = torch.randn(70, 40, device=dev, generator=g)
+    got = linear.split_tiled(x, add)
+    ref = linear.split_tiled((x.view(3, 70, 40) + add).reshape(210, 40).contiguous())
+    assert torch.equal(linear.untile(got), linear.untile(ref))

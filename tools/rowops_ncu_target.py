@@ -1,4 +1,5 @@
-"""ncu target: a few eager launches of the decoder's tail row program at the f8 shapes (see tools/rowops_bench.py)."""
+"""ncu target: a few eager launches of the decoder's row programs and self-attention core at the f8 shapes (see
+tools/rowops_bench.py)."""
 import os
 import sys
 
@@ -17,8 +18,10 @@ layer.init_weights()
 mixed, qf = torch.randn(B, Q, E, device=dev), torch.randn(B, Q, E, device=dev)
 radar = (torch.randn(B * T, Q, E, device=dev), torch.randn(B, Q, T, device=dev))
 lss = (torch.randn(B * T, Q, E, device=dev), torch.randn(B, Q, T, device=dev))
+qb = torch.rand(B, Q, 10, device=dev)
 with torch.no_grad():
-    for _ in range(4):
+    for _ in range(3):
         layer._tail_rows(mixed, qf, radar, lss)
+        layer._self_attn_rows(qb, qf)
 torch.cuda.synchronize()
 print("ok")
