@@ -278,6 +278,14 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
                                      int max_order, int tiled, racf_stream_t stream);
 
 /*
+ * in [batch][channels][positions] -> out[batch][positions][ld] (the first `channels` floats of every ld-long pixel row)
+ * and, when out2 != NULL, the same values into out2 with row length ld2: NCHW -> NHWC in front of the radar temporal
+ * encoder's convolutions (models/racformer_transformer.py:645-656), a tiled transpose.
+ */
+int racf_chw_to_hwc(const float* in, int batch, int channels, int positions, float* out, int ld, float* out2,
+                    int ld2, racf_stream_t stream);
+
+/*
  * Call-site row: the attention core of ScaleAdaptiveSelfAttention
  * (models/racformer_transformer.py:283-336: pairwise centre distances, dist * tau as the additive mask of mmcv's
  * MultiheadAttention, softmax, weighted sum) as one launch, without materialising the [B, H, Q, Q] mask.

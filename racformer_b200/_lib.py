@@ -53,6 +53,7 @@ SIGNATURES = {
     "racf_linear_bf16x3_multi_forward": (_i, [ctypes.c_void_p, ctypes.c_void_p, _i, _i, _i, ctypes.POINTER(_i),
                                               ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _i, _i,
                                               ctypes.c_void_p]),
+    "racf_chw_to_hwc": (_i, [_c_float_p, _i, _i, _i, _c_float_p, _i, _c_float_p, _i, ctypes.c_void_p]),
     "racf_sasa_attention_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, ctypes.POINTER(ctypes.c_double), _i, _i, _i, _i,
                                          _i, _c_float_p, ctypes.c_void_p]),
     "racf_refine_bbox_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,

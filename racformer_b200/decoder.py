@@ -477,12 +477,16 @@ class RadarBEVTemporalEncoder(nn.Module):
             # Same operators on NHWC memory: cuDNN's fp32 / TF32 kernels are NHWC kernels, so NCHW tensors are converted
             # in and out around every convolution (0.27 ms per forward at f8). The result stays channel-last -- it is
             # exactly the [B*T*H*W, C] pixel matrix value_proj consumes (BEVSelfAttention.project_value).
-            x = bev.flatten(0, 1).contiguous(memory_format=torch.channels_last)
+            if bev.dtype == torch.float32 and bev.is_contiguous():
+                from . import points   # one tiled transpose writes x and the first C channels of the concatenation
+                x, both = points.to_channels_last(bev.flatten(0, 1), self.hidden_dims)
+            else:
+                x = bev.flatten(0, 1).contiguous(memory_format=torch.channels_last)
+                both = torch.empty((B * T, C + self.hidden_dims, H, W), dtype=bev.dtype, device=bev.device,
+                                   memory_format=torch.channels_last)
+                both[:, :C].copy_(x)
             down = self.downsample(x).unflatten(0, (B, T))
             hid = self.upsample(self.convGRU(down).flatten(0, 1).contiguous(memory_format=torch.channels_last))
-            both = torch.empty((B * T, C + self.hidden_dims, H, W), dtype=bev.dtype, device=bev.device,
-                               memory_format=torch.channels_last)
-            both[:, :C].copy_(x)
             both[:, C:].copy_(hid)
             return self.temporal_fusion(both).unflatten(0, (B, T))
         down = self.downsample(bev.flatten(0, 1)).reshape(B, T, self.hidden_dims, H // r, W // r)

@@ -78,6 +78,24 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
     return out
 
 
+def to_channels_last(x, concat_channels=0):
+    """x [N, C, H, W] contiguous -> (x as a channels_last tensor, and -- concat_channels > 0 -- a channels_last
+    [N, C + concat_channels, H, W] buffer whose first C channels are x; the rest is uninitialised): one tiled transpose
+    instead of PyTorch's strided copies in front of the radar temporal encoder."""
+    _check(x)
+    N, C, H, W = x.shape
+    dense = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    both = None
+    if concat_channels > 0:
+        both = torch.empty((N, C + concat_channels, H, W), dtype=torch.float32, device=x.device,
+                           memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_chw_to_hwc(x.data_ptr(), N, C, H * W, dense.data_ptr(), C,
+                                         both.data_ptr() if both is not None else None, C + concat_channels, _stream(x.device))
+    _lib.check(rc, "racf_chw_to_hwc")
+    return dense, both
+
+
 def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_groups=0, tensor_cores=True):
     """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
     (csrc/mixing.cu). With split=True the result comes back as its three bf16 pieces [3, QG, out_points, C] (their sum is

@@ -177,3 +177,18 @@ def test_fused_adaptive_mixing_core_declines_unsupported_shapes():
     assert points.adaptive_mixing_core(x, torch.randn(4, 64 * 64 + 128 * 10, device="cuda"), 128) is None
     x = torch.randn(4, 8, 32, device="cuda")           # C != 64
     assert points.adaptive_mixing_core(x, torch.randn(4, 32 * 32 + 128 * 8, device="cuda"), 128) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,extra", [((8, 256, 16, 16), 64), ((2, 37, 5, 7), 3), ((1, 64, 9, 33), 0)])
+def test_to_channels_last_is_a_pure_copy(shape, extra):
+    """racf_chw_to_hwc: same values as .contiguous(memory_format=channels_last), also into the concatenation buffer."""
+    from racformer_b200 import points
+    x = torch.randn(*shape, device="cuda")
+    dense, both = points.to_channels_last(x, extra)
+    assert dense.is_contiguous(memory_format=torch.channels_last) and torch.equal(dense, x)
+    if extra:
+        assert both.shape == (shape[0], shape[1] + extra, shape[2], shape[3])
+        assert both.is_contiguous(memory_format=torch.channels_last) and torch.equal(both[:, :shape[1]], x)
+    else:
+        assert both is None
