@@ -380,11 +380,31 @@ class DecoderWorkload:
                 wl.tensor_shapes["adaptive_mixing_core"] = tuple(x.shape) + (out_points,)
                 return out
 
+            from racformer_b200 import rowops
+            run, sasa = rowops.RowProgram.run, points.sasa_attention
+
+            def timed_run(program):       # the three row programs of an iteration (csrc/rowops.cu)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                run(program)
+                b.record()
+                wl.timers.setdefault("row_programs", []).append((a, b))
+
+            def timed_sasa(*args, **kw):  # the self-attention core (csrc/sasa.cu)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = sasa(*args, **kw)
+                b.record()
+                wl.timers.setdefault("sasa_attention_core", []).append((a, b))
+                return out
+
             linear.linear_bf16x3, points.adaptive_mixing_core = timed_linear, timed_mixing
+            rowops.RowProgram.run, points.sasa_attention = timed_run, timed_sasa
             try:
                 yield
             finally:
                 linear.linear_bf16x3, points.adaptive_mixing_core = lin, mix
+                rowops.RowProgram.run, points.sasa_attention = run, sasa
         return ctx()
 
     def kernel_report(self, hbm_peak):
@@ -428,8 +448,9 @@ class DecoderWorkload:
                             "fp32_equivalent_tflops": flops / (avg * 1e-3) / 1e12,
                             "issued_bf16_mma_tflops": terms * flops / (avg * 1e-3) / 1e12, "bf16_terms_per_product": terms}
                 continue
-            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / max(1, len(ms) // (
-                self.layers * (2 if key == "msda_fwd" else 1)))}
+            per_iteration = {"msda_fwd": 2, "row_programs": 3}.get(key, 1)      # launches per decoder iteration
+            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg,
+                        "total_ms_per_step": sum(ms) / max(1, len(ms) // (self.layers * per_iteration))}
             if key in algo:
                 gbs = algo[key] / (avg * 1e-3) / 1e9
                 rep[key].update({"algorithmic_bytes": algo[key], "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
