@@ -546,10 +546,11 @@ class DecoderTrainWorkload(DecoderWorkload):
     projection of the outputs (Hungarian assignment / losses are outside the path)."""
     metric = "decoder training samples/s (RaCFormer R50 704x256 f8 decoder fwd+bwd+allreduce+AdamW, batch 2/GPU)"
 
-    def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320, num_cams=6, checkpoint=False):
+    def __init__(self, device, seed=0, name="decoder_train_f8", batch=2, dn_queries=320, num_cams=6, checkpoint=False,
+                 mixing_precision="bf16x6"):
         from racformer_b200.parallel import GradientAllReducer
         from racformer_b200.synthetic import make_decoder_inputs
-        super().__init__(device, seed=seed, name=name, graph=False, num_cams=num_cams)
+        super().__init__(device, seed=seed, name=name, graph=False, num_cams=num_cams, mixing_precision=mixing_precision)
         self.samples_per_step = batch
         self.batch, self.dn = batch, dn_queries
         self.model.train()
@@ -581,6 +582,11 @@ class DecoderTrainWorkload(DecoderWorkload):
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=4e-4, weight_decay=0.01)
         self.reducer = GradientAllReducer(list(self.model.parameters()))
         self.launches_per_step = 3 * self.layers * (3 if checkpoint else 2)   # forward, (checkpoint recompute,) backward
+        if mixing_precision.startswith("bf16") and not checkpoint:
+            # AdaptiveMixing's two Linear layers with autograd on the tcgen05 kernel: per iteration 5 launches forward
+            # (2 operand splits, 2 GEMMs, 1 split-K reduce) and 13 backward (6 splits, 4 GEMMs, 3 reduces), plus the
+            # splits of W and W^T of both layers once per step
+            self.launches_per_step += 18 * self.layers + 4
         self.allreduce_bytes = 0
 
     def config(self):
@@ -628,6 +634,8 @@ class DecoderTrainWorkload(DecoderWorkload):
 def build(name, device, seed=0):
     if name == "decoder_train_f8":
         return DecoderTrainWorkload(device, seed=seed)
+    if name == "decoder_train_f8_sgemm":       # AdaptiveMixing's Linear layers on cuBLAS SGEMM (the reference's arithmetic)
+        return DecoderTrainWorkload(device, seed=seed, name=name, mixing_precision="fp32")
     if name == "decoder_train_f8_checkpoint":   # the reference's schedule: activation checkpointing on
         return DecoderTrainWorkload(device, seed=seed, name=name, checkpoint=True)
     if name == "decoder_forward_f8_3cam":      # racformer_r50_nuimg_704x256_f8_3cam_3rad (config 5), forward

@@ -655,6 +655,20 @@ class AdaptiveMixing(nn.Module):
         return (self.gemm_precision in ("bf16x9", "bf16x6") and not torch.is_grad_enabled() and query.is_cuda
                 and query.dtype == torch.float32)
 
+    train_tensor_cores = True      # training on CUDA: the two large Linear layers with autograd on csrc/linear.cu
+
+    def _train_linear(self, name, x):
+        """The tensor-core Linear with autograd (linear.TrainableSplitLinear) for `name` when it applies to x, else None."""
+        if not (self.train_tensor_cores and self.gemm_precision in ("bf16x9", "bf16x6") and torch.is_grad_enabled()
+                and x.is_cuda and x.dtype == torch.float32):
+            return None
+        from . import linear
+        order = linear.ALL_TERMS if self.gemm_precision == "bf16x9" else linear.SIX_TERMS
+        cur = self._split.get(("train", name))
+        if cur is None or cur.max_order != order:
+            cur = self._split[("train", name)] = linear.TrainableSplitLinear(getattr(self, name), max_order=order)
+        return cur if cur.supports(x) else None
+
     def _split_linear(self, name):
         from . import linear
         order = linear.ALL_TERMS if self.gemm_precision == "bf16x9" else linear.SIX_TERMS
@@ -671,6 +685,9 @@ class AdaptiveMixing(nn.Module):
         lin = self.parameter_generator
         if self._tensor_core_linear(query):
             return self._split_linear("parameter_generator")(query)
+        trainable = self._train_linear("parameter_generator", query)
+        if trainable is not None:
+            return trainable(query)
         if torch.is_grad_enabled() or not query.is_cuda or lin.bias is None or not self.fold_bias:
             return lin(query)
         if self.gemm_precision == "tf32x3":
@@ -708,6 +725,9 @@ class AdaptiveMixing(nn.Module):
     def _project(self, out):
         if self._tensor_core_linear(out):
             return self._split_linear("out_proj")(out)
+        trainable = self._train_linear("out_proj", out)
+        if trainable is not None:
+            return trainable(out)
         if self.gemm_precision == "tf32x3" and not torch.is_grad_enabled() and out.is_cuda:
             if self._split_out is None:
                 self._split_out = _SplitTF32Linear(self.out_proj)

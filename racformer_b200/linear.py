@@ -2,8 +2,9 @@
 
 `y = F.linear(x, weight, bias)` for AdaptiveMixing's parameter_generator and out_proj
 (models/racformer_transformer.py:560-566) with every fp32 operand split exactly into three bf16 pieces; all nine (or the
-six largest) piece products are accumulated in fp32 in tensor memory. Forward / inference only; CUDA only -- there is no
-CPU or PyTorch fallback in this module.
+six largest) piece products are accumulated in fp32 in tensor memory. CUDA only -- there is no CPU or PyTorch fallback in
+this module. `SplitLinear` is the inference stand-in for an nn.Linear; `TrainableSplitLinear` adds autograd: the input
+and weight gradients are two more GEMMs of the same kernel on transposed operand splits.
 """
 import ctypes
 
@@ -182,6 +183,81 @@ class SplitLinear:
         bias = self.linear.bias.detach() if self.linear.bias is not None else None
         y = linear_bf16x3(x3, self.weight_pieces(), bias, self.max_order, variant=self.variant)
         return y.reshape(*lead, -1)
+
+
+def split_tiled_transposed(x):
+    """fp32 CUDA matrix [R, C] -> TiledOperand of its transpose [C rows, K = R] (R % 8 == 0): the transposing operand
+    split (racf_split_bf16x3_chw_to_hwc with one batch element), used for the backward GEMMs."""
+    if x.dim() != 2:
+        raise RuntimeError("split_tiled_transposed needs a matrix")
+    return split_bf16x3_chw_to_hwc(x.contiguous().unsqueeze(0), None, tiled=True)
+
+
+class _SplitLinearFunction(torch.autograd.Function):
+    """y = x @ W^T + b on the tcgen05 Linear kernel with autograd (fp32-grade in all three products):
+        grad_x [M,K] = g [M,N] . (W^T) [K,N]^T      grad_W [N,K] = g^T [N,M] . (x^T) [K,M]^T      grad_b = sum_m g
+    Replaces F.linear for AdaptiveMixing's parameter_generator / out_proj while training
+    (models/racformer_transformer.py:560-566, 592, 606); the reference runs three cuBLAS SGEMMs per layer call."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, owner):
+        lead, K = x.shape[:-1], x.shape[-1]
+        x2 = x.reshape(-1, K).contiguous()
+        y = linear_bf16x3(split_tiled(x2), owner.weight_pieces(), bias.detach() if bias is not None else None,
+                          owner.max_order, variant=2)
+        ctx.save_for_backward(x2, weight)
+        ctx.owner, ctx.has_bias, ctx.lead = owner, bias is not None, lead
+        return y.reshape(*lead, weight.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        x2, weight = ctx.saved_tensors
+        owner = ctx.owner
+        g2 = grad_y.reshape(-1, weight.shape[0]).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = linear_bf16x3(split_tiled(g2), owner.weight_t_pieces(), None, owner.max_order, variant=2)
+            gx = gx.reshape(*ctx.lead, weight.shape[1])
+        if ctx.needs_input_grad[1]:
+            gw = linear_bf16x3(split_tiled_transposed(g2), split_tiled_transposed(x2), None, owner.max_order, variant=2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb, None
+
+
+class TrainableSplitLinear:
+    """nn.Linear stand-in with autograd on the tcgen05 kernel. Caches the tiled pieces of W (forward) and of W^T (input
+    gradient); both are re-split when the parameter changes (optimizer step). The row count of the input must be a
+    multiple of 8 when a weight gradient is needed (the transposing split works on 16-byte chunks)."""
+
+    def __init__(self, linear, max_order=SIX_TERMS):
+        self.linear, self.max_order = linear, max_order
+        self._key = self._w3 = self._keyt = self._wt3 = None
+
+    def _version_key(self):
+        w = self.linear.weight
+        return (w.data_ptr(), w._version, w.device)
+
+    def weight_pieces(self):
+        key = self._version_key()
+        if self._key != key:
+            self._w3, self._key = split_tiled(self.linear.weight.detach().contiguous()), key
+        return self._w3
+
+    def weight_t_pieces(self):
+        key = self._version_key()
+        if self._keyt != key:
+            self._wt3, self._keyt = split_tiled_transposed(self.linear.weight.detach()), key
+        return self._wt3
+
+    def supports(self, x):
+        rows = x.numel() // x.shape[-1]
+        return (x.is_cuda and x.dtype == torch.float32 and rows % 8 == 0 and self.linear.out_features % 8 == 0
+                and self.linear.in_features % 8 == 0)
+
+    def __call__(self, x):
+        return _SplitLinearFunction.apply(x, self.linear.weight, self.linear.bias, self)
 
 
 class MultiSplitLinear:

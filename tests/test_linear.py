@@ -244,3 +244,79 @@ def test_split_tiled_with_row_periodic_addend_is_the_split_of_the_sum():
     got = linear.split_tiled(x, add)
     ref = linear.split_tiled((x.view(3, 70, 40) + add).reshape(210, 40).contiguous())
     assert torch.equal(linear.untile(got), linear.untile(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,K,N", [(304, 256, 1024), (64, 512, 256), (2440, 256, 384)])
+def test_trainable_split_linear_gradients_are_fp32_grade(rows, K, N):
+    """TrainableSplitLinear (forward, grad_x, grad_W, grad_b as bf16x3 tcgen05 GEMMs) vs an fp64 evaluation, next to the
+    errors of nn.Linear's cuBLAS SGEMM path on the same inputs."""
+    import torch.nn as nn
+    from racformer_b200 import linear
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(rows + K)
+    lin = nn.Linear(K, N).to(dev)
+    x = torch.randn(2, rows // 2, K, device=dev)
+    g = torch.randn(2, rows // 2, N, device=dev)
+
+    def run(fn, dtype):
+        xx = x.detach().to(dtype).clone().requires_grad_()
+        w = lin.weight.detach().to(dtype).requires_grad_()
+        b = lin.bias.detach().to(dtype).requires_grad_()
+        y = fn(xx, w, b)
+        y.backward(g.to(dtype))
+        return y.detach(), xx.grad, w.grad, b.grad
+
+    ref = run(lambda xx, w, b: torch.nn.functional.linear(xx, w, b), torch.float64)
+    sgemm = run(lambda xx, w, b: torch.nn.functional.linear(xx, w, b), torch.float32)
+    tsl = linear.TrainableSplitLinear(lin, max_order=linear.SIX_TERMS)
+    assert tsl.supports(x)
+    xx = x.detach().clone().requires_grad_()
+    lin.zero_grad()
+    y = tsl(xx)
+    y.backward(g)
+    got = (y.detach(), xx.grad, lin.weight.grad, lin.bias.grad)
+    for name, a, s32, r in zip(("y", "grad_x", "grad_w", "grad_b"), got, sgemm, ref):
+        scale = float(r.abs().max())
+        err, err_sgemm = float((a.double() - r).abs().max()) / scale, float((s32.double() - r).abs().max()) / scale
+        assert err <= max(2 * err_sgemm, 2e-6), (name, err, err_sgemm)
+    # the cached W / W^T pieces follow the parameter
+    with torch.no_grad():
+        lin.weight.mul_(2.0)
+    y2 = tsl(x)
+    assert torch.allclose(y2, torch.nn.functional.linear(x, lin.weight, lin.bias), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_decoder_training_gradients_tensor_core_linears_match_sgemm():
+    """One training-mode decoder iteration on the GPU: AdaptiveMixing's Linear layers on the tcgen05 autograd path vs
+    cuBLAS SGEMM (everything else identical) -- outputs and all parameter / input gradients."""
+    from racformer_b200.decoder import RaCFormerTransformer
+    from racformer_b200.synthetic import fill_parameters_by_name
+    from tests.decoder_cases import SMALL, small_inputs
+    dev = torch.device("cuda", 0)
+    cfg = dict(SMALL, num_layers=1)
+    model = RaCFormerTransformer(**cfg).to(dev)
+    fill_parameters_by_name(model, seed=3)
+    model.train()
+    for m in model.modules():                      # deterministic: no dropout
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    inp = small_inputs(batch=2)
+    results = []
+    for precision in ("bf16x6", "fp32"):
+        model.set_mixing_precision(precision)
+        model.zero_grad()
+        qf = inp["query_feat"].to(dev).requires_grad_()
+        feats = [f.to(dev).requires_grad_() for f in inp["mlvl_feats"]]
+        cls, box = model(inp["query_bbox"].to(dev), qf, feats, inp["lss_bev"].to(dev), inp["radar_bev"].to(dev), None,
+                         inp["img_metas"])
+        (cls.square().sum() + box.square().sum()).backward()
+        mix = model.decoder.decoder_layer.mixing
+        results.append((cls.detach(), box.detach(), qf.grad, feats[0].grad, mix.parameter_generator.weight.grad.clone(),
+                        mix.out_proj.weight.grad.clone()))
+    for name, a, b in zip(("cls", "box", "grad_query", "grad_feat0", "grad_param_gen_w", "grad_out_proj_w"), *results):
+        tol = 1e-4 * float(b.abs().max()) + 1e-6
+        assert float((a - b).abs().max()) <= tol, (name, float((a - b).abs().max()), tol)
