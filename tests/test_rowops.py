@@ -223,3 +223,34 @@ def test_decoder_layer_fused_self_attention_matches_the_pytorch_chain():
         cls_b, box_b = model(*args)
     assert torch.allclose(cls_a, cls_b, rtol=1e-4, atol=2e-4), float((cls_a - cls_b).abs().max())
     assert torch.allclose(box_a, box_b, rtol=1e-4, atol=2e-4), float((box_a - box_b).abs().max())
+
+
+def test_chunked_transpose_layout_matches_the_header():
+    """rowops.chunked_transpose: element [c, k, j] = W[c * 256 + j, k], zero padded (include/racformer_ops.h, LINEAR)."""
+    from racformer_b200.rowops import CHUNK_COLS, chunked_transpose
+    torch.manual_seed(0)
+    for n, k in ((10, 7), (256, 32), (300, 5), (768, 256)):
+        w = torch.randn(n, k)
+        t = chunked_transpose(w)
+        chunks = (n + CHUNK_COLS - 1) // CHUNK_COLS
+        assert t.shape == (chunks, k, CHUNK_COLS) and t.is_contiguous()
+        for c in range(chunks):
+            cols = min(CHUNK_COLS, n - c * CHUNK_COLS)
+            assert torch.equal(t[c, :, :cols], w[c * CHUNK_COLS:c * CHUNK_COLS + cols].t())
+            assert not t[c, :, cols:].any()
+
+
+def test_row_program_builder_rejects_cpu_tensors_and_bad_shapes():
+    """There is no CPU path: the builder raises instead of falling back."""
+    from racformer_b200.rowops import MAX_OPS, RowProgram
+    p = RowProgram(4, width=8)
+    with pytest.raises(RuntimeError, match="fp32 CUDA"):
+        p.load(0, torch.zeros(4, 8))
+    with pytest.raises(RuntimeError, match="empty row program"):
+        p.run()
+    with pytest.raises(RuntimeError, match="queue values"):
+        p.load_queue(0, torch.zeros(8, 4, 8), None, 4, 2)
+    for _ in range(MAX_OPS):
+        p.add(0, 1, 4)
+    with pytest.raises(RuntimeError, match="too long"):
+        p.add(0, 1, 4)
