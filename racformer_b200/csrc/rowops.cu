@@ -143,21 +143,23 @@ __device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, 
                 const float* xh = xs + h * kGroupK;
 #pragma unroll
                 for (int kk = 0; kk < kGroupK; kk += 4) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(wh + (kk + 0) * kChunkCols);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wh + (kk + 1) * kChunkCols);
-                    const float4 w2 = *reinterpret_cast<const float4*>(wh + (kk + 2) * kChunkCols);
-                    const float4 w3 = *reinterpret_cast<const float4*>(wh + (kk + 3) * kChunkCols);
+                    float4 w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wh + (kk + i) * kChunkCols);
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
-                        const float4 x = *reinterpret_cast<const float4*>(xh + r * width + kk);
-                        acc[r][0] = fmaf(x.x, w0.x, acc[r][0]); acc[r][1] = fmaf(x.x, w0.y, acc[r][1]);
-                        acc[r][2] = fmaf(x.x, w0.z, acc[r][2]); acc[r][3] = fmaf(x.x, w0.w, acc[r][3]);
-                        acc[r][0] = fmaf(x.y, w1.x, acc[r][0]); acc[r][1] = fmaf(x.y, w1.y, acc[r][1]);
-                        acc[r][2] = fmaf(x.y, w1.z, acc[r][2]); acc[r][3] = fmaf(x.y, w1.w, acc[r][3]);
-                        acc[r][0] = fmaf(x.z, w2.x, acc[r][0]); acc[r][1] = fmaf(x.z, w2.y, acc[r][1]);
-                        acc[r][2] = fmaf(x.z, w2.z, acc[r][2]); acc[r][3] = fmaf(x.z, w2.w, acc[r][3]);
-                        acc[r][0] = fmaf(x.w, w3.x, acc[r][0]); acc[r][1] = fmaf(x.w, w3.y, acc[r][1]);
-                        acc[r][2] = fmaf(x.w, w3.z, acc[r][2]); acc[r][3] = fmaf(x.w, w3.w, acc[r][3]);
+                        const float4 x4 = *reinterpret_cast<const float4*>(xh + r * width + kk);
+                        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                        // packed FMA (fma.rn.f32x2): two columns per instruction -- a 3-register FFMA issues every second
+                        // cycle per scheduler on sm_100, the packed form does two of them in the same slot
+                        float2 lo = make_float2(acc[r][0], acc[r][1]), hi = make_float2(acc[r][2], acc[r][3]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 xx = make_float2(xv[i], xv[i]);
+                            lo = __ffma2_rn(xx, make_float2(w[i].x, w[i].y), lo);
+                            hi = __ffma2_rn(xx, make_float2(w[i].z, w[i].w), hi);
+                        }
+                        acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = hi.x; acc[r][3] = hi.y;
                     }
                 }
             } else {                               // K tail (or a tiny K): the groups take every fourth k

@@ -63,17 +63,20 @@ sasa_attention_kernel(const SasaArgs a) {
 
     const int qi = min(q0 + lane, a.Q - 1);                  // lanes past the end repeat the last query (not stored)
     const int E3 = 3 * a.E;
-    float q[kHeadDim], acc[kHeadDim];
+    // q and the accumulator as float2 pairs: the products run as packed FMAs (fma.rn.f32x2, two per issue slot; a
+    // 3-register FFMA issues only every second cycle per scheduler on sm_100)
+    float2 q2[kHeadDim / 2], acc2[kHeadDim / 2];
     {
         const float4* qp = reinterpret_cast<const float4*>(a.qkv + (row_base + qi) * E3 + h * kHeadDim);
 #pragma unroll
         for (int i = 0; i < kHeadDim / 4; ++i) {
             const float4 v = __ldg(qp + i);
-            q[4 * i] = v.x * a.scale; q[4 * i + 1] = v.y * a.scale; q[4 * i + 2] = v.z * a.scale; q[4 * i + 3] = v.w * a.scale;
+            q2[2 * i] = make_float2(v.x * a.scale, v.y * a.scale);
+            q2[2 * i + 1] = make_float2(v.z * a.scale, v.w * a.scale);
         }
     }
 #pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) acc[d] = 0.f;
+    for (int d = 0; d < kHeadDim / 2; ++d) acc2[d] = make_float2(0.f, 0.f);
     const float cx = centres[2 * qi], cy = centres[2 * qi + 1];
     const float neg_tau = -__ldg(a.tau + (row_base + qi) * a.H + h);
     float m = -INFINITY, l = 0.f;
@@ -112,19 +115,19 @@ sasa_attention_kernel(const SasaArgs a) {
         for (int jj = 0; jj < kKeyBlock; ++jj) {
             const int j = min(j0 + jj, j_end - 1);
             const float4* kp = reinterpret_cast<const float4*>(blk + jj * 2 * kHeadDim);
-            float d0 = 0.f, d1 = 0.f;
+            float2 d0 = make_float2(0.f, 0.f), d1 = make_float2(0.f, 0.f);   // (even, odd) dims of the two halves
 #pragma unroll
             for (int i = 0; i < kHeadDim / 4; i += 2) {
                 const float4 k0 = kp[i], k1 = kp[i + 1];
-                d0 = fmaf(q[4 * i], k0.x, d0); d0 = fmaf(q[4 * i + 1], k0.y, d0);
-                d0 = fmaf(q[4 * i + 2], k0.z, d0); d0 = fmaf(q[4 * i + 3], k0.w, d0);
-                d1 = fmaf(q[4 * i + 4], k1.x, d1); d1 = fmaf(q[4 * i + 5], k1.y, d1);
-                d1 = fmaf(q[4 * i + 6], k1.z, d1); d1 = fmaf(q[4 * i + 7], k1.w, d1);
+                d0 = __ffma2_rn(q2[2 * i], make_float2(k0.x, k0.y), d0);
+                d0 = __ffma2_rn(q2[2 * i + 1], make_float2(k0.z, k0.w), d0);
+                d1 = __ffma2_rn(q2[2 * i + 2], make_float2(k1.x, k1.y), d1);
+                d1 = __ffma2_rn(q2[2 * i + 3], make_float2(k1.z, k1.w), d1);
             }
             const float2 c = *reinterpret_cast<const float2*>(centres + 2 * j);
             const float dx = cx - c.x, dy = cy - c.y;
             const float dist = sqrtf(fmaf(dy, dy, __fmul_rn(dx, dx)));      // torch.norm's reduction: acc + x * x
-            s[jj] = (j0 + jj < j_end) ? __fadd_rn(d0 + d1, __fmul_rn(dist, neg_tau)) : -INFINITY;
+            s[jj] = (j0 + jj < j_end) ? __fadd_rn((d0.x + d0.y) + (d1.x + d1.y), __fmul_rn(dist, neg_tau)) : -INFINITY;
         }
         float mb = s[0];
 #pragma unroll
@@ -134,7 +137,7 @@ sasa_attention_kernel(const SasaArgs a) {
         m = m_new;
         l *= corr;
 #pragma unroll
-        for (int d = 0; d < kHeadDim; ++d) acc[d] *= corr;
+        for (int d = 0; d < kHeadDim / 2; ++d) { acc2[d].x *= corr; acc2[d].y *= corr; }
 #pragma unroll
         for (int jj = 0; jj < kKeyBlock; ++jj) {
             const float p = expf(s[jj] - m);                 // exp(-inf) = 0 for the padded keys
@@ -143,8 +146,9 @@ sasa_attention_kernel(const SasaArgs a) {
 #pragma unroll
             for (int i = 0; i < kHeadDim / 4; ++i) {
                 const float4 v = vp[i];
-                acc[4 * i] = fmaf(p, v.x, acc[4 * i]); acc[4 * i + 1] = fmaf(p, v.y, acc[4 * i + 1]);
-                acc[4 * i + 2] = fmaf(p, v.z, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(p, v.w, acc[4 * i + 3]);
+                const float2 pp = make_float2(p, p);
+                acc2[2 * i] = __ffma2_rn(pp, make_float2(v.x, v.y), acc2[2 * i]);
+                acc2[2 * i + 1] = __ffma2_rn(pp, make_float2(v.z, v.w), acc2[2 * i + 1]);
             }
         }
         __syncwarp();                                        // the block after next overwrites this buffer
@@ -155,7 +159,10 @@ sasa_attention_kernel(const SasaArgs a) {
     mine[0] = m;
     mine[32] = l;
 #pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) mine[(2 + d) * 32] = acc[d];
+    for (int d = 0; d < kHeadDim / 2; ++d) {
+        mine[(2 + 2 * d) * 32] = acc2[d].x;
+        mine[(3 + 2 * d) * 32] = acc2[d].y;
+    }
     __syncthreads();
     float mx = -INFINITY;
 #pragma unroll
