@@ -361,11 +361,16 @@ class DecoderWorkload:
             lin, mix = linear.linear_bf16x3, points.adaptive_mixing_core
 
             def timed_linear(a3, w3, bias=None, *args, **kw):
+                M, K, N = (a3.rows, a3.K, w3.rows) if isinstance(a3, linear.TiledOperand) else (a3.shape[1], a3.shape[2], w3.shape[1])
+                # prime the caching allocator with the output / split-K workspace sizes so that a cudaMalloc inside the
+                # wrapper (eager pass, pool state left by the graph capture) is not timed as kernel time
+                prime = [torch.empty((M, N), dtype=torch.float32, device=wl.device),
+                         torch.empty((linear.plan(M, N, K)[0], M, N), dtype=torch.float32, device=wl.device)]
+                del prime
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 out = lin(a3, w3, bias, *args, **kw)
                 b.record()
-                M, K, N = (a3.rows, a3.K, w3.rows) if isinstance(a3, linear.TiledOperand) else (a3.shape[1], a3.shape[2], w3.shape[1])
                 name = {(256, 65536): "linear_parameter_generator", (32768, 256): "linear_out_proj"}.get((K, N), "linear_value_proj")
                 wl.timers.setdefault(name, []).append((a, b))
                 wl.tensor_shapes[name] = (M, N, K)
