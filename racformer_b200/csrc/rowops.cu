@@ -117,10 +117,11 @@ __device__ __forceinline__ bool next_tile(const RowProgram& prog, TileCursor& cu
 // of every tile, so each weight element is read from shared memory once (LDS.128) and each input once per warp
 // (LDS.128 broadcast): 4 + kRows shared-memory instructions per 16 * kRows FMAs. A warp releases a stage by arriving on
 // its "empty" barrier -- the consumer warps never wait for each other inside a Linear. The four k groups are added at
-// the end of a chunk through the destination buffer, in a fixed order.
+// the end of a chunk through a scratch area, in a fixed order, behind one barrier.
 template <int kRows>
-__device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, const float* wtiles, uint32_t full_bar,
-                                          uint32_t empty_bar, int width, int tid, unsigned& consumed) {
+__device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, float* scratch, const float* wtiles,
+                                          uint32_t full_bar, uint32_t empty_bar, int width, int tid, unsigned& consumed) {
+    static_assert(kSplitK >= 2, "the epilogue sums kSplitK - 1 parked partials and the owner's accumulators");
     constexpr int kGroupK = kTileK / kSplitK;   // 8
     const int jq = tid & 63, h = tid >> 6, lane = tid & 31;
     const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
@@ -146,20 +147,23 @@ __device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, 
                     float4 w[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wh + (kk + i) * kChunkCols);
+                    // packed FMAs (fma.rn.f32x2): two columns per instruction -- a 3-register FFMA issues every second
+                    // cycle per scheduler on sm_100, the packed form does two of them in the same slot. k outer, rows
+                    // inner: 16 independent instructions between two updates of one accumulator pair.
+                    float4 x4[kRows];
 #pragma unroll
-                    for (int r = 0; r < kRows; ++r) {
-                        const float4 x4 = *reinterpret_cast<const float4*>(xh + r * width + kk);
-                        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-                        // packed FMA (fma.rn.f32x2): two columns per instruction -- a 3-register FFMA issues every second
-                        // cycle per scheduler on sm_100, the packed form does two of them in the same slot
-                        float2 lo = make_float2(acc[r][0], acc[r][1]), hi = make_float2(acc[r][2], acc[r][3]);
+                    for (int r = 0; r < kRows; ++r) x4[r] = *reinterpret_cast<const float4*>(xh + r * width + kk);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 xx = make_float2(xv[i], xv[i]);
-                            lo = __ffma2_rn(xx, make_float2(w[i].x, w[i].y), lo);
-                            hi = __ffma2_rn(xx, make_float2(w[i].z, w[i].w), hi);
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 wlo = make_float2(w[i].x, w[i].y), whi = make_float2(w[i].z, w[i].w);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) {
+                            const float xs1 = i == 0 ? x4[r].x : i == 1 ? x4[r].y : i == 2 ? x4[r].z : x4[r].w;
+                            const float2 xx = make_float2(xs1, xs1);
+                            const float2 lo = __ffma2_rn(xx, wlo, make_float2(acc[r][0], acc[r][1]));
+                            const float2 hi = __ffma2_rn(xx, whi, make_float2(acc[r][2], acc[r][3]));
+                            acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = hi.x; acc[r][3] = hi.y;
                         }
-                        acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = hi.x; acc[r][3] = hi.y;
                     }
                 }
             } else {                               // K tail (or a tiny K): the groups take every fourth k
@@ -177,48 +181,43 @@ __device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, 
             if (lane == 0) mbar_arrive(empty_bar + 8u * stage);   // this warp is done with the stage
             ++consumed;
         }
-        // dst = ((p3 + p2) + p1) + p0, then bias and activation
+        // dst = ((p3 + p2) + p1) + p0, then bias and activation. Groups 1..3 park their partial sums in a scratch area
+        // ([3][kRows][256] floats behind the row buffers), one barrier, group 0 finishes the chunk.
         const int j = c * kChunkCols + 4 * jq;
-        const bool vec = (j + 3 < N) && ((op.dst_col & 3) == 0);
-        for (int g = kSplitK - 1; g >= 0; --g) {
-            if (h == g && vec) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g == 0 && op.p1 != nullptr) {
-                    b.x = __ldg(op.p1 + j); b.y = __ldg(op.p1 + j + 1); b.z = __ldg(op.p1 + j + 2); b.w = __ldg(op.p1 + j + 3);
-                }
+        if (h != 0) {
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) {
-                    float4* d4 = reinterpret_cast<float4*>(dst + r * width + j);
-                    float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                    if (g != kSplitK - 1) {
-                        const float4 p = *d4;
-                        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-                    }
-                    if (g == 0) {
-                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    }
-                    *d4 = v;
-                }
-            } else if (h == g) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (j + e < N) {
-                        const float b = (g == 0 && op.p1 != nullptr) ? __ldg(op.p1 + j + e) : 0.f;
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) {
-                            float v = acc[r][e];
-                            if (g != kSplitK - 1) v += dst[r * width + j + e];
-                            if (g == 0) {
-                                v += b;
-                                if (relu) v = fmaxf(v, 0.f);
-                            }
-                            dst[r * width + j + e] = v;
-                        }
-                    }
-            }
-            if (g != 0) consumer_sync();
+            for (int r = 0; r < kRows; ++r)
+                *reinterpret_cast<float4*>(scratch + ((h - 1) * kRows + r) * kChunkCols + 4 * jq) =
+                    make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
+        consumer_sync();
+        if (h == 0 && j < N) {
+            float b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) b[e] = (op.p1 != nullptr && j + e < N) ? __ldg(op.p1 + j + e) : 0.f;
+            const bool vec = (j + 3 < N) && ((op.dst_col & 3) == 0);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                float4 v = *reinterpret_cast<const float4*>(scratch + ((kSplitK - 2) * kRows + r) * kChunkCols + 4 * jq);
+#pragma unroll
+                for (int g = kSplitK - 3; g >= 0; --g) {
+                    const float4 p = *reinterpret_cast<const float4*>(scratch + (g * kRows + r) * kChunkCols + 4 * jq);
+                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+                v.x = (v.x + acc[r][0]) + b[0]; v.y = (v.y + acc[r][1]) + b[1];
+                v.z = (v.z + acc[r][2]) + b[2]; v.w = (v.w + acc[r][3]) + b[3];
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (vec) {
+                    *reinterpret_cast<float4*>(dst + r * width + j) = v;
+                } else {
+                    const float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j + e < N) dst[r * width + j + e] = o[e];
+                }
+            }
+        }
+        if (c + 1 < chunks) consumer_sync();       // the next chunk reuses the scratch area
     }
 }
 
@@ -338,6 +337,7 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
     __shared__ __align__(8) unsigned long long bars[2 * kStages];
     float* wtiles = smem;                                  // [kStages][32][256]
     float* bufs = smem + (size_t)kStages * kTileFloats;    // [num_bufs][kRows][width]
+    float* scratch = bufs + (size_t)prog.num_bufs * kRows * prog.width;   // [kSplitK - 1][kRows][256]: Linear k-group partials
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int width = prog.width;
     const long long row0 = (long long)blockIdx.x * kRows;
@@ -455,7 +455,9 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
             }
             break;
         }
-        case RACF_ROWOP_LINEAR: op_linear<kRows>(op, bufs, wtiles, full_bar, empty_bar, width, tid, consumed); break;
+        case RACF_ROWOP_LINEAR:
+            op_linear<kRows>(op, bufs, scratch, wtiles, full_bar, empty_bar, width, tid, consumed);
+            break;
         case RACF_ROWOP_LINEAR_NARROW:
             op_linear_narrow<kRows>(op, bufs, wtiles, full_bar, empty_bar, width, tid, consumed);
             break;
@@ -510,7 +512,8 @@ static int validate(const racf_row_op_t& op, int width, int num_bufs) {
 
 template <int kRows>
 static int launch(const RowProgram& prog, cudaStream_t st) {
-    const size_t smem = ((size_t)kStages * kTileFloats + (size_t)prog.num_bufs * kRows * prog.width) * sizeof(float);
+    const size_t smem = ((size_t)kStages * kTileFloats + (size_t)prog.num_bufs * kRows * prog.width +
+                         (size_t)(kSplitK - 1) * kRows * kChunkCols) * sizeof(float);
     if (smem > 227u * 1024u - 1024u) return RACF_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(row_program_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
