@@ -4,8 +4,8 @@
  * The drop-in boundary for RaCFormer's sampling hot path. Every entry point
  * takes plain device pointers, integer sizes and a CUDA stream; the library
  * never allocates or frees device memory, never synchronises, keeps no
- * mutable global state (one tuning knob, RACF_MSMV_FWD_MODE, is read from the
- * environment once) and returns an int status instead of printing.
+ * mutable global state, reads no environment variable and returns an int
+ * status instead of printing.
  *
  * Reference interfaces replaced (paths relative to the RaCFormer tree):
  *   racf_msmv_forward   <- ms_deformable_im2col_cuda_c{45,2345,23456}
@@ -64,6 +64,17 @@ int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels,
                       const float* loc, const float* weights,
                       int batch, int channels, int num_views, int num_query, int num_point,
                       float* out, racf_stream_t stream);
+
+/*
+ * racf_msmv_forward with an explicit kernel variant (tuning / profiling; results are identical):
+ *   variant  0 : one query per warp, one launch-time CTA per 8 queries
+ *   variant -1 : persistent warps with a 3-stage query pipeline (what racf_msmv_forward uses)
+ *   variant k>0: the persistent kernel, prefetching the first k levels of the next query into L2
+ */
+int racf_msmv_forward_variant(const float* const* feats, const int* hw, int num_levels,
+                              const float* loc, const float* weights,
+                              int batch, int channels, int num_views, int num_query, int num_point,
+                              int variant, float* out, racf_stream_t stream);
 
 /*
  * Forward with the un-packing of sampling_4d's tail fused in (models/sparsebev_sampling.py:128-131): batch is
@@ -365,17 +376,6 @@ typedef struct racf_row_op {
 } racf_row_op_t;
 int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, int rows, int rows_per_cta, int num_bufs,
                              int width, racf_stream_t stream);
-
-/*
- * Measurement aid: random 512-byte coalesced row reads (the request shape of one bilinear cell row) over
- * buf[0 : num_rows * 512 B], total_rows reads, `ilp` independent loads in flight per warp (1,2,4,8,16).
- * Used by tools/gather_ceiling.py to measure the achievable gather bandwidth for HBM- and L2-sized footprints.
- */
-int racf_bench_gather_ceiling(const float* buf, long long num_rows, long long total_rows, int ilp,
-                              float* sink, racf_stream_t stream);
-
-/* Measurement aid: the same for the scatter -- red.global.add.v4.f32 on random 512-byte rows of buf. */
-int racf_bench_scatter_ceiling(float* buf, long long num_rows, long long total_rows, racf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@ SIGNATURES = {
     "racf_status_string": (ctypes.c_char_p, [_i]),
     "racf_msmv_forward": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
                                _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_msmv_forward_variant": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
+                                       _i, _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_msmv_forward_grouped": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p, _c_float_p,
                                        _i, _i, _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_msmv_backward": (_i, [_c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p,
@@ -59,8 +61,6 @@ SIGNATURES = {
     "racf_refine_bbox_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                       _c_float_p, ctypes.c_void_p]),
     "racf_row_program_forward": (_i, [ctypes.c_void_p, _i, _i, _i, _i, _i, ctypes.c_void_p]),
-    "racf_bench_gather_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
-    "racf_bench_scatter_ceiling": (_i, [_c_float_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
 }
 

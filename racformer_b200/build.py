@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.environ.get("RACF_LIB_PATH") or os.path.join(LIB_DIR, "libracformer_ops.so")   # override: tuning experiments
 STAMP = LIB_PATH + ".srchash"
 
-SOURCES = ["msmv.cu", "msda.cu", "points.cu", "layout.cu", "bev_pool.cu", "mixing.cu", "mixing_tc.cu", "linear.cu", "rowops.cu", "sasa.cu", "ceiling.cu"]
+SOURCES = ["msmv.cu", "msda.cu", "points.cu", "layout.cu", "bev_pool.cu", "mixing.cu", "mixing_tc.cu", "linear.cu", "rowops.cu", "sasa.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -36,14 +36,22 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libracformer_ops.so cannot be built")
 
 
-def source_hash():
+COMPILE_FLAGS = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+HEADERS = lambda: sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join(INCLUDE, "racformer_ops.h")]
+
+
+def _digest(paths, extra=""):
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "racformer_ops.h")]
-    for f in files:
+    for f in paths:
         with open(f, "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
-    h.update((" ".join(NVCC_FLAGS) + os.environ.get("RACF_NVCC_DEFINES", "")).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("RACF_NVCC_DEFINES", "") + extra).encode())
     return h.hexdigest()
+
+
+def source_hash():
+    return _digest([os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "racformer_ops.h")])
 
 
 def is_current():
@@ -54,19 +62,47 @@ def is_current():
 
 
 def build(force=False, verbose=False):
-    """Compile the library if sources changed. Returns the path of the .so."""
+    """Compile the library if sources changed. Returns the path of the .so.
+
+    Each .cu is compiled to its own object (in parallel; an object is reused while its source, the shared headers and
+    the flags are unchanged), then linked into one shared library."""
     if not force and is_current():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("RACF_NVCC_DEFINES", "").split() + ["-I", INCLUDE, "-I", CSRC]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    obj_dir = os.path.join(LIB_DIR, "obj" + ("" if LIB_PATH.endswith("libracformer_ops.so") else "_" + os.path.basename(LIB_PATH)))
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    defines = os.environ.get("RACF_NVCC_DEFINES", "").split()
+    headers = HEADERS()
+    jobs, objs = [], []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
+        stamp = obj + ".srchash"
+        digest = _digest([path] + headers)
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+            continue
+        cmd = [nvcc] + COMPILE_FLAGS + defines + ["-I", INCLUDE, "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + [
+            "-c", path, "-o", obj]
+        jobs.append((cmd, stamp, digest, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for cmd, stamp, digest, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            for _c, _s, _d, other in jobs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+        log.append(out)
+        with open(stamp, "w") as fh:
+            fh.write(digest)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC"] + objs + ["-o", LIB_PATH]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log) + res.stdout + res.stderr)
     with open(STAMP, "w") as fh:
         fh.write(source_hash())
     return LIB_PATH

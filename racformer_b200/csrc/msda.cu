@@ -324,7 +324,7 @@ extern "C" int racf_msda_forward(const float* value, const int64_t* spatial_shap
         msda_fwd_d64_kernel<<<(unsigned)((nw + kMsdaWarps - 1) / kMsdaWarps), kMsdaWarps * 32, 0, st>>>(a);
     } else {
         const long long total = (long long)batch * num_query * num_heads * head_dim;
-        msda_fwd_generic_kernel<<<capped_grid(total, 256, 148LL * 64), 256, 0, st>>>(a);
+        msda_fwd_generic_kernel<<<capped_grid(total, 256, 64LL * sm_count()), 256, 0, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
@@ -354,7 +354,7 @@ extern "C" int racf_msda_backward(const float* value, const int64_t* spatial_sha
         e = cudaMemsetAsync(grad_attn, 0, ntap * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
         const long long total = (long long)ntap * head_dim;
-        msda_bwd_generic_kernel<<<capped_grid(total, 256, 148LL * 64), 256, 0, st>>>(a);
+        msda_bwd_generic_kernel<<<capped_grid(total, 256, 64LL * sm_count()), 256, 0, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
@@ -369,7 +369,7 @@ extern "C" int racf_msda_tap_masks(const int64_t* spatial_shapes, const float* l
     a.shapes = spatial_shapes; a.loc = loc; a.mask = tap_mask;
     a.ntaps = (long long)batch * num_query * num_heads * num_levels * num_point;
     a.L = num_levels; a.P = num_point;
-    msda_mask_kernel<<<capped_grid(a.ntaps, 256, 148LL * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    msda_mask_kernel<<<capped_grid(a.ntaps, 256, 32LL * sm_count()), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }
 

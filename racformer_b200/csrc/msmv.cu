@@ -694,20 +694,16 @@ static int check_msmv_common(const float* const* feats, const int* hw, int L, co
     return RACF_OK;
 }
 
-// Forward variant selector (tuning knob, read once): RACF_MSMV_FWD_MODE = 0 one-query-per-warp kernel,
-// -1 persistent kernel without prefetch, k > 0 persistent kernel prefetching the first k levels into L2.
-static int msmv_fwd_mode() {
-    static int mode = [] {
-        const char* e = getenv("RACF_MSMV_FWD_MODE");
-        return e ? atoi(e) : -1;   // measured best on B200 (profiles/r01_msmv_fwd_variants.txt)
-    }();
-    return mode;
-}
+// Forward variants (explicit argument of racf_msmv_forward_variant; the plain entry points use kMsmvFwdDefault):
+// 0 one-query-per-warp kernel, -1 persistent kernel without prefetch (measured best on B200,
+// profiles/r01_msmv_fwd_variants.txt), k > 0 persistent kernel prefetching the first k levels into L2.
+constexpr int kMsmvFwdDefault = -1;
 
 template <int L>
 static int launch_fast(bool backward, const float* grad_out, const float* const* feats, float* const* grad_feats,
                        const int* hw, const float* loc, const float* wts, int B, int C, int N, int Q, int P,
-                       float* out, float* grad_loc, float* grad_wts, cudaStream_t st, int out_T = 0, int out_G = 0) {
+                       float* out, float* grad_loc, float* grad_wts, cudaStream_t st, int out_T = 0, int out_G = 0,
+                       int mode = kMsmvFwdDefault) {
     MsmvArgs<L> a;
     a.out_T = out_T;
     a.out_G = out_G;
@@ -728,9 +724,9 @@ static int launch_fast(bool backward, const float* grad_out, const float* const*
         bool fits32 = true;   // the persistent kernel indexes whole levels (all batch elements) with 32-bit float4 offsets
         for (int l = 0; l < L; ++l)
             if ((long long)B * N * hw[2 * l] * hw[2 * l + 1] * 16 >= (1LL << 31)) fits32 = false;
-        const int mode = msmv_fwd_mode();
         if (mode != 0 && P <= PB && fits32) {
-            const unsigned pgrid = grid < 148u * 2u ? grid : 148u * 2u;   // persistent: 2 CTAs per SM
+            const unsigned cap = 2u * (unsigned)sm_count();               // persistent: 2 CTAs per SM
+            const unsigned pgrid = grid < cap ? grid : cap;
             msmv_fwd_c64_pf_kernel<L><<<pgrid, kMsmvWarps * 32, 0, st>>>(a, mode < 0 ? 0 : (mode > L ? L : mode));
         } else {
             msmv_fwd_c64_kernel<L><<<grid, kMsmvWarps * 32, 0, st>>>(a);
@@ -752,7 +748,8 @@ static int launch_generic(bool backward, const float* grad_out, const float* con
     a.loc = loc; a.wts = wts; a.grad_out = grad_out; a.out = out; a.grad_loc = grad_loc; a.grad_wts = grad_wts;
     a.B = B; a.N = N; a.Q = Q; a.P = P; a.C = C; a.L = L;
     const long long total = (long long)B * Q * C * (backward ? P : 1);
-    const unsigned grid = (unsigned)((total + 255) / 256 > 148LL * 64 ? 148LL * 64 : (total + 255) / 256);
+    const long long gcap = 64LL * sm_count();
+    const unsigned grid = (unsigned)((total + 255) / 256 > gcap ? gcap : (total + 255) / 256);
     if (backward) {
         cudaError_t e = cudaMemsetAsync(grad_loc, 0, sizeof(float) * (size_t)B * Q * P * 3, st);
         if (e != cudaSuccess) return (int)e;
@@ -778,22 +775,29 @@ static bool fast_ok(const float* const* feats, float* const* grad_feats, int L, 
 
 using namespace racf;
 
-extern "C" int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels, const float* loc,
-                                 const float* weights, int batch, int channels, int num_views, int num_query,
-                                 int num_point, float* out, racf_stream_t stream) {
+extern "C" int racf_msmv_forward_variant(const float* const* feats, const int* hw, int num_levels, const float* loc,
+                                         const float* weights, int batch, int channels, int num_views, int num_query,
+                                         int num_point, int variant, float* out, racf_stream_t stream) {
     int rc = check_msmv_common(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query, num_point);
     if (rc != RACF_OK) return rc;
     if (!out) return RACF_ERR_NULL_POINTER;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (fast_ok(feats, nullptr, num_levels, channels, out)) {
         switch (num_levels) {
-            case 2: return launch_fast<2>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
-            case 4: return launch_fast<4>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
-            case 5: return launch_fast<5>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st);
+            case 2: return launch_fast<2>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, 0, 0, variant);
+            case 4: return launch_fast<4>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, 0, 0, variant);
+            case 5: return launch_fast<5>(false, nullptr, feats, nullptr, hw, loc, weights, batch, channels, num_views, num_query, num_point, out, nullptr, nullptr, st, 0, 0, variant);
         }
     }
     return launch_generic(false, nullptr, feats, nullptr, hw, num_levels, loc, weights, batch, channels, num_views,
                           num_query, num_point, out, nullptr, nullptr, st);
+}
+
+extern "C" int racf_msmv_forward(const float* const* feats, const int* hw, int num_levels, const float* loc,
+                                 const float* weights, int batch, int channels, int num_views, int num_query,
+                                 int num_point, float* out, racf_stream_t stream) {
+    return racf_msmv_forward_variant(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query,
+                                     num_point, kMsmvFwdDefault, out, stream);
 }
 
 extern "C" int racf_msmv_forward_grouped(const float* const* feats, const int* hw, int num_levels, const float* loc,
@@ -856,7 +860,8 @@ extern "C" int racf_msmv_tap_masks(const int* hw, int num_levels, const float* l
     a.loc = loc; a.view = view_index; a.mask = tap_mask;
     a.npts = (long long)batch * num_query * num_point;
     a.N = num_views; a.L = num_levels;
-    const unsigned grid = (unsigned)((a.npts + 255) / 256 > 148LL * 32 ? 148LL * 32 : (a.npts + 255) / 256);
+    const long long gcap = 32LL * sm_count();
+    const unsigned grid = (unsigned)((a.npts + 255) / 256 > gcap ? gcap : (a.npts + 255) / 256);
     msmv_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) bev_points_kernel(const BevPointArgs a) {
 
 static unsigned grid_for(long long total) {
     long long g = (total + 255) / 256;
-    const long long cap = 148LL * 16;
+    const long long cap = 16LL * sm_count();
     return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 

@@ -60,6 +60,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
+// Number of SMs of the current device (B200: 148), queried per launch -- a driver attribute read, no synchronisation,
+// legal during stream capture. Grid caps and persistent grids are sized from it instead of a hard-coded 148.
+inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        n = 148;
+    return n;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "racformer_ops.h"
+#include "racformer_tools.h"
 
 namespace racf {
 

@@ -1,4 +1,4 @@
-"""Measure the gather speed of light on this GPU: random coalesced 512-byte row reads (see csrc/ceiling.cu)."""
+"""Measure the gather speed of light on this GPU: random coalesced 512-byte row reads (see tools/csrc/ceiling.cu)."""
 import ctypes
 import json
 import os
@@ -7,9 +7,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from racformer_b200 import _lib  # noqa: E402
+from tools import tools_lib  # noqa: E402
 
-lib = _lib.load()
+lib = tools_lib.load()
 dev = torch.device("cuda", 0)
 sink = torch.zeros(4, device=dev)
 res = []
