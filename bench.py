@@ -9,8 +9,11 @@ data-path collective, so N GPUs run N independent samples per step ("scaling": "
 
 Prints ONE JSON line on rank 0 (keys: see the task contract): value = whole-job samples/s with inputs resident in
 HBM; e2e = the same through the public API with pinned-host inputs copied in and the result read back every step;
-roofline = dominant kernel (MSMV forward), live CUDA-event time vs MEASURED_PEAKS.json; cpu_baseline = the reference's
-PyTorch grid_sample path (oracle port) on the host cores.
+roofline = the step's dominant kernel (timed by event nodes inside the timed region's CUDA graph) against the measured
+peak that bounds it; roofline_sampling_in_step = MSMV / MSDA forward inside the same step; roofline_ops = config 1, the
+four sampling kernels forward + backward at the op shapes with a DRAM-level fraction beside the algorithmic one;
+train / full_inference = configs 4 / 3 as secondary legs; kernels = per-family launch table of the step;
+cpu_baseline = the reference's PyTorch grid_sample path (oracle port) on the host cores.
 
 `--impl reference` times only that CPU path (rank 0 only) on the same workload.
 """
@@ -43,27 +46,6 @@ def load_peaks():
             p = json.load(fh)
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def tensor_roofline(kernels):
-    """Secondary roofline entry for the tcgen05 Linear kernel (the largest kernel of the step after the sampling ops moved
-    out of the way): issued bf16 MMA throughput against the measured dense bf16 peak. It is a fp32-grade GEMM evaluated
-    as six exact bf16 piece products per fp32 product, so the fp32-equivalent rate is one sixth of the issued rate."""
-    k = (kernels or {}).get("linear_parameter_generator")
-    if not k:
-        return None
-    peak, src = 1600.0, "fallback (B200_PROFILING.md)"
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            p = json.load(fh)
-        peak, src = float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", peak))), "measured, sustained (MEASURED_PEAKS.json)"
-    return {"kernel": "linear_bf16x3_kernel (AdaptiveMixing.parameter_generator, %dx%dx%d)" % tuple(k["shape"]), "bound": "tensor",
-            "achieved": k["issued_bf16_mma_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": k["issued_bf16_mma_tflops"] / peak,
-            "fp32_equivalent_tflops": k["fp32_equivalent_tflops"], "bf16_terms_per_product": k["bf16_terms_per_product"],
-            "avg_launch_us": k["avg_us"], "peak_source": src, "timing": "CUDA events, eager pass after the timed region",
-            "note": "limited by L2->SM operand traffic (1.6 GB per launch at 128x128 tiles), not by the tensor pipe: "
-                    "profiles/r01c_linear_ncu_summary.json"}
 
 
 class ClockSampler:
@@ -169,8 +151,11 @@ def _main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("RACF_BENCH_WORKLOAD", "decoder_forward_f8"))
-    ap.add_argument("--cpu-baseline-steps", type=int, default=6)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--legs", default=os.environ.get("RACF_BENCH_LEGS", "ops,train,full_inference"),
+                    help="secondary measurements added to the JSON line (comma list; '' = none): ops = config 1 op "
+                         "microbench (N=1 only), train = config 4 decoder training step, full_inference = config 3")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -212,14 +197,19 @@ def _main():
     barrier()
     total_ms = parallel.max_over_ranks(start.elapsed_time(stop), dev)   # device time, max over ranks
     value = world * args.steps * wl.samples_per_step / (total_ms * 1e-3)
-    # per-kernel CUDA-event timing for the roofline: from event nodes inside the captured graph (they now hold the last
-    # step of the timed region); workloads that do not run as a graph time their launches in an eager pass instead
-    roof = wl.roofline(hbm_peak, peak_src) if getattr(wl, "graph_events", None) else None
-    for _ in range(min(args.steps, 20)):
-        wl.step(time_kernels=True)
+    # per-kernel times: the dominant kernel from event nodes inside the timed region's own graph (they now hold its last
+    # replay); every other kernel family from an instrumented copy of the graph replayed right after (workloads that do
+    # not run as a graph: an eager pass with events around each launch)
+    ms_per_step = total_ms / args.steps
+    if getattr(wl, "use_graph", False):
+        wl.probe_kernels()
+    else:
+        for _ in range(min(args.steps, 20)):
+            wl.step(time_kernels=True)
     barrier()
-    roof = roof or wl.roofline(hbm_peak, peak_src)
+    roof = wl.roofline(hbm_peak, peak_src, step_ms=ms_per_step)
     kernels = wl.kernel_report(hbm_peak)
+    roof_sampling = wl.sampling_rooflines(hbm_peak)
     launches = wl.launches_per_step * args.steps
 
     # ---- end to end: pinned host inputs -> H2D -> ops -> D2H result, every step --------------------------------
@@ -257,20 +247,45 @@ def _main():
                         "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_baseline_steps} steps of: {cpu_wl.reference_sample_description}"}
 
+    wl_metric, wl_unit, wl_config = wl.metric, wl.unit, wl.config()
+    h2d_bytes, d2h_bytes = wl.h2d_bytes_per_step, wl.d2h_bytes_per_step
+
+    # ---- secondary legs (never part of `value`): each one reports {"error": ...} instead of failing the run ------
+    legs = {}
+    want = [x for x in args.legs.split(",") if x]
+    if args.workload != "decoder_forward_f8":
+        want = []
+    del wl
+    torch.cuda.empty_cache()
+    for leg in want:
+        try:
+            if leg == "ops":
+                if world == 1:
+                    legs["roofline_ops"] = workloads.OpMicrobench(dev).run(hbm_peak)
+            elif leg in workloads.LEGS:
+                legs[leg] = workloads.LEGS[leg](dev, rank, world, parallel)
+        except Exception as exc:  # noqa: BLE001
+            import traceback
+            legs[leg if leg != "ops" else "roofline_ops"] = {"error": f"{type(exc).__name__}: {exc}",
+                                                            "trace": traceback.format_exc()[-600:]}
+        barrier()
+        torch.cuda.empty_cache()
+
     if rank == 0:
         line = {
-            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "metric": wl_metric, "value": value, "unit": wl_unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl_config,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": wl.d2h_bytes_per_step, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": wl_unit, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": roof,
-            "roofline_tensor": tensor_roofline(kernels),
+            "roofline_sampling_in_step": roof_sampling,
             "cpu_baseline": cpu_baseline,
             "kernels": kernels,
         }
+        line.update(legs)
     else:
         line = None
     if world > 1:

@@ -146,28 +146,26 @@ class SamplingWorkload:
             ms = [a.elapsed_time(b) for a, b in pairs]
             avg = sum(ms) / len(ms)
             gbs = algo[key] / (avg * 1e-3) / 1e9
-            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "algorithmic_bytes": algo[key], "gbs": gbs,
-                        "frac_of_hbm_peak": gbs / hbm_peak}
+            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "algorithmic_bytes": algo[key], "algorithmic_gbs": gbs,
+                        "frac_algorithmic": gbs / hbm_peak, "total_ms_per_step": sum(ms) / max(1, len(ms) // (
+                            self.layers * (2 if key.startswith("msda") else 1)))}
         return rep
 
-    def roofline(self, hbm_peak, peak_src):
+    def roofline(self, hbm_peak, peak_src, step_ms=None):
         rep = self.kernel_report(hbm_peak)
-        key = "msmv_bwd" if self.backward else "msmv_fwd"
+        key = max(rep, key=lambda k: rep[k]["total_ms_per_step"])
         k = rep[key]
-        traffic = None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernel and shapes
-            import json
-            import os
-            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
-            traffic = json.load(open(path)).get(key)
-        except Exception:
-            traffic = None
-        return {"kernel": key, "bound": "hbm", "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": k["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+        return {"kernel": key, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": None, "frac_algorithmic": k["frac_algorithmic"], "traffic": None, "peak_source": peak_src,
                 "avg_launch_us": k["avg_us"], "algorithmic_bytes_per_launch": k["algorithmic_bytes"],
-                "note": "algorithmic bytes count every corner read of every tap (SURVEY 8d); the pyramid's coarse "
-                        "levels and repeated pixels hit in the 126 MB L2, so achieved can exceed the HBM copy peak; "
-                        "`traffic` is the measured DRAM bytes per launch (ncu)"}
+                "note": "random (unclustered) sampling locations; no ncu capture exists for this workload's inputs, so only "
+                        "the algorithmic rate is given (it charges L2-resident corner reads and can exceed the HBM peak)"}
+
+    def sampling_rooflines(self, hbm_peak):
+        return self.kernel_report(hbm_peak)
+
+    def probe_kernels(self, replays=5):
+        return None
 
     # ------------------------------------------------------------------------------------------------ end to end
     def prepare_host_inputs(self):
@@ -236,12 +234,93 @@ class SamplingWorkload:
         return out
 
 
+class OpMicrobench:
+    """Config 1: msmv_sampling and MSDeformAttn, forward and backward, at the f8 op shapes (MSMV: 32 x 6
+    views x 4 levels x 64 ch, 900 queries x 12 points; MSDA: 8 x 128x128 x 4 heads x 64, 900 x 20 points), for an all-valid
+    and a mixed-validity set of sampling locations, the L2 flushed before every launch. Per kernel: CUDA-event time,
+    algorithmic GB/s (SURVEY 8d byte model evaluated on the actual validity masks) and the DRAM-level fraction
+    `frac_dram` = DRAM bytes of the same launch on the same inputs (ncu --set full, profiles/r02_ncu_traffic.json) /
+    time / measured HBM peak. Backward times include the zero-fill of the value gradient the op needs."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+
+    @staticmethod
+    def _time(fn, iters, warmup, flush):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()                     # 256 MB > 126 MB L2; also keeps the GPU busy while the host enqueues fn
+            torch.cuda._sleep(200000)         # ~0.1 ms spin so the launch below is queued before the events execute
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2], sum(ts) / len(ts)
+
+    def run(self, hbm_peak, iters=8, warmup=2):
+        import json
+        import os
+        from racformer_b200 import wrapper
+        from racformer_b200.multi_scale_deformable_attn_function import ext_module, msda_tap_masks
+        from racformer_b200.roofline import msda_bytes, msmv_bytes
+        from racformer_b200.synthetic import make_op_inputs
+        traffic, src = {}, None
+        try:
+            t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_traffic.json")))
+            traffic, src = t, t.get("_source")
+        except Exception:
+            pass
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        out = {"shapes": "racformer_r50_nuimg_704x256_f8 op shapes, batch 1", "l2_policy": "256 MB memset before every launch",
+               "peak_gbs": hbm_peak, "traffic_source": src, "iters": iters}
+        for case in ("allvalid", "mixed"):
+            d = make_op_inputs(case, self.device)
+            gv = torch.empty_like(d["value"])
+            gl, ga = torch.empty_like(d["mloc"]), torch.empty_like(d["aw"])
+
+            def msda_bwd():
+                gv.zero_()
+                ext_module.ms_deform_attn_backward(d["value"], d["sp"], d["lsi"], d["mloc"], d["aw"], d["mg"], gv, gl, ga,
+                                                   im2col_step=64)
+            ops = {"msmv_fwd": lambda: wrapper.msmv_forward(d["feats"], d["loc"], d["w"]),
+                   "msmv_bwd": lambda: wrapper.msmv_backward(d["g"], d["feats"], d["loc"], d["w"]),
+                   "msda_fwd": lambda: ext_module.ms_deform_attn_forward(d["value"], d["sp"], d["lsi"], d["mloc"], d["aw"],
+                                                                         im2col_step=64),
+                   "msda_bwd": msda_bwd}
+            _, mask = wrapper.msmv_tap_masks(d["level_shapes"], d["loc"], d["num_views"])
+            mmask = msda_tap_masks(d["sp"], d["mloc"])
+            algo = {}
+            algo["msmv_fwd"], algo["msmv_bwd"] = msmv_bytes(mask, C=64, L=4, feat_bytes=sum(f.numel() * 4 for f in d["feats"]))
+            algo["msda_fwd"], algo["msda_bwd"] = msda_bytes(mmask, D=64, value_bytes=d["value"].numel() * 4)
+            res = {}
+            for name, fn in ops.items():
+                med, mean = self._time(fn, iters, warmup, flush)
+                gbs = algo[name] / (med * 1e-3) / 1e9
+                e = {"median_us": 1e3 * med, "mean_us": 1e3 * mean, "algorithmic_bytes": algo[name], "algorithmic_gbs": gbs,
+                     "frac_algorithmic": gbs / hbm_peak}
+                tr = (traffic.get(case) or {}).get(name)
+                if tr:
+                    e.update({"dram_traffic_bytes": tr, "dram_gbs": tr / (med * 1e-3) / 1e9,
+                              "frac_dram": tr / (med * 1e-3) / 1e9 / hbm_peak})
+                res[name] = e
+            out[case] = res
+            del d, gv, gl, ga, ops
+            torch.cuda.empty_cache()
+        return out
+
+
 class DecoderWorkload:
     """Config 2: RaCFormer decoder forward (6 iterations: SASA, radar/LSS BEV deformable attention, MSMV image
     sampling, adaptive mixing, FFN, heads) at 704x256 f8, batch 1, synthetic features, random-init weights."""
     metric = "decoder samples/s (RaCFormer R50 704x256 f8 decoder forward, batch 1)"
     unit = "samples/s"
-    reference_sample_description = ("one of the six decoder iterations per step (1/6 sample) of the same decoder on the "
+    reference_sample_description = ("one full sample per step (all six decoder iterations) of the same decoder on the "
                                     "reference's PyTorch CPU path (grid_sample ops, reference schedule without hoisting), "
                                     "full f8 shapes, all host threads")
 
@@ -259,8 +338,10 @@ class DecoderWorkload:
                         d_region_list=D_REGION_LIST, spatial_shapes=(128, 128), num_cams=num_cams)
         self.num_cams = num_cams
         self.timers = {}
-        self.graph_events = {}
-        self._collect_graph_events = False
+        self.graph_events = {}          # events inside the graph of the timed region (the step's dominant kernel only)
+        self.probe_events = {}          # events inside the instrumented copy of the graph (every kernel family of ours)
+        self._graph_event_keys = None   # kernel families bracketed while capturing (None: capture nothing)
+        self._graph_event_sink = self.graph_events
         self._time_kernels = False
         if self.on_gpu:
             base = SamplingOps()
@@ -300,28 +381,26 @@ class DecoderWorkload:
                 "sharding": "one sample per GPU, no data-path collective",
                 "l2_policy": "inputs larger than L2 (735 MB pyramid + 2x134 MB BEV maps vs 126 MB L2); no flush"}
 
-    def _timed(self, key, fn, args):
-        if self._collect_graph_events and key == "msmv_fwd" and torch.cuda.is_current_stream_capturing():
-            # external events become event-record nodes of the captured graph: every replay re-records them, so after
-            # the timed region they hold the kernel times of its last step
-            a = torch.cuda.Event(enable_timing=True, external=True)
-            b = torch.cuda.Event(enable_timing=True, external=True)
-            a.record()
-            out = fn(*args)
-            b.record()
-            self.graph_events.setdefault(key, []).append((a, b))
-            if self._captured is None:
-                self._captured = (args[1].detach().clone(), [tuple(f.shape[2:4]) for f in args[0]], args[0][0].shape[1])
-            return out
-        if not self._time_kernels:
-            return fn(*args)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = fn(*args)
-        b.record()
-        self.timers.setdefault(key, []).append((a, b))
+    def _capture_msmv_inputs(self, key, args):
         if self._captured is None and key == "msmv_fwd":
             self._captured = (args[1].detach().clone(), [tuple(f.shape[2:4]) for f in args[0]], args[0][0].shape[1])
+
+    def _timed(self, key, fn, args, kw=None):
+        """Bracket one launch with CUDA events. While a graph is being captured the events are external ones: they become
+        event-record nodes of the graph and every replay re-records them, so they hold the times of the last replay."""
+        kw = kw or {}
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing and (self._graph_event_keys is None or key not in self._graph_event_keys):
+            return fn(*args, **kw)
+        if not capturing and not self._time_kernels:
+            return fn(*args, **kw)
+        a = torch.cuda.Event(enable_timing=True, external=capturing)
+        b = torch.cuda.Event(enable_timing=True, external=capturing)
+        a.record()
+        out = fn(*args, **kw)
+        b.record()
+        (self._graph_event_sink if capturing else self.timers).setdefault(key, []).append((a, b))
+        self._capture_msmv_inputs(key, args)
         return out
 
     def reset_kernel_timers(self):
@@ -336,9 +415,10 @@ class DecoderWorkload:
         if self.use_graph and not time_kernels:
             if self._graphed is None:
                 from racformer_b200.graphs import GraphedDecoderForward
-                self._collect_graph_events = True
-                self._graphed = GraphedDecoderForward(self.model, self.inp)   # its static buffers = the resident inputs
-                self._collect_graph_events = False
+                self._graph_event_keys, self._graph_event_sink = {self.DOMINANT}, self.graph_events
+                with self._timed_tensor_core_kernels():
+                    self._graphed = GraphedDecoderForward(self.model, self.inp)   # its static buffers = the resident inputs
+                self._graph_event_keys = None
             return self._graphed()
         self._time_kernels = time_kernels
         if time_kernels:
@@ -349,62 +429,40 @@ class DecoderWorkload:
         self._time_kernels = False
         return out
 
+    DOMINANT = "adaptive_mixing_core"    # largest kernel family of the step (checked against the probe graph's table)
+
     def _timed_tensor_core_kernels(self):
-        """Eager timing pass only: CUDA events around the tcgen05 Linear and AdaptiveMixing launches (module-level
-        functions of racformer_b200.linear / .points, looked up at call time by the decoder)."""
+        """Route the launches of this library's non-sampling kernel families (module-level functions of
+        racformer_b200.linear / .points / .rowops, looked up at call time by the decoder) through self._timed."""
         import contextlib
-        from racformer_b200 import linear, points
+        from racformer_b200 import linear, points, rowops
         wl = self
 
         @contextlib.contextmanager
         def ctx():
             lin, mix = linear.linear_bf16x3, points.adaptive_mixing_core
+            run, sasa = rowops.RowProgram.run, points.sasa_attention
 
             def timed_linear(a3, w3, bias=None, *args, **kw):
                 M, K, N = (a3.rows, a3.K, w3.rows) if isinstance(a3, linear.TiledOperand) else (a3.shape[1], a3.shape[2], w3.shape[1])
-                # prime the caching allocator with the output / split-K workspace sizes so that a cudaMalloc inside the
-                # wrapper (eager pass, pool state left by the graph capture) is not timed as kernel time
-                prime = [torch.empty((M, N), dtype=torch.float32, device=wl.device),
-                         torch.empty((linear.plan(M, N, K)[0], M, N), dtype=torch.float32, device=wl.device)]
-                del prime
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                out = lin(a3, w3, bias, *args, **kw)
-                b.record()
-                name = {(256, 65536): "linear_parameter_generator", (32768, 256): "linear_out_proj"}.get((K, N), "linear_value_proj")
-                wl.timers.setdefault(name, []).append((a, b))
+                if not torch.cuda.is_current_stream_capturing():
+                    # prime the caching allocator with the output / split-K workspace sizes so that a cudaMalloc inside
+                    # the wrapper is not timed as kernel time
+                    prime = [torch.empty((M, N), dtype=torch.float32, device=wl.device),
+                             torch.empty((linear.plan(M, N, K)[0], M, N), dtype=torch.float32, device=wl.device)]
+                    del prime
+                name = {(256, 65536): "linear_parameter_generator", (32768, 256): "linear_out_proj"}.get(
+                    (K, N), "linear_value_proj" if M > 4096 else "linear_sampling_heads")
                 wl.tensor_shapes[name] = (M, N, K)
-                return out
+                return wl._timed(name, lin, (a3, w3, bias) + args, kw)
 
             def timed_mixing(x, params, out_points, *args, **kw):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                out = mix(x, params, out_points, *args, **kw)
-                b.record()
-                wl.timers.setdefault("adaptive_mixing_core", []).append((a, b))
                 wl.tensor_shapes["adaptive_mixing_core"] = tuple(x.shape) + (out_points,)
-                return out
-
-            from racformer_b200 import rowops
-            run, sasa = rowops.RowProgram.run, points.sasa_attention
-
-            def timed_run(program):       # the three row programs of an iteration (csrc/rowops.cu)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                run(program)
-                b.record()
-                wl.timers.setdefault("row_programs", []).append((a, b))
-
-            def timed_sasa(*args, **kw):  # the self-attention core (csrc/sasa.cu)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                out = sasa(*args, **kw)
-                b.record()
-                wl.timers.setdefault("sasa_attention_core", []).append((a, b))
-                return out
+                return wl._timed("adaptive_mixing_core", mix, (x, params, out_points) + args, kw)
 
             linear.linear_bf16x3, points.adaptive_mixing_core = timed_linear, timed_mixing
-            rowops.RowProgram.run, points.sasa_attention = timed_run, timed_sasa
+            rowops.RowProgram.run = lambda program: wl._timed("row_programs", run, (program,))
+            points.sasa_attention = lambda *a, **kw: wl._timed("sasa_attention_core", sasa, a, kw)
             try:
                 yield
             finally:
@@ -412,36 +470,65 @@ class DecoderWorkload:
                 rowops.RowProgram.run, points.sasa_attention = run, sasa
         return ctx()
 
+    ALL_FAMILIES = {"msmv_fwd", "msda_fwd", "adaptive_mixing_core", "linear_parameter_generator", "linear_out_proj",
+                    "linear_value_proj", "linear_sampling_heads", "row_programs", "sasa_attention_core"}
+
+    def probe_kernels(self, replays=5):
+        """Per-kernel device times of the step: an instrumented copy of the step's CUDA graph with an event-record node on
+        either side of every launch of this library's kernel families, replayed `replays` times (the record nodes break the
+        back-to-back launch chain, so this copy is never the one whose step time is reported)."""
+        if not self.use_graph:
+            return
+        if getattr(self, "_probe", None) is None:
+            from racformer_b200.graphs import GraphedDecoderForward
+            self._graph_event_keys, self._graph_event_sink = self.ALL_FAMILIES, self.probe_events
+            with self._timed_tensor_core_kernels():
+                self._probe = GraphedDecoderForward(self.model, self.inp)
+            self._graph_event_keys = None
+        self._probe_ms = {k: [0.0] * len(v) for k, v in self.probe_events.items()}
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(replays):
+            a.record()
+            self._probe()
+            b.record()
+            torch.cuda.synchronize()
+            total += a.elapsed_time(b)
+            for k, pairs in self.probe_events.items():
+                for n, (ea, eb) in enumerate(pairs):
+                    self._probe_ms[k][n] += ea.elapsed_time(eb) / replays
+        self._probe_step_ms = total / replays
+
     def kernel_report(self, hbm_peak):
+        """Per kernel family: launches per step, average launch time, total per step, share of the step. Times come from
+        the instrumented graph (probe_kernels) when the workload runs as a graph, else from the eager timing pass."""
         from racformer_b200 import wrapper
         from racformer_b200.roofline import msmv_bytes
         torch.cuda.synchronize()
-        rep = {}
-        algo = {}
+        rep, algo = {}, {}
         if self._captured is not None:
             loc, hw, n_views = self._captured
             _, mask = wrapper.msmv_tap_masks(hw, loc, n_views)
             feat_bytes = sum(loc.shape[0] * n_views * h * w * 64 * 4 for h, w in hw)
             algo["msmv_fwd"] = msmv_bytes(mask, C=64, L=len(hw), feat_bytes=feat_bytes)[0]
-            rep["msmv_valid_corner_fraction"] = float(((mask.int() >> 1) & 1).float().mean() + ((mask.int() >> 2) & 1).float().mean()
-                                                      + ((mask.int() >> 3) & 1).float().mean() + ((mask.int() >> 4) & 1).float().mean()) / 4
-        sources = dict(self.timers)
-        timing = "CUDA events around each launch in an eager pass after the timed region"
-        if self.graph_events:
-            try:   # MSMV kernel times of the LAST replay of the timed region, from event nodes inside the captured graph
-                for pairs in self.graph_events.values():
-                    pairs[0][0].elapsed_time(pairs[0][1])
-                sources.update(self.graph_events)
-                timing = ("msmv_fwd: event-record nodes inside the CUDA graph (the 6 launches of the last step of the "
-                          "timed region); other kernels: eager pass after the timed region")
-            except Exception:
-                pass
-        rep["kernel_timing"] = timing
-        passes = max(1, len(sources.get("msda_fwd", [])) // (2 * self.layers)) if "msda_fwd" in sources else 1
-        for key, pairs in sources.items():
-            ms = [a.elapsed_time(b) for a, b in pairs]
+            m = mask.int()
+            rep["msmv_valid_corner_fraction"] = float(sum(((m >> k) & 1).float().mean() for k in (1, 2, 3, 4))) / 4
+        if getattr(self, "_probe_ms", None):
+            per_family = {k: (list(v), 1) for k, v in self._probe_ms.items()}
+            rep["kernel_timing"] = ("event-record nodes around every launch inside an instrumented copy of the step's CUDA "
+                                    "graph, mean of 5 replays right after the timed region")
+            rep["instrumented_step_ms"] = self._probe_step_ms
+        else:
+            per_family = {}
+            for key, pairs in self.timers.items():
+                ms = [a.elapsed_time(b) for a, b in pairs]
+                passes = max(1, len(ms) // max(1, {"msda_fwd": 2, "row_programs": 3}.get(key, 1) * self.layers))
+                per_family[key] = (ms, passes)
+            rep["kernel_timing"] = "CUDA events around each launch in an eager pass after the timed region"
+        for key, (ms, passes) in per_family.items():
             avg = sum(ms) / len(ms)
-            if key in self.tensor_shapes:      # tcgen05 kernels (eager pass): fp32-equivalent and issued bf16 MMA throughput
+            e = {"launches_per_step": len(ms) // passes, "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / passes}
+            if key in self.tensor_shapes:      # tcgen05 kernels: fp32-equivalent and issued bf16 MMA throughput
                 shp = self.tensor_shapes[key]
                 if key == "adaptive_mixing_core":
                     qg, p_in, c, p_out = shp
@@ -449,38 +536,95 @@ class DecoderWorkload:
                 else:
                     flops = 2.0 * shp[0] * shp[1] * shp[2]
                 terms = 9 if self.mixing_precision == "bf16x9" and key != "adaptive_mixing_core" else 6
-                rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg, "total_ms_per_step": sum(ms) / passes, "shape": list(shp),
-                            "fp32_equivalent_tflops": flops / (avg * 1e-3) / 1e12,
-                            "issued_bf16_mma_tflops": terms * flops / (avg * 1e-3) / 1e12, "bf16_terms_per_product": terms}
-                continue
-            per_iteration = {"msda_fwd": 2, "row_programs": 3}.get(key, 1)      # launches per decoder iteration
-            rep[key] = {"launches": len(ms), "avg_us": 1e3 * avg,
-                        "total_ms_per_step": sum(ms) / max(1, len(ms) // (self.layers * per_iteration))}
+                e.update({"shape": list(shp), "fp32_equivalent_tflops": flops / (avg * 1e-3) / 1e12,
+                          "issued_bf16_mma_tflops": terms * flops / (avg * 1e-3) / 1e12, "bf16_terms_per_product": terms})
             if key in algo:
                 gbs = algo[key] / (avg * 1e-3) / 1e9
-                rep[key].update({"algorithmic_bytes": algo[key], "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+                e.update({"algorithmic_bytes": algo[key], "algorithmic_gbs": gbs})
+            rep[key] = e
         return rep
 
-    def roofline(self, hbm_peak, peak_src):
-        rep = self.kernel_report(hbm_peak)
-        k = rep["msmv_fwd"]
-        traffic = None
+    def _dominant_times(self):
+        """Launch times of the dominant family from the event nodes of the timed region's own graph (its last replay)."""
+        pairs = self.graph_events.get(self.DOMINANT) or []
         try:
-            import json
-            import os
-            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
-            traffic = json.load(open(path)).get("msmv_fwd")
+            return [a.elapsed_time(b) for a, b in pairs]
+        except Exception:
+            return []
+
+    def roofline(self, hbm_peak, peak_src, step_ms=None):
+        """`roofline` of the JSON line: the step's dominant kernel, timed by event nodes inside the timed region's graph."""
+        import json
+        import os
+        rep = self.kernel_report(hbm_peak)
+        fams = {k: v for k, v in rep.items() if isinstance(v, dict) and "total_ms_per_step" in v}
+        ranked = sorted(fams, key=lambda k: -fams[k]["total_ms_per_step"])
+        key = self.DOMINANT if self.DOMINANT in fams else ranked[0]
+        k = fams[key]
+        live = self._dominant_times() if key == self.DOMINANT else []
+        avg_ms = sum(live) / len(live) if live else k["avg_us"] * 1e-3
+        root = os.path.dirname(os.path.abspath(__file__))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        return {"kernel": "msmv_fwd (timed with its wrapper-side allocation inside the decoder)", "bound": "hbm",
-                "achieved": k.get("gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": k.get("frac_of_hbm_peak"),
-                "traffic": traffic, "peak_source": peak_src, "avg_launch_us": k["avg_us"],
-                "algorithmic_bytes_per_launch": k.get("algorithmic_bytes"),
-                "timing": rep.get("kernel_timing"),
-                "note": "algorithmic bytes count every valid corner read of every tap (SURVEY 8d) of the decoder's actual "
-                        "sampling locations (first iteration); repeated pixels and coarse levels hit the 126 MB L2 so "
-                        "achieved may exceed the HBM copy peak; `traffic` = DRAM bytes/launch from ncu at the op-benchmark "
-                        "shapes (profiles/)"}
+        traffic, traffic_src = None, None
+        try:
+            t = json.load(open(os.path.join(root, "profiles", "r02_ncu_traffic.json")))
+            traffic, traffic_src = t["decoder_forward_f8"].get(key), t.get("_source")
+        except Exception:
+            pass
+        out = {"kernel": key, "dominance": {f: round(fams[f]["total_ms_per_step"], 4) for f in ranked[:6]},
+               "avg_launch_us": 1e3 * avg_ms, "launches_per_step": k["launches_per_step"],
+               "share_of_step": (avg_ms * k["launches_per_step"] / step_ms) if step_ms else None,
+               "timing": ("event-record nodes around the kernel's launches inside the CUDA graph of the timed region (last "
+                          "replay)" if live else rep["kernel_timing"]),
+               "traffic": traffic, "traffic_source": traffic_src}
+        if "shape" in k:     # tensor-core kernel: issued bf16 MMA rate against the measured dense bf16 peak
+            peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1600.0)))
+            flops = k["issued_bf16_mma_tflops"] * k["avg_us"]          # TFLOP/s * us = MFLOP per launch
+            achieved = flops / (1e3 * avg_ms)
+            out.update({"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "peak_source": "measured, sustained (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+                        "flops_per_launch": flops * 1e6, "shape": k["shape"],
+                        "fp32_equivalent_tflops": achieved / k["bf16_terms_per_product"],
+                        "note": "fp32-grade product evaluated as 6 exact bf16 piece products per fp32 product; achieved = "
+                                "issued bf16 MMA flops per launch / launch time"})
+        else:
+            gbs = k.get("algorithmic_bytes", 0) / (avg_ms * 1e-3) / 1e9
+            out.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                        "frac_algorithmic": gbs / hbm_peak,
+                        "frac": (traffic / (avg_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                        "note": "frac = measured DRAM bytes (ncu, same inputs) / launch time / peak; frac_algorithmic charges "
+                                "every corner read, many of which hit the 126 MB L2"})
+        return out
+
+    def sampling_rooflines(self, hbm_peak):
+        """MSMV / MSDA forward inside the decoder step (the decoder's own clustered sampling locations): algorithmic GB/s and
+        the DRAM-level fraction from the ncu capture of the same bench command."""
+        import json
+        import os
+        rep = self.kernel_report(hbm_peak)
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                                                  "r02_ncu_traffic.json")))["decoder_forward_f8"]
+        except Exception:
+            pass
+        out = {}
+        for key in ("msmv_fwd", "msda_fwd"):
+            if key not in rep:
+                continue
+            k = rep[key]
+            e = {"avg_launch_us": k["avg_us"], "launches_per_step": k["launches_per_step"], "total_ms_per_step": k["total_ms_per_step"]}
+            if "algorithmic_gbs" in k:
+                e.update({"algorithmic_bytes": k["algorithmic_bytes"], "algorithmic_gbs": k["algorithmic_gbs"],
+                          "frac_algorithmic": k["algorithmic_gbs"] / hbm_peak})
+            if traffic.get(key):
+                e.update({"dram_traffic_bytes": traffic[key], "frac_dram": traffic[key] / (k["avg_us"] * 1e-6) / 1e9 / hbm_peak})
+            out[key] = e
+        return out
 
     # end to end: pinned host inputs -> H2D -> decoder -> D2H of (cls_scores, bbox_preds)
     def prepare_host_inputs(self):
@@ -527,21 +671,13 @@ class DecoderWorkload:
         torch.cuda.current_stream().synchronize()
 
     # CPU reference leg
-    @property
-    def reference_samples_per_step(self):
-        return 1.0 / 6.0
+    reference_samples_per_step = 1.0
 
     def reference_step(self):
-        """One decoder iteration (a bounded 1/6 sample) on the reference's PyTorch CPU path, reference schedule."""
+        """One full decoder forward (six iterations) on the reference's PyTorch CPU path, reference schedule (the model of
+        a CPU workload is built with hoist_invariants=False and the oracle's port of the grid_sample ops)."""
         assert not self.on_gpu
-        if not hasattr(self, "_ref_model"):
-            from racformer_b200.decoder import RaCFormerTransformer
-            m = RaCFormerTransformer(**dict(self.cfg, num_layers=1), ops=self.model.ops, hoist_invariants=False)
-            m.load_state_dict(self.model.state_dict())
-            self._ref_model = m.eval()
-        with torch.no_grad():
-            return self._ref_model(self.inp["query_bbox"], self.inp["query_feat"], self.inp["mlvl_feats"],
-                                   self.inp["lss_bev"], self.inp["radar_bev"], None, self.inp["img_metas"])
+        return self._forward(self.inp)
 
 
 class DecoderTrainWorkload(DecoderWorkload):
@@ -597,26 +733,56 @@ class DecoderTrainWorkload(DecoderWorkload):
     def config(self):
         c = super().config()
         c.update({"batch_per_gpu": self.batch, "num_query": 900 + self.dn, "mode": "train", "activation_checkpoint": self.checkpoint,
-                  "optimizer": "AdamW", "grad_allreduce": "bucketed NCCL all-reduce of decoder parameter grads (25 MB buckets)",
+                  "optimizer": "AdamW", "grad_allreduce": "bucketed NCCL all-reduce of decoder parameter grads (25 MB buckets, "
+                  "gradients accumulate in place in the buckets, each bucket reduced from a hook inside backward)",
                   "loss": "fixed random projection of cls/bbox outputs (assignment + losses out of scope)"})
         return c
+
+    overlap_allreduce = True
 
     def step(self, time_kernels=False):
         self._time_kernels = time_kernels
         inp = self.inp
         for t in [inp["lss_bev"], inp["radar_bev"]] + inp["mlvl_feats"]:
             t.grad = None
-        self.opt.zero_grad(set_to_none=True)
+        if self.overlap_allreduce:
+            self.reducer.prepare()       # zero the gradient buckets, .grad = views into them, arm the per-bucket hooks
+        else:
+            self.opt.zero_grad(set_to_none=True)
         qf = inp["query_feat"].detach().requires_grad_()
         cls, box = self.model(inp["query_bbox"], qf, inp["mlvl_feats"], inp["lss_bev"], inp["radar_bev"], self.mask,
                               inp["img_metas"])
         loss = (cls * self.proj_cls).mean() + (box * self.proj_box).mean()
-        loss.backward()
-        self.allreduce_bytes = self.reducer.all_reduce()
+        loss.backward()                  # bucket all-reduces start inside backward as their last gradient arrives
+        self.allreduce_bytes = self.reducer.finish() if self.overlap_allreduce else self.reducer.all_reduce()
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 35.0)
         self.opt.step()
         self._time_kernels = False
         return loss.detach()
+
+    def time_allreduce_alone(self, reps=5):
+        """The gradient all-reduce by itself (all buckets, nothing to overlap with): ms and NCCL bus bandwidth."""
+        import torch.distributed as dist
+        if not (dist.is_initialized() and dist.get_world_size() > 1):
+            return None
+        world = dist.get_world_size()
+        flats = self.reducer._buffers()
+        for _ in range(2):
+            for w in [dist.all_reduce(f, async_op=True) for f in flats]:
+                w.wait()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        a.record()
+        for _ in range(reps):
+            for w in [dist.all_reduce(f, async_op=True) for f in flats]:
+                w.wait()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        nbytes = self.reducer.nbytes
+        return {"ms": ms, "bytes": nbytes, "buckets": len(flats), "algbw_gbs": nbytes / ms / 1e6,
+                "busbw_gbs": 2 * (world - 1) / world * nbytes / ms / 1e6}
 
     def prepare_host_inputs(self):
         self._host_feats = [f.detach().cpu().pin_memory() for f in self.inp["mlvl_feats"]]
@@ -634,6 +800,41 @@ class DecoderTrainWorkload(DecoderWorkload):
 
     def reference_step(self):
         raise NotImplementedError("the CPU reference arm is defined for the forward workloads")
+
+
+def train_leg(device, rank, world, parallel, steps=6, warmup=2, name="decoder_train_f8"):
+    """bench.py leg `train`: config 4, the decoder's training step (B = 2 per GPU, 900 + 320 denoising queries, forward +
+    backward + gradient all-reduce over NCCL overlapped with backward + clip + AdamW) on `world` GPUs, weak scaling."""
+    wl = build(name, device, seed=rank)
+    for _ in range(warmup):
+        wl.step()
+    parallel.barrier(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = wl.step()
+    b.record()
+    parallel.barrier(device)
+    ms = parallel.max_over_ranks(a.elapsed_time(b), device) / steps
+    launched = wl.reducer.launched_in_backward
+    alone = wl.time_allreduce_alone()
+    out = {"workload": name, "metric": wl.metric, "value": world * wl.samples_per_step * 1e3 / ms, "unit": "samples/s",
+           "ms_per_step": ms, "n_gpus": world, "steps": steps, "warmup": warmup, "scaling": "weak",
+           "loss_finite": bool(torch.isfinite(loss)), "config": wl.config(),
+           "allreduce": {"bytes_per_step": wl.reducer.nbytes, "buckets": len(wl.reducer.buckets),
+                         "buckets_launched_inside_backward": launched, "alone": alone}}
+    del wl
+    return out
+
+
+def full_inference_leg(device, rank, world, parallel):
+    import bench_full_model
+    return bench_full_model.full_inference_leg(device, rank, world, parallel)
+
+
+# secondary legs of the default bench line: name -> fn(device, rank, world, parallel) -> dict
+LEGS = {"train": train_leg, "full_inference": full_inference_leg,
+        "train_3cam": lambda d, r, w, p: train_leg(d, r, w, p, name="decoder_train_f8_3cam")}
 
 
 def build(name, device, seed=0):

@@ -104,6 +104,20 @@ int racf_msmv_backward(const float* grad_out,
                        int zero_grad_feats, racf_stream_t stream);
 
 /*
+ * Backward of racf_msmv_forward_grouped: grad_out is [B/(T*G), Q, G, T*P, C] (the layout AdaptiveMixing's gradient has),
+ * everything else as racf_msmv_backward. With zero_grad_feats == 0 the feature gradients of several calls accumulate in
+ * one set of buffers -- the decoder's six iterations sample the same pyramid, so their gradients are summed by the
+ * scatter itself instead of by six 1.5 GB additions. Fast path only (RACF_ERR_UNSUPPORTED otherwise).
+ */
+int racf_msmv_backward_grouped(const float* grad_out,
+                               const float* const* feats, const int* hw, int num_levels,
+                               const float* loc, const float* weights,
+                               int batch, int channels, int num_views, int num_query, int num_point,
+                               int num_frames, int num_groups,
+                               float* const* grad_feats, float* grad_loc, float* grad_weights,
+                               int zero_grad_feats, racf_stream_t stream);
+
+/*
  * Debug/verification entry: the integer decisions of the MSMV kernels.
  *   view_index : [B, Q, P]     int32  round(z*(N-1))
  *   tap_mask   : [B, Q, P, L]  uint8  bit0 = tap in range (msmv_sampling_forward.cu:126),
@@ -191,6 +205,24 @@ int racf_to_sampling_layout(const float* in, float* out, int batch, int num_fram
                             int num_groups, int channels, int height, int width, racf_stream_t stream);
 
 /*
+ * Inverse of racf_to_sampling_layout (its backward): in [B*T*G, N, H, W, C] -> out [B, T*N, G*C, H, W], C == 64.
+ */
+int racf_from_sampling_layout(const float* in, float* out, int batch, int num_frames, int num_views,
+                              int num_groups, int channels, int height, int width, racf_stream_t stream);
+
+/*
+ * The same re-layout from fp16 storage, upcast fused into the copy: `in` holds IEEE binary16 values, `out` is the fp32
+ * sampling layout the MSMV kernels read. The reference's image branch runs in fp16 and casts its FPN outputs up to fp32
+ * (models/racformer.py:106 `auto_fp16(apply_to=('img'), out_fp32=True)`), so the result is bit-identical to the
+ * reference's fp32 tensors; what changes is that the 2-byte form is what is transported / re-read.
+ *   channels_last == 0 : in [B, T*N, G*C, H, W] halves
+ *   channels_last != 0 : in [B*T*N, H, W, G*C] halves (the layout cuDNN's fp16 convolutions emit), 16-byte aligned
+ */
+int racf_to_sampling_layout_f16(const void* in, float* out, int batch, int num_frames, int num_views,
+                                int num_groups, int channels, int height, int width, int channels_last,
+                                racf_stream_t stream);
+
+/*
  * "next" row: BEVPoolv2, the reference's other in-tree native op
  * (models/csrc/bev_pool_v2/src/bev_pool.cpp:30-104 -> bev_pool_cuda.cu:125-140). All pointers are device pointers.
  *   depth [b,n,d,h,w] fp32, feat [b,n,h,w,c] fp32, ranks_* int32 [n_points], interval_* int32 [n_intervals].
@@ -235,6 +267,18 @@ int racf_adaptive_mixing_forward_split(const float* x, const float* params, int 
 int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
                                     int out_points, int channels, float eps, float* out, void* out3,
                                     int tiled_groups, racf_stream_t stream);
+
+/*
+ * Backward of the AdaptiveMixing core for training (autograd of models/racformer_transformer.py:592-604): given
+ * grad_out = dL/d(out) [QG, out_points, C] it recomputes the forward from x and params (nothing else is saved) and writes
+ * grad_x [QG, in_points, C] and grad_params [QG, C*C + out_points*in_points] (dL/dM then dL/dS), both fully overwritten.
+ * fp32 FMA on the CUDA cores. C == 64, out_points == 128, in_points % 16 == 0, 16 <= in_points <= 128, 16-byte aligned
+ * pointers (RACF_ERR_UNSUPPORTED otherwise).
+ */
+int racf_adaptive_mixing_backward(const float* x, const float* params, const float* grad_out, int num_query_groups,
+                                  int in_points, int out_points, int channels, float eps, float* grad_x,
+                                  float* grad_params, racf_stream_t stream);
+
 
 /*
  * "next" row: AdaptiveMixing's two large Linear layers (parameter_generator and out_proj,

@@ -24,6 +24,9 @@ SIGNATURES = {
     "racf_msmv_backward": (_i, [_c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p,
                                 _c_float_p, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                 _c_float_p, _i, ctypes.c_void_p]),
+    "racf_msmv_backward_grouped": (_i, [_c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i), _i, _c_float_p,
+                                        _c_float_p, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
+                                        _c_float_p, _i, ctypes.c_void_p]),
     "racf_msmv_tap_masks": (_i, [ctypes.POINTER(_i), _i, _c_float_p, _i, _i, _i, _i, ctypes.c_void_p,
                                  ctypes.c_void_p, ctypes.c_void_p]),
     "racf_msda_forward": (_i, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _c_float_p,
@@ -36,6 +39,8 @@ SIGNATURES = {
     "racf_bev_points_forward": (_i, [_c_float_p] * 6 + [ctypes.POINTER(ctypes.c_double), ctypes.c_float] + [_i] * 6
                                 + [_c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_to_sampling_layout": (_i, [_c_float_p, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
+    "racf_from_sampling_layout": (_i, [_c_float_p, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
+    "racf_to_sampling_layout_f16": (_i, [ctypes.c_void_p, _c_float_p] + [_i] * 8 + [ctypes.c_void_p]),
     "racf_bev_pool_v2_forward": (_i, [_c_float_p] * 7 + [_i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_bev_pool_v2_backward": (_i, [_c_float_p] * 8 + [_i, _i, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_adaptive_mixing_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
@@ -43,6 +48,8 @@ SIGNATURES = {
                                                 _i, ctypes.c_void_p]),
     "racf_adaptive_mixing_tc_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                              ctypes.c_void_p, _i, ctypes.c_void_p]),
+    "racf_adaptive_mixing_backward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
+                                           _c_float_p, ctypes.c_void_p]),
     "racf_linear_tiled_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _i]),
     "racf_split_bf16x3_tiled": (_i, [_c_float_p, ctypes.c_longlong, _i, ctypes.c_void_p, ctypes.c_void_p]),
     "racf_split_bf16x3_tiled_add": (_i, [_c_float_p, ctypes.c_longlong, _i, _c_float_p, ctypes.c_longlong, ctypes.c_void_p,
@@ -97,7 +104,14 @@ def status_string(code):
     return load().racf_status_string(int(code)).decode()
 
 
+class Unsupported(RuntimeError):
+    """RACF_ERR_UNSUPPORTED: the fused variant does not exist for these shapes / alignments. Callers that have another
+    GPU path for the same computation (e.g. the decoder's PyTorch operator chain) catch this and use it."""
+
+
 def check(code, what):
     """Turn a non-zero status into the RuntimeError the reference's ATen asserts would raise."""
+    if code == -6:
+        raise Unsupported(f"{what}: {status_string(code)} (status {code})")
     if code != 0:
         raise RuntimeError(f"{what}: {status_string(code)} (status {code})")

@@ -5,15 +5,21 @@
 // f8 pyramid on B200, 1.7 TB/s). This is the same copy as a tiled transpose: each (b,t,n,g) slab is a [C][H*W] matrix
 // that becomes [H*W][C]; 64 channels x 32 pixels go through shared memory so that both the reads (along pixels) and
 // the writes (along channels, 256 B per pixel) are coalesced.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include "racf_common.cuh"
 #include "racformer_ops.h"
 
 namespace racf {
 
 constexpr int kTilePix = 32;
 
-__global__ void __launch_bounds__(256) to_sampling_layout_c64_kernel(const float* __restrict__ in, float* __restrict__ out,
+__device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_as_float(const __half* p) { return __half2float(__ldg(p)); }
+
+template <typename In>
+__global__ void __launch_bounds__(256) to_sampling_layout_c64_kernel(const In* __restrict__ in, float* __restrict__ out,
                                                                      int T, int N, int G, int HW) {
     __shared__ float tile[64][kTilePix + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -24,11 +30,11 @@ __global__ void __launch_bounds__(256) to_sampling_layout_c64_kernel(const float
     const long long btn = slab / G;
     const int n = (int)(btn % N);
     const long long bt = btn / N;
-    const float* src = in + (btn * G + g) * 64 * (long long)HW;                 // [C][HW]
+    const In* src = in + (btn * G + g) * 64 * (long long)HW;                    // [C][HW]
     float* dst = out + ((bt * G + g) * N + n) * (long long)HW * 64;             // [HW][C]
     const int p = p0 + lane;
 #pragma unroll
-    for (int c = warp; c < 64; c += 8) tile[c][lane] = (p < HW) ? __ldg(src + (long long)c * HW + p) : 0.f;
+    for (int c = warp; c < 64; c += 8) tile[c][lane] = (p < HW) ? load_as_float(src + (long long)c * HW + p) : 0.f;
     __syncthreads();
 #pragma unroll
     for (int q = warp; q < kTilePix; q += 8) {
@@ -37,6 +43,57 @@ __global__ void __launch_bounds__(256) to_sampling_layout_c64_kernel(const float
             row[lane] = tile[lane][q];
             row[lane + 32] = tile[lane + 32][q];
         }
+    }
+}
+
+// The inverse copy (backward of the re-layout): [HW][64] slabs of the sampling layout -> [64][HW] slabs of the FPN layout.
+__global__ void __launch_bounds__(256) from_sampling_layout_c64_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                       int T, int N, int G, int HW) {
+    __shared__ float tile[kTilePix][64 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles = (HW + kTilePix - 1) / kTilePix;
+    const long long slab = blockIdx.x / tiles;            // ((b*T + t)*N + n)*G + g  in FPN order
+    const int p0 = (blockIdx.x % tiles) * kTilePix;
+    const int g = (int)(slab % G);
+    const long long btn = slab / G;
+    const int n = (int)(btn % N);
+    const long long bt = btn / N;
+    const float* src = in + ((bt * G + g) * N + n) * (long long)HW * 64;        // [HW][C]
+    float* dst = out + (btn * G + g) * 64 * (long long)HW;                       // [C][HW]
+#pragma unroll
+    for (int q = warp; q < kTilePix; q += 8) {
+        const bool ok = p0 + q < HW;
+        const float* row = src + (long long)(p0 + q) * 64;
+        tile[q][lane] = ok ? __ldg(row + lane) : 0.f;
+        tile[q][lane + 32] = ok ? __ldg(row + lane + 32) : 0.f;
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+#pragma unroll
+    for (int c = warp; c < 64; c += 8)
+        if (p < HW) dst[(long long)c * HW + p] = tile[lane][c];
+}
+
+// fp16 channel-last input (the FPN's own output format under mixed precision: NHWC halves, models/racformer.py:106
+// `auto_fp16(..., out_fp32=True)` casts exactly these values up) -> the fp32 sampling layout, upcast fused into the copy.
+// in [B*T*N][HW][G*64] halves; one thread moves 8 channels: a 16-byte load, two 16-byte stores.
+__global__ void __launch_bounds__(256) nhwc_half_to_sampling_layout_c64_kernel(const uint4* __restrict__ in, float4* __restrict__ out,
+                                                                               int N, int G, int HW, long long total8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i & 7);
+        long long r = i >> 3;
+        const int g = (int)(r % G);
+        r /= G;
+        const int p = (int)(r % HW);
+        const long long btn = r / HW;
+        const int n = (int)(btn % N);
+        const long long bt = btn / N;
+        const uint4 v = __ldg(in + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+        float4* dst = out + ((((bt * G + g) * N + n) * (long long)HW + p) * 16 + c8 * 2);
+        dst[0] = make_float4(a.x, a.y, b.x, b.y);
+        dst[1] = make_float4(c.x, c.y, d.x, d.y);
     }
 }
 
@@ -88,7 +145,47 @@ extern "C" int racf_to_sampling_layout(const float* in, float* out, int batch, i
     const long long slabs = (long long)batch * num_frames * num_views * num_groups;
     const long long blocks = slabs * ((HW + racf::kTilePix - 1) / racf::kTilePix);
     if (blocks >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
-    racf::to_sampling_layout_c64_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    racf::to_sampling_layout_c64_kernel<float><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         in, out, num_frames, num_views, num_groups, HW);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int racf_from_sampling_layout(const float* in, float* out, int batch, int num_frames, int num_views,
+                                         int num_groups, int channels, int height, int width, racf_stream_t stream) {
+    if (!in || !out) return RACF_ERR_NULL_POINTER;
+    if (batch <= 0 || num_frames <= 0 || num_views <= 0 || num_groups <= 0 || height <= 0 || width <= 0 || channels != 64)
+        return RACF_ERR_BAD_SHAPE;
+    const int HW = height * width;
+    const long long slabs = (long long)batch * num_frames * num_views * num_groups;
+    const long long blocks = slabs * ((HW + racf::kTilePix - 1) / racf::kTilePix);
+    if (blocks >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
+    racf::from_sampling_layout_c64_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, num_frames, num_views, num_groups, HW);
+    return (int)cudaGetLastError();
+}
+
+// fp16 input, fp32 sampling layout out. channels_last == 0: in [B, T*N, G*64, H, W] halves (the tiled transpose above with
+// 2-byte loads); channels_last != 0: in [B*T*N, H, W, G*64] halves (16-byte aligned).
+extern "C" int racf_to_sampling_layout_f16(const void* in, float* out, int batch, int num_frames, int num_views,
+                                           int num_groups, int channels, int height, int width, int channels_last,
+                                           racf_stream_t stream) {
+    if (!in || !out) return RACF_ERR_NULL_POINTER;
+    if (batch <= 0 || num_frames <= 0 || num_views <= 0 || num_groups <= 0 || height <= 0 || width <= 0 || channels != 64)
+        return RACF_ERR_BAD_SHAPE;
+    const int HW = height * width;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (channels_last) {
+        if ((reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return RACF_ERR_UNSUPPORTED;
+        const long long total8 = (long long)batch * num_frames * num_views * HW * num_groups * 8;
+        const long long cap = 32LL * racf::sm_count(), want = (total8 + 255) / 256;
+        racf::nhwc_half_to_sampling_layout_c64_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+            static_cast<const uint4*>(in), reinterpret_cast<float4*>(out), num_views, num_groups, HW, total8);
+        return (int)cudaGetLastError();
+    }
+    const long long slabs = (long long)batch * num_frames * num_views * num_groups;
+    const long long blocks = slabs * ((HW + racf::kTilePix - 1) / racf::kTilePix);
+    if (blocks >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
+    racf::to_sampling_layout_c64_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const __half*>(in), out, num_frames,
+                                                                                  num_views, num_groups, HW);
     return (int)cudaGetLastError();
 }

@@ -438,6 +438,12 @@ __global__ void __launch_bounds__(kMsmvWarps * 32) msmv_bwd_c64_kernel(const Msm
     const float* loc_q = a.loc + bq * a.P * 3;
     const float* wts_q = a.wts + bq * a.P * L;
     const float* go_q = a.grad_out + bq * 64 * a.P;
+    const bool grouped = a.out_T > 0;       // grad_out arrives in the forward_grouped layout [B/(T*G), Q, G, T*P, C]
+    if (grouped) {
+        const int q = (int)(bq % a.Q);
+        const int g = b % a.out_G, t = (b / a.out_G) % a.out_T, bb = b / (a.out_G * a.out_T);
+        go_q = a.grad_out + ((((size_t)bb * a.Q + q) * a.out_G + g) * ((size_t)a.out_T * a.P) + (size_t)t * a.P) * 64;
+    }
     float* gl_q = a.grad_loc + bq * a.P * 3;
     float* gw_q = a.grad_wts + bq * a.P * L;
     const bool vec_load = (a.P % 4) == 0;
@@ -445,9 +451,9 @@ __global__ void __launch_bounds__(kMsmvWarps * 32) msmv_bwd_c64_kernel(const Msm
 
     for (int p0 = 0; p0 < a.P; p0 += kMsmvChunk) {
         __syncwarp();
-        // stage grad_out[b,q,:,p0:p0+4] transposed to [point][channel]
+        // stage grad_out[b,q,:,p0:p0+4] transposed to [point][channel] (the grouped layout is already channel-contiguous)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2 && !grouped; ++h) {
             const int c = lane + 32 * h;
             float g4[4] = {0.f, 0.f, 0.f, 0.f};
             if (vec_load) {
@@ -484,7 +490,12 @@ __global__ void __launch_bounds__(kMsmvWarps * 32) msmv_bwd_c64_kernel(const Msm
 
 #pragma unroll
         for (int pp = 0; pp < kMsmvChunk; ++pp) {
-            const float4 g = *reinterpret_cast<const float4*>(&s_g[warp][pp][4 * j]);
+            float4 g;
+            if (grouped)
+                g = (p0 + pp < a.P) ? __ldg(reinterpret_cast<const float4*>(go_q + (size_t)(p0 + pp) * 64) + j)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            else
+                g = *reinterpret_cast<const float4*>(&s_g[warp][pp][4 * j]);
             float glx = 0.f, gly = 0.f;
             float gw[L];
 #pragma unroll
@@ -844,6 +855,34 @@ extern "C" int racf_msmv_backward(const float* grad_out, const float* const* fea
     }
     return launch_generic(true, grad_out, feats, grad_feats, hw, num_levels, loc, weights, batch, channels, num_views,
                           num_query, num_point, nullptr, grad_loc, grad_weights, st);
+}
+
+extern "C" int racf_msmv_backward_grouped(const float* grad_out, const float* const* feats, const int* hw, int num_levels,
+                                          const float* loc, const float* weights, int batch, int channels, int num_views,
+                                          int num_query, int num_point, int num_frames, int num_groups,
+                                          float* const* grad_feats, float* grad_loc, float* grad_weights,
+                                          int zero_grad_feats, racf_stream_t stream) {
+    int rc = check_msmv_common(feats, hw, num_levels, loc, weights, batch, channels, num_views, num_query, num_point);
+    if (rc != RACF_OK) return rc;
+    if (!grad_out || !grad_feats || !grad_loc || !grad_weights) return RACF_ERR_NULL_POINTER;
+    for (int l = 0; l < num_levels; ++l)
+        if (!grad_feats[l]) return RACF_ERR_NULL_POINTER;
+    if (num_frames <= 0 || num_groups <= 0 || batch % (num_frames * num_groups) != 0) return RACF_ERR_BAD_SHAPE;
+    if (!fast_ok(feats, grad_feats, num_levels, channels, grad_out)) return RACF_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (zero_grad_feats) {
+        for (int l = 0; l < num_levels; ++l) {
+            const size_t n = (size_t)batch * num_views * hw[2 * l] * hw[2 * l + 1] * channels;
+            cudaError_t e = cudaMemsetAsync(grad_feats[l], 0, n * sizeof(float), st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    switch (num_levels) {
+        case 2: return launch_fast<2>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st, num_frames, num_groups);
+        case 4: return launch_fast<4>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st, num_frames, num_groups);
+        case 5: return launch_fast<5>(true, grad_out, feats, grad_feats, hw, loc, weights, batch, channels, num_views, num_query, num_point, nullptr, grad_loc, grad_weights, st, num_frames, num_groups);
+    }
+    return RACF_ERR_UNSUPPORTED;
 }
 
 extern "C" int racf_msmv_tap_masks(const int* hw, int num_levels, const float* loc, int batch, int num_views,

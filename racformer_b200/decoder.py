@@ -126,7 +126,7 @@ def make_sample_points(query_bbox, offset, pc_range):
 
 
 # ---------------------------------------------------------------------------------------------- MSMV call site
-def sampling_4d(ops, sample_points, mlvl_feats, scale_weights, lidar2img, image_h, image_w, eps=1e-5):
+def sampling_4d(ops, sample_points, mlvl_feats, scale_weights, lidar2img, image_h, image_w, eps=1e-5, shared_grads=None):
     """models/sparsebev_sampling.py:28-134 (aggregate=True).
 
     sample_points [B,Q,T,G,P,3]; mlvl_feats[l] [B*T*G,N,H,W,C]; scale_weights [B,Q,G,T,P,L]; lidar2img [B,T*N,4,4].
@@ -157,7 +157,12 @@ def sampling_4d(ops, sample_points, mlvl_feats, scale_weights, lidar2img, image_
 
     w = scale_weights.reshape(B, Q, G, T, P, -1).permute(0, 2, 3, 1, 4, 5).reshape(B * G * T, Q, P, -1)  # quirk (i)
 
-    out = ops.msmv(mlvl_feats, loc.contiguous(), w.contiguous())                     # [B*T*G,Q,C,P]
+    loc, w = loc.contiguous(), w.contiguous()
+    if shared_grads is not None and getattr(ops, "msmv_grouped", None) is not None:
+        from . import training   # training on CUDA: grouped output + grouped grad_out, feature gradients accumulated in place
+        if training.msmv_grouped_supported(mlvl_feats, loc, w):
+            return training.MSMVGrouped.apply(shared_grads.get(mlvl_feats), T, G, loc, w, *mlvl_feats)
+    out = ops.msmv(mlvl_feats, loc, w)                                               # [B*T*G,Q,C,P]
     C = out.shape[2]
     out = out.reshape(B, T, G, Q, C, P).permute(0, 3, 2, 1, 5, 4)                    # [B,Q,G,T,P,C]
     return out.flatten(3, 4)
@@ -326,7 +331,8 @@ class RaCFormerSampling(nn.Module):
                          cart[..., 2:]], dim=-1)
         w = self.scale_weights(query_feat).view(B, Q, G, T, D * Pn, self.num_levels)
         w = torch.softmax(w, dim=-1)
-        return sampling_4d(ops, pts, mlvl_feats, w, meta["lidar2img"], meta["image_h"], meta["image_w"])
+        return sampling_4d(ops, pts, mlvl_feats, w, meta["lidar2img"], meta["image_h"], meta["image_w"],
+                           shared_grads=meta.get("shared_grads"))
 
     def forward(self, ops, query_ray, query_feat, mlvl_feats, meta, d_region=0.1, heads=None):
         fn = lambda qr, qf, *feats: self.inner_forward(ops, qr, qf, list(feats), meta, d_region, heads)
@@ -381,14 +387,14 @@ class BEVSelfAttention(nn.Module):
         v = self.value_proj(bev.reshape(B * T, C, -1).permute(0, 2, 1))
         return v.reshape(B * T, v.shape[1], self.num_heads, -1)
 
-    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False):
+    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False, shared_grads=None):
         B, Q, C = query.shape
         T, M, L, P = self.num_bev_queue, self.num_heads, self.num_levels, self.num_points
         loc = sampling_locations.view(B, Q, M, T, L, P, 2).permute(3, 0, 1, 2, 4, 5, 6).reshape(B * T, Q, M, L, P, 2)
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
-        return self.attend(ops, query, value, loc, aw, spatial_shapes, raw=raw)
+        return self.attend(ops, query, value, loc, aw, spatial_shapes, raw=raw, shared_grads=shared_grads)
 
-    def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None, raw=False):
+    def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None, raw=False, shared_grads=None):
         """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing; queue_logits: bev_queue_weight(query)
         when the caller has already computed it (the decoder layer's stacked head launch). raw: return the MSDA output
         [B*T,Q,C] and the queue logits (None: plain mean) -- the caller's row program (csrc/rowops.cu) does the queue
@@ -397,7 +403,13 @@ class BEVSelfAttention(nn.Module):
         T = self.num_bev_queue
         shapes = _const_long((tuple(int(v) for v in spatial_shapes),), value.device)
         lsi = _const_long((0,), value.device)
-        out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
+        if (shared_grads is not None and value.is_cuda and value.requires_grad and value.dtype == torch.float32
+                and value.is_contiguous()):
+            from . import training   # training on CUDA: the value gradient of all iterations accumulates in one buffer
+            out = training.MSDAShared.apply(shared_grads.get([value]), value, shapes, lsi, loc.contiguous(),
+                                            aw.contiguous(), self.im2col_step)
+        else:
+            out = ops.msda(value, shapes, lsi, loc.contiguous(), aw.contiguous(), self.im2col_step)   # [B*T,Q,C]
         if raw:
             if not self.queue_weight:
                 return out, None
@@ -509,7 +521,8 @@ class BEVSampling(nn.Module):
         self.ray_points_offset = nn.Linear(embed_dims, depth_num)
         self.sampling_offset = nn.Linear(embed_dims, depth_num * num_heads * num_points * 2)
         self.scale_weights = nn.Linear(embed_dims, num_heads * num_levels * depth_num * num_points)
-        self.positional_encoding = LearnedPositionalEncoding(128, row_num_embed=spatial_shapes[1],
+        # the reference hard-codes num_feats=128 (embed_dims 256); embed_dims // 2 is the same there and keeps other widths valid
+        self.positional_encoding = LearnedPositionalEncoding(embed_dims // 2, row_num_embed=spatial_shapes[1],
                                                              col_num_embed=spatial_shapes[0])
         self.attention = BEVSelfAttention(embed_dims, num_heads=4, num_levels=1, num_points=num_points * depth_num,
                                           num_bev_queue=num_frames, queue_weight=True)
@@ -542,7 +555,8 @@ class BEVSampling(nn.Module):
                                                                 self.scale_weights(query_feat), None)
             loc, aw = points.bev_points(query_ray.contiguous(), off, ray, sw, meta["time_diff"],
                                         _depth_base(d_region, D, query_feat.device), pr, d_region, T, M, Pn, D)
-            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw)
+            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw,
+                                         shared_grads=meta.get("shared_grads"))
         query_bbox = theta_d2xy_coods(query_ray)
         offset = self.sampling_offset(query_feat).view(B, Q, M * Pn * D, 2)
         offset = torch.cat([offset, torch.zeros_like(offset[..., 0:1])], dim=-1)
@@ -556,7 +570,7 @@ class BEVSampling(nn.Module):
         loc = theta_d2xy_coods(polar).permute(0, 1, 3, 2, 4, 5).contiguous()               # [B,Q,M,T,P,2]
         w = self.scale_weights(query_feat).view(B, Q, M, 1, self.num_levels, D * Pn)
         w = torch.softmax(w, dim=-1).expand(B, Q, M, T, self.num_levels, D * Pn).contiguous()
-        return self.attention(ops, query_feat, value, loc, w, hw, raw=raw)
+        return self.attention(ops, query_feat, value, loc, w, hw, raw=raw, shared_grads=meta.get("shared_grads"))
 
     def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None, heads=None, raw=False):
         def fn(qr, qf, bev):
@@ -712,6 +726,12 @@ class AdaptiveMixing(nn.Module):
             if core is not None:
                 if split:
                     return query + self._split_linear("out_proj")(x3=core, lead=(B, Q))
+                return query + self._project(core.reshape(B, Q, -1))
+        if self.fused_core and torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32:
+            from . import training   # training on CUDA: one forward and one (recomputing) backward kernel for the core
+            xs, ps = x.reshape(B * Q * G, P, C), params.reshape(B * Q * G, -1)
+            if training.AdaptiveMixingCore.supported(xs, ps, self.out_points):
+                core = training.AdaptiveMixingCore.apply(xs, ps, self.out_points)
                 return query + self._project(core.reshape(B, Q, -1))
         m, s = params.split([self.m_parameters, self.s_parameters], 2)
         m = m.reshape(B * Q, G, self.eff_in_dim, self.eff_out_dim)
@@ -924,8 +944,23 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
 
     def forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer=0,
                 prepared=None):
-        d_region = self.d_region_list[layer]
         rows = self._rows_ok(query_feat)
+        if rows:
+            from ._lib import Unsupported
+            try:
+                return self._forward(ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask,
+                                     meta, layer, prepared, True)
+            except Unsupported:
+                # a fused call-site kernel does not exist for this configuration (embed_dims too wide for the shared-memory
+                # row buffers, parameters that are not 16-byte aligned such as views into a flat buffer, ...): the kernels
+                # are pure functions of their inputs, so the iteration is simply redone with the PyTorch operator chain
+                self.row_programs = False
+        return self._forward(ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta,
+                             layer, prepared, False)
+
+    def _forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer,
+                 prepared, rows):
+        d_region = self.d_region_list[layer]
         attended = self._self_attn_rows(query_bbox, query_feat) if rows and attn_mask is None else None
         if attended is not None:
             query_feat = attended
@@ -969,9 +1004,16 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
     """[B, T*N, G*C, H, W] FPN level -> channel-last sampling layout [B*T*G, N, H, W, C] (racformer_transformer.py:112-124)."""
     B, TN, GC, H, W = feat.shape
     N, T, G, C = num_cams, TN // num_cams, num_groups, GC // num_groups
-    if (C == 64 and feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous()
-            and not (torch.is_grad_enabled() and feat.requires_grad)):
-        from . import points   # tiled-transpose kernel (SURVEY 8f-3); the PyTorch permute below is the autograd path
+    if C == 64 and feat.is_cuda and feat.dtype == torch.float16 and not (torch.is_grad_enabled() and feat.requires_grad):
+        # fp16 FPN outputs (the reference's image branch is fp16 with fp32 outputs, models/racformer.py:106): the cast up
+        # to fp32 is fused into the re-layout kernel; same values as `.float()` followed by the fp32 path
+        from . import points
+        return points.to_sampling_layout_f16(feat, num_cams, num_groups)
+    if C == 64 and feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous():
+        if torch.is_grad_enabled() and feat.requires_grad:
+            from . import training   # the same tiled-transpose kernels in both directions, as an autograd Function
+            return training.SamplingLayout.apply(feat, num_cams, num_groups)
+        from . import points   # tiled-transpose kernel (SURVEY 8f-3); the PyTorch permute below is the generic path
         return points.to_sampling_layout(feat, num_cams, num_groups)
     return feat.reshape(B, T, N, G, C, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, C).contiguous()
 
@@ -986,6 +1028,8 @@ class RaCFormerTransformerDecoder(nn.Module):
             embed_dims, num_frames, num_points, num_points_bev, num_levels, num_classes, code_size,
             img_depth_num=img_depth_num, bev_depth_num=bev_depth_num, num_ray=num_ray, pc_range=pc_range,
             d_region_list=d_region_list, spatial_shapes=spatial_shapes)
+
+    shared_gradients = True     # training on CUDA: see forward()
 
     @torch.no_grad()
     def init_weights(self):
@@ -1005,6 +1049,12 @@ class RaCFormerTransformerDecoder(nn.Module):
         meta = img_metas if isinstance(img_metas, dict) else self.build_meta(img_metas, query_bbox.shape[0], query_bbox.device)
         feats = list(mlvl_feats) if feats_in_sampling_layout else [to_sampling_layout(f, self.num_cams) for f in mlvl_feats]
         layer = self.decoder_layer
+        if (self.shared_gradients and torch.is_grad_enabled() and query_bbox.is_cuda and getattr(ops, "msmv_grouped", None) is not None
+                and not (self.training and layer.sampling.activation_checkpoint)):
+            # training on CUDA: the six iterations scatter their feature / value gradients into shared buffers
+            # (racformer_b200/training.py); not with activation checkpointing, whose recompute re-runs the forwards
+            from . import training
+            meta = dict(meta, shared_grads=training.SharedGrads())
         prepared = None
         if hoist_invariants:
             prepared = (layer.sampling_radar_bev.prepare_value(radar_bev_feats),

@@ -82,10 +82,17 @@ def barrier(device):
 
 
 class GradientAllReducer:
-    """Bucketed average of parameter gradients across ranks (what DDP does for the reference, C2 in SURVEY 2.4).
+    """Bucketed average of parameter gradients across ranks (what DDP does for the reference: train.py:139-140,
+    MMDistributedDataParallel; C2 in SURVEY 2.4) over NCCL / NVLink.
 
-    Gradients are packed into flat fp32 buckets of `bucket_bytes` (default 25 MB, DDP's default) so the NCCL
-    all-reduce is launch-latency-efficient over NVLink/NVSwitch; one async all-reduce per bucket, then unpack.
+    Parameters are packed, in reverse order (~ the order in which backward finishes them), into flat fp32 buckets of
+    `bucket_bytes` (25 MB, DDP's default).
+
+    * `prepare()` + backward + `finish()` -- the overlapped mode: every parameter's `.grad` is a view into its bucket
+      (no pack / unpack copies), autograd accumulates straight into the bucket, and a post-accumulate hook launches the
+      bucket's asynchronous all-reduce the moment its last gradient has been produced, while backward is still running.
+      `finish()` launches what is left (buckets holding parameters that received no gradient), waits, and averages.
+    * `all_reduce()` -- the plain mode for gradients that already exist: pack, reduce, unpack after backward.
     """
 
     def __init__(self, params, bucket_bytes=25 << 20):
@@ -101,35 +108,101 @@ class GradientAllReducer:
         if cur:
             self.buckets.append(cur)
         self._flat = None
+        self._views = None
+        self._bucket_of = {id(p): b for b, bucket in enumerate(self.buckets) for p in bucket}
+        self._hooks, self._armed = [], False
+        self._pending, self._works = [], {}
+        self.launched_in_backward = 0
 
-    def all_reduce(self):
-        if not (dist.is_initialized() and dist.get_world_size() > 1):
+    # ---- shared pieces
+    def _buffers(self):
+        if self._flat is None:
+            self._flat = [torch.zeros(sum(p.numel() for p in b), dtype=b[0].dtype, device=b[0].device) for b in self.buckets]
+            self._views = []
+            for flat, bucket in zip(self._flat, self.buckets):
+                off, views = 0, []
+                for p in bucket:
+                    views.append(flat[off:off + p.numel()].view(p.shape))
+                    off += p.numel()
+                self._views.append(views)
+        return self._flat
+
+    @staticmethod
+    def _distributed():
+        return dist.is_initialized() and dist.get_world_size() > 1
+
+    def _launch(self, b):
+        flat = self._flat[b]
+        if dist.get_backend() == "nccl":
+            self._works[b] = (dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=True), False)
+        else:
+            self._works[b] = (dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), True)
+
+    @property
+    def nbytes(self):
+        return sum(p.numel() * p.element_size() for p in self.params)
+
+    # ---- overlapped mode
+    def prepare(self):
+        """Call before backward: zero the buckets (one memset each), point every `.grad` at its slice, arm the hooks."""
+        flats = self._buffers()
+        for flat in flats:
+            flat.zero_()
+        for bucket, views in zip(self.buckets, self._views):
+            for p, v in zip(bucket, views):
+                p.grad = v
+        if not self._hooks:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._pending = [len(b) for b in self.buckets]
+        self._works, self._armed, self.launched_in_backward = {}, True, 0
+
+    def _on_grad(self, p):
+        if not self._armed:
+            return
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self._distributed():
+            self._launch(b)
+            self.launched_in_backward += 1
+
+    def finish(self):
+        """Call after backward: reduce the buckets whose hooks did not all fire, wait for everything, average.
+        Returns the bytes all-reduced (0 on a single rank)."""
+        self._armed = False
+        if not self._distributed():
             return 0
         world = dist.get_world_size()
-        if self._flat is None:
-            self._flat = [torch.empty(sum(p.numel() for p in b), dtype=b[0].dtype, device=b[0].device) for b in self.buckets]
-        works = []
-        for flat, bucket in zip(self._flat, self.buckets):
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                if p.grad is None:
-                    flat[off:off + n].zero_()
-                else:
-                    flat[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
-        nbytes = 0
-        for work, flat, bucket in zip(works, self._flat, self.buckets):
+        for b in range(len(self.buckets)):
+            if b not in self._works:
+                self._launch(b)
+        for b, (work, divide) in self._works.items():
             work.wait()
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                n = p.numel()
+            if divide:
+                self._flat[b].div_(world)
+        return self.nbytes
+
+    # ---- plain mode
+    def all_reduce(self):
+        if not self._distributed():
+            return 0
+        world = dist.get_world_size()
+        flats = self._buffers()
+        self._works = {}
+        for b, (flat, bucket, views) in enumerate(zip(flats, self.buckets, self._views)):
+            for p, v in zip(bucket, views):
                 if p.grad is None:
-                    p.grad = flat[off:off + n].reshape(p.shape).clone()
-                else:
-                    p.grad.copy_(flat[off:off + n].reshape(p.shape))
-                off += n
-            nbytes += flat.numel() * flat.element_size()
-        return nbytes
+                    v.zero_()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+            self._launch(b)
+        for b, (work, divide) in self._works.items():
+            work.wait()
+            if divide:
+                flats[b].div_(world)
+            for p, v in zip(self.buckets[b], self._views[b]):
+                if p.grad is None:
+                    p.grad = v.clone()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    p.grad.copy_(v)
+        return self.nbytes

@@ -78,6 +78,28 @@ def to_sampling_layout(feat, num_cams, num_groups=4):
     return out
 
 
+def to_sampling_layout_f16(feat, num_cams, num_groups=4):
+    """fp16 features -> fp32 sampling layout [B*T*G, N, H, W, C], the upcast fused into the re-layout (C == 64).
+    feat: [B, T*N, G*C, H, W] halves, either contiguous or channels-last per image (memory [B*T*N, H, W, G*C], what cuDNN's
+    fp16 convolutions produce). Bit-identical to `to_sampling_layout(feat.float(), ...)`."""
+    if not (feat.is_cuda and feat.dtype == torch.float16 and feat.dim() == 5):
+        raise RuntimeError("to_sampling_layout_f16 needs a [B, T*N, G*C, H, W] float16 CUDA tensor")
+    B, TN, GC, H, W = feat.shape
+    T, C = TN // num_cams, GC // num_groups
+    if feat.is_contiguous():
+        nhwc = 0
+    elif feat.permute(0, 1, 3, 4, 2).is_contiguous():
+        nhwc = 1
+    else:
+        feat, nhwc = feat.contiguous(), 0
+    out = torch.empty((B * T * num_groups, num_cams, H, W, C), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        rc = _lib.load().racf_to_sampling_layout_f16(feat.data_ptr(), out.data_ptr(), B, T, num_cams, num_groups, C, H, W,
+                                                     nhwc, _stream(feat.device))
+    _lib.check(rc, "racf_to_sampling_layout_f16")
+    return out
+
+
 def to_channels_last(x, concat_channels=0):
     """x [N, C, H, W] contiguous -> (x as a channels_last tensor, and -- concat_channels > 0 -- a channels_last
     [N, C + concat_channels, H, W] buffer whose first C channels are x; the rest is uninitialised): one tiled transpose
@@ -139,6 +161,22 @@ def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_gro
         return None
     _lib.check(rc, "racf_adaptive_mixing_forward")
     return out
+
+
+def adaptive_mixing_core_backward(x, params, grad_out, out_points, eps=1e-5):
+    """Backward of adaptive_mixing_core: (grad_x like x, grad_params like params); None when the kernel does not exist for
+    the shapes. Recomputes the forward from x and params (csrc/mixing_bwd.cu)."""
+    _check(x, params, grad_out)
+    QG, P_in, C = x.shape
+    if not (C == 64 and out_points == 128 and P_in % 16 == 0 and 16 <= P_in <= 128):
+        return None
+    grad_x, grad_params = torch.empty_like(x), torch.empty_like(params)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_adaptive_mixing_backward(x.data_ptr(), params.data_ptr(), grad_out.data_ptr(), QG, P_in,
+                                                       out_points, C, float(eps), grad_x.data_ptr(), grad_params.data_ptr(),
+                                                       _stream(x.device))
+    _lib.check(rc, "racf_adaptive_mixing_backward")
+    return grad_x, grad_params
 
 
 def refine_bbox(proposal, delta, time_diff, num_ray):

@@ -33,6 +33,7 @@ _transposed = weakref.WeakKeyDictionary()     # module -> (key, W^T); dies with 
 
 
 CHUNK_COLS = 256
+ROW_BUFFER_BYTES = 74 * 1024      # csrc/rowops.cu: 226 KB - 128 KB weight-tile ring - 24 KB reduction scratch
 
 
 def chunked_transpose(w):
@@ -62,7 +63,9 @@ def _ptr(t):
 class RowProgram:
     """Builds and launches one row program over `rows` rows. Buffers are numbered 0..num_bufs-1, `width` floats each."""
 
-    def __init__(self, rows, width, num_bufs=3, rows_per_cta=8, device=None):
+    def __init__(self, rows, width, num_bufs=3, rows_per_cta=None, device=None):
+        if rows_per_cta is None:      # the row buffers share ~74 KB of shared memory with the weight-tile ring
+            rows_per_cta = 8 if int(num_bufs) * int(width) * 8 * 4 <= ROW_BUFFER_BYTES else 4
         self.rows, self.width, self.num_bufs, self.rows_per_cta = int(rows), int(width), int(num_bufs), int(rows_per_cta)
         self.device = device
         self.ops, self._keep = [], []

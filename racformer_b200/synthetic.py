@@ -101,3 +101,29 @@ def make_lss_pool_case(seed, B, N, D, H, W, C, bev=(128, 128), device="cpu"):
     mv = lambda t: t.to(device)
     return dict(depth=mv(depth), feat=mv(feat), ranks_depth=mv(ranks_depth), ranks_feat=mv(ranks_feat),
                 ranks_bev=mv(ranks_bev), starts=mv(starts), lengths=mv(lengths), shape=(B, 1, bev[1], bev[0], C))
+
+
+def make_op_inputs(case="allvalid", device="cuda", num_views=6, batch=1, num_query=900):
+    """Config 1: the op-level inputs of both sampling ops at the f8 shapes, seeded on the device so that
+    bench.py, tools/op_timing.py and the ncu captures under profiles/ all see the same tensors.
+    case "allvalid": MSMV xy ~ U(0,1), MSDA xy ~ U(0,1); "mixed": U(-0.1,1.1) (~75 % of corners valid) / U(-0.05,1.05)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(0)
+    Bp, N, C, Q, P = 32 * batch, num_views, 64, num_query, 12
+    lo, hi = (0.0, 1.0) if case == "allvalid" else (-0.1, 1.1)
+    feats = [torch.randn(Bp, N, h, w, C, device=dev, generator=g) for h, w in F8_LEVEL_SHAPES]
+    xy = torch.rand(Bp, Q, P, 2, device=dev, generator=g) * (hi - lo) + lo
+    view = torch.randint(0, N, (Bp, Q, P, 1), device=dev, generator=g).float() / (N - 1)
+    loc = torch.cat([xy, view], -1).contiguous()
+    w = torch.softmax(torch.randn(Bp, Q, P, 4, device=dev, generator=g), -1).contiguous()
+    grad_out = torch.randn(Bp, Q, C, P, device=dev, generator=g)
+    B, S, M, D, MP = 8 * batch, 128 * 128, 4, 64, 20
+    mlo, mhi = (0.0, 1.0) if case == "allvalid" else (-0.05, 1.05)
+    value = torch.randn(B, S, M, D, device=dev, generator=g)
+    mloc = (torch.rand(B, Q, M, 1, MP, 2, device=dev, generator=g) * (mhi - mlo) + mlo).contiguous()
+    aw = torch.softmax(torch.randn(B, Q, M, 1, MP, device=dev, generator=g), -1).contiguous()
+    mgrad = torch.randn(B, Q, M * D, device=dev, generator=g)
+    sp = torch.tensor([[128, 128]], dtype=torch.long, device=dev)
+    lsi = torch.tensor([0], dtype=torch.long, device=dev)
+    return dict(feats=feats, loc=loc, w=w, g=grad_out, value=value, sp=sp, lsi=lsi, mloc=mloc, aw=aw, mg=mgrad,
+                level_shapes=list(F8_LEVEL_SHAPES), num_views=N)

@@ -1,0 +1,178 @@
+"""Training-mode (autograd) bindings of the fused kernels around the sampling ops.
+
+The reference trains the decoder through `MSMVSamplingC2345` / `MultiScaleDeformableAttnFunction_fp32`
+(models/csrc/wrapper.py:78-142, models/multi_scale_deformable_attn_function.py:90-163) plus PyTorch ops for everything
+between them. The Functions here keep those two contracts (inputs saved with `save_for_backward` only, fp32, gradients
+for features / locations / weights) and add what the B200 path needs to stop re-reading and re-adding 1.5 GB tensors:
+
+* `SamplingLayout`      : channel-last re-layout of an FPN level (racformer_transformer.py:112-124) with the tiled-transpose
+                          kernels in both directions instead of PyTorch's strided copies.
+* `MSMVGrouped`         : msmv_sampling with sampling_4d's un-packing (sparsebev_sampling.py:128-131) fused into the forward
+                          output AND into the backward's grad_out read -- no [B',Q,C,P] <-> [B,Q,G,T*P,C] permute copies.
+* `SharedGrad`          : the six decoder iterations read the SAME pyramid / BEV value maps (one shared layer,
+                          racformer_transformer.py:84-89). Autograd would materialise six zero-filled 1.5 GB feature gradients
+                          and add them pairwise; here every backward scatters into one shared buffer (one zero-fill) and only
+                          the last backward to run hands the buffer to autograd (the others return None = zero).
+* `MSDAShared`          : MultiScaleDeformableAttnFunction_fp32 with the value gradient accumulated the same way.
+
+No CPU fallback; nothing here imports `oracle/`.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib, points, wrapper
+from .multi_scale_deformable_attn_function import ext_module
+
+
+class SharedGrad:
+    """One gradient buffer (or list of buffers) shared by several autograd nodes that consume the same tensors.
+
+    forward of every consumer calls `join()`; backward calls `buffers()` to get the (lazily zero-filled) buffers to
+    accumulate into and then `leave()`, which returns the buffers when this was the last outstanding consumer (they are
+    then returned to autograd as the gradient) and None otherwise (autograd treats None as zero)."""
+
+    def __init__(self, like):
+        self.like = list(like)
+        self.users = 0
+        self.bufs = None
+
+    def join(self):
+        self.users += 1
+
+    def buffers(self):
+        if self.bufs is None:
+            self.bufs = [torch.zeros_like(t) for t in self.like]
+        return self.bufs
+
+    def leave(self):
+        self.users -= 1
+        if self.users == 0:
+            bufs, self.bufs = self.buffers(), None
+            return bufs
+        return None
+
+
+class SharedGrads:
+    """Per-forward registry: tensors (by identity of the first tensor) -> SharedGrad."""
+
+    def __init__(self):
+        self._by_key = {}
+
+    def get(self, tensors):
+        key = tuple(t.data_ptr() for t in tensors)
+        sg = self._by_key.get(key)
+        if sg is None:
+            sg = self._by_key[key] = SharedGrad(tensors)
+        return sg
+
+
+class SamplingLayout(Function):
+    """[B, T*N, G*C, H, W] -> [B*T*G, N, H, W, C] (C == 64), both directions on the tiled-transpose kernels."""
+
+    @staticmethod
+    def forward(ctx, feat, num_cams, num_groups):
+        ctx.shape, ctx.num_cams, ctx.num_groups = feat.shape, num_cams, num_groups
+        return points.to_sampling_layout(feat.contiguous(), num_cams, num_groups)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        B, TN, GC, H, W = ctx.shape
+        N, G = ctx.num_cams, ctx.num_groups
+        grad = grad.contiguous()
+        out = torch.empty(ctx.shape, dtype=torch.float32, device=grad.device)
+        with torch.cuda.device(grad.device):
+            rc = _lib.load().racf_from_sampling_layout(grad.data_ptr(), out.data_ptr(), B, TN // N, N, G, GC // G, H, W,
+                                                       wrapper._stream(grad.device))
+        _lib.check(rc, "racf_from_sampling_layout")
+        return out, None, None
+
+
+class MSMVGrouped(Function):
+    """apply(shared, num_frames, num_groups, loc [B*T*G,Q,P,3], weights [B*T*G,Q,P,L], *feats) -> [B, Q, G, T*P, C].
+    `shared`: a SharedGrad over `feats` or None (then the feature gradients are fresh zero-filled tensors)."""
+
+    @staticmethod
+    def forward(ctx, shared, num_frames, num_groups, loc, weights, *feats):
+        ctx.shared, ctx.T, ctx.G = shared, int(num_frames), int(num_groups)
+        if shared is not None:
+            shared.join()
+        ctx.save_for_backward(loc, weights, *feats)
+        return wrapper.msmv_forward_grouped(feats, loc, weights, num_frames, num_groups)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        loc, weights, *feats = ctx.saved_tensors
+        Bp, N, C, Q, P = wrapper._check_inputs(feats, loc, weights)
+        grad_out = grad_out.contiguous()
+        shared = ctx.shared
+        grad_feats = shared.buffers() if shared is not None else [torch.empty_like(f) for f in feats]
+        grad_loc, grad_w = torch.empty_like(loc), torch.empty_like(weights)
+        with torch.cuda.device(loc.device):
+            rc = _lib.load().racf_msmv_backward_grouped(
+                grad_out.data_ptr(), wrapper._ptr_array(feats), wrapper._hw_array(feats), len(feats), loc.data_ptr(),
+                weights.data_ptr(), Bp, C, N, Q, P, ctx.T, ctx.G, wrapper._ptr_array(grad_feats), grad_loc.data_ptr(),
+                grad_w.data_ptr(), 0 if shared is not None else 1, wrapper._stream(loc.device))
+        _lib.check(rc, "racf_msmv_backward_grouped")
+        if shared is not None:
+            grad_feats = shared.leave() or [None] * len(feats)
+        return (None, None, None, grad_loc, grad_w, *grad_feats)
+
+
+def msmv_grouped_supported(feats, loc, weights):
+    f = feats[0]
+    return (f.is_cuda and f.dtype == torch.float32 and f.shape[-1] == 64 and len(feats) in (2, 4, 5)
+            and all(t.data_ptr() % 16 == 0 for t in feats))
+
+
+class MSDAShared(Function):
+    """MultiScaleDeformableAttnFunction_fp32 whose value gradient accumulates into a SharedGrad (the hoisted value map is
+    read by all six iterations). apply(shared, value, shapes, level_start, loc, attn, im2col_step)."""
+
+    @staticmethod
+    def forward(ctx, shared, value, shapes, lsi, loc, attn, im2col_step):
+        ctx.shared, ctx.im2col_step = shared, im2col_step
+        shared.join()
+        ctx.save_for_backward(value, shapes, lsi, loc, attn)
+        return ext_module.ms_deform_attn_forward(value, shapes, lsi, loc, attn, im2col_step=im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_value = ctx.shared.buffers()[0]
+        grad_loc, grad_attn = torch.empty_like(loc), torch.empty_like(attn)
+        ext_module.ms_deform_attn_backward(value, shapes, lsi, loc, attn, grad_out.contiguous(), grad_value, grad_loc,
+                                           grad_attn, im2col_step=ctx.im2col_step)
+        done = ctx.shared.leave()
+        return None, (done[0] if done is not None else None), None, None, grad_loc, grad_attn, None
+
+
+class AdaptiveMixingCore(Function):
+    """relu(LN(S @ relu(LN(x @ M)))) per (query, group) -- models/racformer_transformer.py:592-604 -- as one forward kernel
+    (tcgen05, csrc/mixing_tc.cu) and one backward kernel that recomputes the forward (csrc/mixing_bwd.cu); only x and the
+    generated parameters are saved. apply(x [QG,P_in,C], params [QG, C*C + P_out*P_in], out_points) -> [QG, P_out, C]."""
+
+    @staticmethod
+    def supported(x, params, out_points):
+        QG, P_in, C = x.shape
+        return (x.is_cuda and x.dtype == torch.float32 and params.dtype == torch.float32 and C == 64 and out_points == 128
+                and P_in % 16 == 0 and 16 <= P_in <= 128)
+
+    @staticmethod
+    def forward(ctx, x, params, out_points):
+        x, params = x.contiguous(), params.contiguous()
+        ctx.out_points = out_points
+        ctx.save_for_backward(x, params)
+        return points.adaptive_mixing_core(x, params, out_points)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, params = ctx.saved_tensors
+        gx, gp = points.adaptive_mixing_core_backward(x, params, grad_out.contiguous(), ctx.out_points)
+        return gx, gp, None

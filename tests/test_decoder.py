@@ -302,3 +302,57 @@ def test_decoder_full_f8_size_cuda_path_vs_cpu_reference_path():
         bad_rows = ((a - b).abs() > 1e-3 + 1e-3 * b.abs()).any(-1)
         assert int(bad_rows.sum()) <= 6, f"f8 {what}: {int(bad_rows.sum())} query rows differ, worst {float((a - b).abs().max()):.3g}"
         assert float((a - b).abs().median()) < 5e-5, what
+
+
+def _forward_both_ways(model, inp):
+    """(fused call-site kernels where they exist, pure PyTorch operator chain) for the same model and inputs."""
+    outs = []
+    for fused in (True, False):
+        layer = model.decoder.decoder_layer
+        layer.row_programs, layer.stacked_heads = fused, fused
+        with torch.no_grad():
+            outs.append(model(inp["query_bbox"], inp["query_feat"], inp["mlvl_feats"], inp["lss_bev"], inp["radar_bev"],
+                              None, inp["img_metas"]))
+    return outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("embed_dims", [384, 512, 768])
+def test_decoder_wide_embed_dims_run_and_match_eager_gpu(embed_dims):
+    """embed_dims beyond the row programs' shared-memory budget at 8 rows per CTA: the default eval() forward
+    must pick a configuration that exists (4 rows per CTA) or fall back to the PyTorch chain -- never raise."""
+    from tests.decoder_cases import SMALL_INPUTS
+    from racformer_b200.synthetic import make_decoder_inputs
+    cfg = dict(SMALL, embed_dims=embed_dims)
+    model = RaCFormerTransformer(**cfg)
+    model.init_weights()
+    fill_parameters_by_name(model, seed=3)
+    model = model.eval().cuda()
+    inp = make_decoder_inputs(seed=5, device="cuda", embed_dims=embed_dims, **SMALL_INPUTS)
+    fused, eager = _forward_both_ways(model, inp)
+    _close(fused[0], eager[0], f"cls, embed_dims={embed_dims}", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+    _close(fused[1], eager[1], f"box, embed_dims={embed_dims}", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+
+
+@pytest.mark.gpu
+def test_decoder_parameters_as_views_into_a_flat_buffer_gpu():
+    """Parameters that are 4-byte-aligned views into one flat buffer (DDP / flat-parameter optimisers): kernels that need
+    16-byte aligned weights must report 'unsupported' and the forward must fall back, with the same result."""
+    model = _my_model().cuda()
+    ref_inp = small_inputs(seed=5, device="cuda")
+    with torch.no_grad():
+        want = model(ref_inp["query_bbox"], ref_inp["query_feat"], ref_inp["mlvl_feats"], ref_inp["lss_bev"],
+                     ref_inp["radar_bev"], None, ref_inp["img_metas"])
+    params = list(model.parameters())
+    flat = torch.empty(sum(p.numel() + 1 for p in params) + 1, device="cuda")
+    off = 1                                           # every view starts at an odd float offset: 4-byte aligned only
+    for p in params:
+        view = flat[off:off + p.numel()].view_as(p)
+        view.copy_(p.data)
+        p.data = view
+        off += p.numel() + 1
+    with torch.no_grad():
+        got = model(ref_inp["query_bbox"], ref_inp["query_feat"], ref_inp["mlvl_feats"], ref_inp["lss_bev"],
+                    ref_inp["radar_bev"], None, ref_inp["img_metas"])
+    _close(got[0], want[0], "cls, flat-buffer parameter views", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+    _close(got[1], want[1], "box, flat-buffer parameter views", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)

@@ -45,6 +45,20 @@ def _worker(rank, world, port, out):
     for p, lst in zip(model.parameters(), gathered):
         torch.testing.assert_close(p.grad, sum(lst) / world)
     assert torch.equal(extra.grad, torch.zeros(5))
+    # overlapped mode: grads are views into the buckets, hooks launch each bucket's all-reduce during backward
+    torch.manual_seed(0)
+    model2 = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4))
+    extra2 = torch.nn.Parameter(torch.zeros(5))
+    red2 = parallel.GradientAllReducer(list(model2.parameters()) + [extra2], bucket_bytes=256)
+    for step in range(2):                                  # second step: buckets are re-zeroed, hooks re-armed
+        red2.prepare()
+        (model2(x).sum() * (step + 1)).backward()
+        assert red2.launched_in_backward >= 1              # at least one bucket went out before backward returned
+        assert red2.finish() == moved
+        for p, q in zip(model2.parameters(), model.parameters()):
+            torch.testing.assert_close(p.grad, q.grad * (step + 1))
+        assert torch.equal(extra2.grad, torch.zeros(5))
+        assert all(p.grad.data_ptr() == v.data_ptr() for b, vs in zip(red2.buckets, red2._views) for p, v in zip(b, vs))
     # sharding: each rank works on its own samples, results gathered only for the check
     a, b = parallel.shard_range(5, rank, world)
     mine = torch.arange(a, b, dtype=torch.float32) * 2

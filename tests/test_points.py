@@ -192,3 +192,21 @@ def test_to_channels_last_is_a_pure_copy(shape, extra):
         assert both.is_contiguous(memory_format=torch.channels_last) and torch.equal(both[:, :shape[1]], x)
     else:
         assert both is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_to_sampling_layout_f16_is_bit_identical_to_upcast_then_relayout(channels_last):
+    """racf_to_sampling_layout_f16: fp16 storage (NCHW or cuDNN's NHWC) -> fp32 sampling layout == .float() + permute."""
+    from racformer_b200 import points
+    from racformer_b200.decoder import to_sampling_layout
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, T, N, G, C, H, W = 2, 3, 3, 4, 64, 5, 11
+    x = torch.randn(B, T * N, G * C, H, W, device="cuda", generator=g).half()
+    if channels_last:
+        x = x.flatten(0, 1).contiguous(memory_format=torch.channels_last).view(B, T * N, G * C, H, W)
+        assert not x.is_contiguous()
+    got = points.to_sampling_layout_f16(x, N, G)
+    want = x.float().reshape(B, T, N, G, C, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, C).contiguous()
+    assert torch.equal(got, want)
+    assert torch.equal(to_sampling_layout(x, N, G), want)

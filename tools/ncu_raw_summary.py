@@ -22,8 +22,12 @@ KEYS = {
     "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors",
     "lts__t_sectors_srcunit_tex_op_write.sum": "l2_write_sectors",
     "lts__t_sectors_srcunit_tex_op_red.sum": "l2_red_sectors",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
+    "launch__shared_mem_per_block_dynamic": "dynamic_smem_bytes",
 }
-UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3}
+UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "Kbyte/block": 1e3, "byte/block": 1.0}
 
 
 def main(path):
@@ -36,7 +40,10 @@ def main(path):
         d = per.setdefault(name, {})
         for k, short in KEYS.items():
             if k in idx and r[idx[k]] not in ("", "n/a"):
-                v = float(r[idx[k]].replace(",", "")) * UNIT_SCALE.get(units[idx[k]], 1.0)
+                try:
+                    v = float(r[idx[k]].replace(",", "")) * UNIT_SCALE.get(units[idx[k]], 1.0)
+                except ValueError:      # "no data"
+                    continue
                 d.setdefault(short, []).append(v)
     out = {}
     for name, d in per.items():

@@ -20,24 +20,9 @@ from racformer_b200.roofline import msda_bytes, msmv_bytes  # noqa: E402
 F8_SHAPES = [(64, 176), (32, 88), (16, 44), (8, 22)]
 
 
-def make_inputs(case, Bp=32, N=6, C=64, Q=900, P=12, dev="cuda"):
-    torch.manual_seed(0)
-    lo, hi = (0.0, 1.0) if case == "allvalid" else (-0.1, 1.1)
-    feats = [torch.randn(Bp, N, h, w, C, device=dev) for h, w in F8_SHAPES]
-    xy = torch.rand(Bp, Q, P, 2, device=dev) * (hi - lo) + lo
-    view = torch.randint(0, N, (Bp, Q, P, 1), device=dev).float() / (N - 1)
-    loc = torch.cat([xy, view], -1).contiguous()
-    w = torch.softmax(torch.randn(Bp, Q, P, 4, device=dev), -1).contiguous()
-    g = torch.randn(Bp, Q, C, P, device=dev)
-    B, S, M, D, MP = 8, 128 * 128, 4, 64, 20
-    mlo, mhi = (0.0, 1.0) if case == "allvalid" else (-0.05, 1.05)
-    value = torch.randn(B, S, M, D, device=dev)
-    mloc = (torch.rand(B, Q, M, 1, MP, 2, device=dev) * (mhi - mlo) + mlo).contiguous()
-    aw = torch.softmax(torch.randn(B, Q, M, 1, MP, device=dev), -1).contiguous()
-    mg = torch.randn(B, Q, M * D, device=dev)
-    sp = torch.tensor([[128, 128]], dtype=torch.long, device=dev)
-    lsi = torch.tensor([0], dtype=torch.long, device=dev)
-    return dict(feats=feats, loc=loc, w=w, g=g, value=value, sp=sp, lsi=lsi, mloc=mloc, aw=aw, mg=mg)
+def make_inputs(case):
+    from racformer_b200.synthetic import make_op_inputs
+    return make_op_inputs(case, "cuda")
 
 
 def time_op(fn, iters, warm, flush):

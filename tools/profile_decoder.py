@@ -35,12 +35,12 @@ for e in prof.key_averages():
 evs = [e for e in prof.events() if e.device_type.name == "CUDA"]
 agg = {}
 for e in evs:
-    k = e.name[:90]
+    k = e.name[:160]
     d = agg.setdefault(k, [0.0, 0])
     d[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
     d[1] += 1
 total = sum(v[0] for v in agg.values())
-top = sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]
+top = sorted(agg.items(), key=lambda kv: -kv[1][0])[:90]
 single = sorted(evs, key=lambda e: -(e.device_time if hasattr(e, "device_time") else e.cuda_time))[:30]
 hist = {"<3us": 0, "3-10us": 0, "10-50us": 0, "50-200us": 0, ">200us": 0}
 hist_ms = dict.fromkeys(hist, 0.0)
