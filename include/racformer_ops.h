@@ -356,6 +356,26 @@ int racf_sasa_attention_forward(const float* qkv, const float* tau, const float*
                                 float* out, racf_stream_t stream);
 
 /*
+ * The same attention core for TRAINING (autograd of models/racformer_transformer.py:296-336 incl. the query-denoising mask
+ * of models/racformer_head.py:205-206 and MultiheadAttention's attention dropout): forward with an optional blocked-pair
+ * mask and dropout, saving only the log-sum-exp of every row; backward recomputes the probabilities.
+ *   blocked_t : uint8 [num_query, num_query] TRANSPOSED (blocked_t[j * Q + i] != 0: query i may not attend to key j) or NULL
+ *   drop_p    : attention dropout probability (0: none); the keep mask is a hash of (seed, batch, head, query, key)
+ *   lse       : [batch, num_heads, num_query]   dsum: same shape, scratch written by the backward
+ *   grad_qkv  : [batch * num_query, 3E] (dq | dk | dv), grad_tau [batch * num_query, num_heads]; both fully overwritten
+ * No gradient flows to query_ray (the reference computes the centre distances under no_grad). head_dim == 32.
+ */
+int racf_sasa_attention_train_forward(const float* qkv, const float* tau, const float* query_ray,
+                                      const uint8_t* blocked_t, const double* pc_range, int batch, int num_query,
+                                      int num_heads, int head_dim, int code_size, float drop_p, unsigned seed,
+                                      float* out, float* lse, racf_stream_t stream);
+int racf_sasa_attention_train_backward(const float* qkv, const float* tau, const float* query_ray,
+                                       const uint8_t* blocked_t, const double* pc_range, int batch, int num_query,
+                                       int num_heads, int head_dim, int code_size, float drop_p, unsigned seed,
+                                       const float* out, const float* lse, const float* grad_out, float* dsum,
+                                       float* grad_qkv, float* grad_tau, racf_stream_t stream);
+
+/*
  * Call-site row: box refinement at the end of a decoder iteration
  * (models/racformer_transformer.py:255-259,264-279 and theta_d2xy_coods, models/bbox/utils.py:82-90) as one launch.
  *   proposal, delta : [batch * num_query, code_size]  the iteration's input rays and the reg branch output
@@ -390,11 +410,27 @@ int racf_refine_bbox_forward(const float* proposal, const float* delta, const fl
  *                  (n * k <= 8192, a multiple of 4, 16-byte aligned)
  *   LAYERNORM      in place over buf[dst][.. dst_col .. dst_col + n), gamma p0 / beta p1 (either may be NULL), eps
  * flags & RACF_ROWOP_RELU applies max(., 0) to the operator's result (LINEAR*, LAYERNORM).
+ * flags & RACF_ROWOP_ACCUM (LOAD, LINEAR): the result is added to buf[dst] instead of replacing it.
+ * Operators of the training programs (the backward pass of a chain is itself a row program over gradient buffers, built by
+ * the host from the forward program; the forward saves what it needs with STORE operators):
+ *   ZERO           buf[dst][.. dst_col + c] = 0
+ *   RELU_MASK      buf[dst][.. dst_col + c] = 0 where the saved forward output p0[row * ld + c] <= 0
+ *   DROPOUT        buf[dst][.. dst_col + c] *= keep / (1 - eps), keep = [hash(aux, row, k + c) >= eps] (eps = drop probability,
+ *                  aux = seed, k = column offset of the stream): the same record replays the same mask in the backward program
+ *   LAYERNORM_BWD  in place on the gradient in buf[dst][.. dst_col .. dst_col + n): p2 = the LayerNorm's saved INPUT rows
+ *                  [rows][ld] (mean / rstd are recomputed), gamma p0 / beta p1, RELU flag = the forward applied max(., 0);
+ *                  adds the column sums of g * xhat to out[c] (d gamma) and of g to out2[c] (d beta) with one atomicAdd per
+ *                  CTA and column (either may be NULL). n <= 384.
+ *   STORE_COLSUM   out[row * ld + c] = buf[src][.. src_col + c] (out may be NULL) and out2[c] += sum over the CTA's rows
+ *                  (atomicAdd; out2 may be NULL): a Linear's output gradient for the weight-gradient GEMM + its bias gradient
+ *   QUEUE_BWD      backward of LOAD_QUEUE: g = buf[src][.. src_col .. + n); out[((b * aux + t) * k + q) * ld + c] = w_t * g[c]
+ *                  (gradient of the queue values) and out2[row * aux + t] = w_t * (d_t - sum_s w_s d_s), d_t = <g, value_t>
+ *                  (gradient of the logits; skipped when p1 == NULL)
  * LOAD_QUEUE needs n, ld, dst_col multiples of 4 and a 16-byte aligned p0.
  * fp32 FMA on the CUDA cores, bias added last. `ops` is a HOST array, copied into the kernel parameters
  * (capture-safe). rows_per_cta is 4 or 8; 128 KB (weight tiles) + (num_bufs * width + 768) * rows_per_cta * 4 bytes <= 226 KB.
  */
-#define RACF_ROW_MAX_OPS        40
+#define RACF_ROW_MAX_OPS        128
 #define RACF_ROW_MAX_QUEUE      16
 #define RACF_ROW_CHUNK_COLS    256
 #define RACF_ROWOP_LOAD          1
@@ -404,7 +440,14 @@ int racf_refine_bbox_forward(const float* proposal, const float* delta, const fl
 #define RACF_ROWOP_LINEAR        5
 #define RACF_ROWOP_LINEAR_NARROW 6
 #define RACF_ROWOP_LAYERNORM     7
+#define RACF_ROWOP_ZERO          8
+#define RACF_ROWOP_RELU_MASK     9
+#define RACF_ROWOP_DROPOUT      10
+#define RACF_ROWOP_LAYERNORM_BWD 11
+#define RACF_ROWOP_STORE_COLSUM 12
+#define RACF_ROWOP_QUEUE_BWD    13
 #define RACF_ROWOP_RELU          1   /* flags bit */
+#define RACF_ROWOP_ACCUM         2   /* flags bit */
 typedef struct racf_row_op {
     int kind;
     int dst, dst_col;
@@ -417,6 +460,8 @@ typedef struct racf_row_op {
     const float* p0;
     const float* p1;
     float* out;
+    const float* p2;
+    float* out2;
 } racf_row_op_t;
 int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, int rows, int rows_per_cta, int num_bufs,
                              int width, racf_stream_t stream);

@@ -65,6 +65,12 @@ SIGNATURES = {
     "racf_chw_to_hwc": (_i, [_c_float_p, _i, _i, _i, _c_float_p, _i, _c_float_p, _i, ctypes.c_void_p]),
     "racf_sasa_attention_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, ctypes.POINTER(ctypes.c_double), _i, _i, _i, _i,
                                          _i, _c_float_p, ctypes.c_void_p]),
+    "racf_sasa_attention_train_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                               _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_uint, _c_float_p, _c_float_p,
+                                               ctypes.c_void_p]),
+    "racf_sasa_attention_train_backward": (_i, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                                                _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_uint, _c_float_p, _c_float_p,
+                                                _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_refine_bbox_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                       _c_float_p, ctypes.c_void_p]),
     "racf_row_program_forward": (_i, [ctypes.c_void_p, _i, _i, _i, _i, _i, ctypes.c_void_p]),

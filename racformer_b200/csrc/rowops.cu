@@ -127,7 +127,7 @@ __device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, 
     const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
     float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
     const int N = op.n, K = op.k;
-    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
+    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0, accum = (op.flags & RACF_ROWOP_ACCUM) != 0;
     const int kblocks = (K + kTileK - 1) / kTileK, chunks = (N + kChunkCols - 1) / kChunkCols;
     for (int c = 0; c < chunks; ++c) {
         float acc[kRows][4];
@@ -208,12 +208,16 @@ __device__ __forceinline__ void op_linear(const racf_row_op_t& op, float* bufs, 
                 v.z = (v.z + acc[r][2]) + b[2]; v.w = (v.w + acc[r][3]) + b[3];
                 if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 if (vec) {
+                    if (accum) {
+                        const float4 o = *reinterpret_cast<const float4*>(dst + r * width + j);
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
                     *reinterpret_cast<float4*>(dst + r * width + j) = v;
                 } else {
                     const float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (j + e < N) dst[r * width + j + e] = o[e];
+                        if (j + e < N) dst[r * width + j + e] = accum ? dst[r * width + j + e] + o[e] : o[e];
                 }
             }
         }
@@ -329,11 +333,81 @@ __device__ __forceinline__ void op_layernorm(const racf_row_op_t& op, float* buf
     }
 }
 
+// Counter-based keep mask of the DROPOUT operator: a murmur-style finaliser of (seed, row, column). The same record in the
+// forward and the backward program regenerates the same mask.
+__device__ __forceinline__ float dropout_scale(unsigned seed, long long row, int col, float p) {
+    unsigned h = seed ^ (unsigned)(row * 0x9E3779B1ull) ^ ((unsigned)col * 0x85EBCA77u);
+    h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    return u >= p ? 1.0f / (1.0f - p) : 0.f;
+}
+
+// Backward of op_layernorm on the gradient held in buf[dst]: one warp per row recomputes mean / rstd / xhat from the saved
+// input row p2, applies the ReLU mask of the forward (y = xhat * gamma + beta > 0), parks g and g * xhat in the scratch area
+// for the gamma / beta gradients and rewrites the gradient in place: rstd * (g' - mean(g') - xhat * mean(g' * xhat)), g' = g * gamma.
+template <int kRows>
+__device__ __forceinline__ void op_layernorm_bwd(const racf_row_op_t& op, float* bufs, float* scratch, int width, long long row0,
+                                                 int valid, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n = op.n;
+    const bool relu = (op.flags & RACF_ROWOP_RELU) != 0;
+    float* part_b = scratch;                      // [kRows][n]: masked g        -> d beta
+    float* part_g = scratch + kRows * n;          // [kRows][n]: masked g * xhat -> d gamma
+    for (int r = warp; r < kRows; r += kRowWarps) {
+        float* g = bufs + ((size_t)op.dst * kRows + r) * width + op.dst_col;
+        if (r >= valid) {
+            for (int c = lane; c < n; c += 32) { part_b[r * n + c] = 0.f; part_g[r * n + c] = 0.f; g[c] = 0.f; }
+            continue;
+        }
+        const float* x = op.p2 + (row0 + r) * op.ld;
+        float s = 0.f;
+        for (int c = lane; c < n; c += 32) s += __ldg(x + c);
+        const float mean = warp_sum(s) / (float)n;
+        float q = 0.f;
+        for (int c = lane; c < n; c += 32) {
+            const float d = __ldg(x + c) - mean;
+            q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)n + op.eps);
+        float m1 = 0.f, m2 = 0.f;
+        for (int c = lane; c < n; c += 32) {
+            const float xh = (__ldg(x + c) - mean) * rstd;
+            const float gam = op.p0 != nullptr ? __ldg(op.p0 + c) : 1.f;
+            float gv = g[c];
+            if (relu) {
+                const float y = xh * gam + (op.p1 != nullptr ? __ldg(op.p1 + c) : 0.f);
+                if (!(y > 0.f)) gv = 0.f;
+            }
+            part_b[r * n + c] = gv;
+            part_g[r * n + c] = gv * xh;
+            const float gp = gv * gam;
+            g[c] = gp;                            // g' parked in place for the second pass
+            m1 += gp;
+            m2 = fmaf(gp, xh, m2);
+        }
+        m1 = warp_sum(m1) / (float)n;
+        m2 = warp_sum(m2) / (float)n;
+        for (int c = lane; c < n; c += 32) {
+            const float xh = (__ldg(x + c) - mean) * rstd;
+            g[c] = rstd * (g[c] - m1 - xh * m2);
+        }
+    }
+    consumer_sync();
+    for (int c = tid; c < n; c += kRowThreads) {
+        float sb = 0.f, sg = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { sb += part_b[r * n + c]; sg += part_g[r * n + c]; }
+        if (op.out != nullptr) atomicAdd(op.out + c, sg);
+        if (op.out2 != nullptr) atomicAdd(op.out2 + c, sb);
+    }
+}
+
 template <int kRows>
 __global__ void __launch_bounds__(kLaunchThreads, 1)
 row_program_kernel(const __grid_constant__ RowProgram prog) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float queue_w[kRows][RACF_ROW_MAX_QUEUE];
+    __shared__ float queue_d[kRows][RACF_ROW_MAX_QUEUE];
     __shared__ __align__(8) unsigned long long bars[2 * kStages];
     float* wtiles = smem;                                  // [kStages][32][256]
     float* bufs = smem + (size_t)kStages * kTileFloats;    // [num_bufs][kRows][width]
@@ -378,19 +452,108 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
         switch (op.kind) {
         case RACF_ROWOP_LOAD: {      // dst[r][c] = p0[row * ld + c]; rows past the end read as 0
             float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            const bool accum = (op.flags & RACF_ROWOP_ACCUM) != 0;
             if (((op.n | op.ld | op.dst_col) & 3) == 0 && (reinterpret_cast<uintptr_t>(op.p0) & 15u) == 0) {
                 const int n4 = op.n >> 2;
                 for (int e = tid; e < kRows * n4; e += kRowThreads) {
                     const int r = e / n4, c = (e - r * n4) * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < valid) v = __ldg(reinterpret_cast<const float4*>(op.p0 + (row0 + r) * op.ld + c));
+                    if (accum) {
+                        const float4 o = *reinterpret_cast<const float4*>(dst + r * width + c);
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
                     *reinterpret_cast<float4*>(dst + r * width + c) = v;
                 }
             } else {
                 for (int e = tid; e < kRows * op.n; e += kRowThreads) {
                     const int r = e / op.n, c = e - r * op.n;
-                    dst[r * width + c] = r < valid ? __ldg(op.p0 + (row0 + r) * op.ld + c) : 0.f;
+                    const float v = r < valid ? __ldg(op.p0 + (row0 + r) * op.ld + c) : 0.f;
+                    dst[r * width + c] = accum ? dst[r * width + c] + v : v;
                 }
+            }
+            break;
+        }
+        case RACF_ROWOP_ZERO: {
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            for (int e = tid; e < kRows * op.n; e += kRowThreads) {
+                const int r = e / op.n, c = e - r * op.n;
+                dst[r * width + c] = 0.f;
+            }
+            break;
+        }
+        case RACF_ROWOP_RELU_MASK: {
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            for (int e = tid; e < kRows * op.n; e += kRowThreads) {
+                const int r = e / op.n, c = e - r * op.n;
+                if (r >= valid || !(__ldg(op.p0 + (row0 + r) * op.ld + c) > 0.f)) dst[r * width + c] = 0.f;
+            }
+            break;
+        }
+        case RACF_ROWOP_DROPOUT: {
+            float* dst = bufs + (size_t)op.dst * kRows * width + op.dst_col;
+            for (int e = tid; e < kRows * op.n; e += kRowThreads) {
+                const int r = e / op.n, c = e - r * op.n;
+                dst[r * width + c] *= dropout_scale((unsigned)op.aux, row0 + r, op.k + c, op.eps);
+            }
+            break;
+        }
+        case RACF_ROWOP_LAYERNORM_BWD:
+            op_layernorm_bwd<kRows>(op, bufs, scratch, width, row0, valid, tid);
+            break;
+        case RACF_ROWOP_STORE_COLSUM: {
+            const float* src = bufs + (size_t)op.src * kRows * width + op.src_col;
+            if (op.out != nullptr)
+                for (int e = tid; e < valid * op.n; e += kRowThreads) {
+                    const int r = e / op.n, c = e - r * op.n;
+                    op.out[(row0 + r) * op.ld + c] = src[r * width + c];
+                }
+            if (op.out2 != nullptr)
+                for (int c = tid; c < op.n; c += kRowThreads) {
+                    float sum = 0.f;
+                    for (int r = 0; r < valid; ++r) sum += src[r * width + c];
+                    atomicAdd(op.out2 + c, sum);
+                }
+            break;
+        }
+        case RACF_ROWOP_QUEUE_BWD: {   // one warp per row: d_t = <g, value_t>, grad value_t = w_t g, grad logit_t = w_t (d_t - sum_s w_s d_s)
+            const int T = op.aux, Q = op.k;
+            for (int r = warp; r < valid; r += kRowWarps) {
+                const float* g = bufs + ((size_t)op.src * kRows + r) * width + op.src_col;
+                const long long row = row0 + r;
+                const long long b = row / Q, q = row - b * Q;
+                float* w = queue_w[r];            // this warp's row: softmax weights, then the dots
+                float* d = queue_d[r];
+                if (lane == 0) {
+                    if (op.p1 != nullptr) {
+                        const float* lg = op.p1 + row * T;
+                        float m = -INFINITY;
+                        for (int t = 0; t < T; ++t) m = fmaxf(m, __ldg(lg + t));
+                        float den = 0.f;
+                        for (int t = 0; t < T; ++t) den += expf(__ldg(lg + t) - m);
+                        for (int t = 0; t < T; ++t) w[t] = expf(__ldg(lg + t) - m) / den;
+                    } else {
+                        for (int t = 0; t < T; ++t) w[t] = 1.f / (float)T;
+                    }
+                }
+                __syncwarp();
+                float dot_all = 0.f;
+                for (int t = 0; t < T; ++t) {
+                    const long long off = ((b * T + t) * Q + q) * op.ld;
+                    const float wt = w[t];
+                    float acc = 0.f;
+                    for (int c = lane; c < op.n; c += 32) {
+                        const float gv = g[c];
+                        acc = fmaf(gv, __ldg(op.p0 + off + c), acc);
+                        if (op.out != nullptr) op.out[off + c] = wt * gv;
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) d[t] = acc;
+                    dot_all = fmaf(wt, acc, dot_all);
+                }
+                __syncwarp();
+                if (op.out2 != nullptr && op.p1 != nullptr)
+                    for (int t = lane; t < T; t += 32) op.out2[row * T + t] = w[t] * (d[t] - dot_all);
             }
             break;
         }
@@ -470,9 +633,10 @@ row_program_kernel(const __grid_constant__ RowProgram prog) {
 
 static int validate(const racf_row_op_t& op, int width, int num_bufs) {
     const bool reads_buf = op.kind == RACF_ROWOP_STORE || op.kind == RACF_ROWOP_ADD || op.kind == RACF_ROWOP_LINEAR ||
-                           op.kind == RACF_ROWOP_LINEAR_NARROW;
-    const bool writes_buf = op.kind != RACF_ROWOP_STORE;
-    if (op.kind < RACF_ROWOP_LOAD || op.kind > RACF_ROWOP_LAYERNORM) return RACF_ERR_UNSUPPORTED;
+                           op.kind == RACF_ROWOP_LINEAR_NARROW || op.kind == RACF_ROWOP_STORE_COLSUM ||
+                           op.kind == RACF_ROWOP_QUEUE_BWD;
+    const bool writes_buf = op.kind != RACF_ROWOP_STORE && op.kind != RACF_ROWOP_STORE_COLSUM && op.kind != RACF_ROWOP_QUEUE_BWD;
+    if (op.kind < RACF_ROWOP_LOAD || op.kind > RACF_ROWOP_QUEUE_BWD) return RACF_ERR_UNSUPPORTED;
     if (op.n <= 0) return RACF_ERR_BAD_SHAPE;
     const bool is_linear = op.kind == RACF_ROWOP_LINEAR || op.kind == RACF_ROWOP_LINEAR_NARROW;
     const int in_w = is_linear ? op.k : op.n;
@@ -492,6 +656,26 @@ static int validate(const racf_row_op_t& op, int width, int num_bufs) {
     case RACF_ROWOP_STORE:
         if (!op.out) return RACF_ERR_NULL_POINTER;
         if (op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_STORE_COLSUM:
+        if (!op.out && !op.out2) return RACF_ERR_NULL_POINTER;
+        if (op.out && op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_RELU_MASK:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_DROPOUT:
+        if (!(op.eps >= 0.f && op.eps < 1.f)) return RACF_ERR_BAD_SHAPE;
+        break;
+    case RACF_ROWOP_LAYERNORM_BWD:
+        if (!op.p2) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n) return RACF_ERR_BAD_SHAPE;
+        if (op.n > 384) return RACF_ERR_UNSUPPORTED;                // two [rows_per_cta][n] partials in the scratch area
+        break;
+    case RACF_ROWOP_QUEUE_BWD:
+        if (!op.p0) return RACF_ERR_NULL_POINTER;
+        if (op.ld < op.n || op.aux <= 0 || op.aux > RACF_ROW_MAX_QUEUE || op.k <= 0) return RACF_ERR_BAD_SHAPE;
         break;
     case RACF_ROWOP_LINEAR:
         if (!op.p0) return RACF_ERR_NULL_POINTER;

@@ -259,6 +259,28 @@ class ScaleAdaptiveSelfAttention(nn.Module):
     def forward(self, query_bbox, query_feat, pre_attn_mask=None):
         return _maybe_checkpoint(self, lambda qb, qf: self.inner_forward(qb, qf, pre_attn_mask), query_bbox, query_feat)
 
+    fused_training_core = True
+
+    def attention_core(self, query_bbox, qkv, tau, pre_attn_mask, num_heads, dropout_p):
+        """softmax(q k^T / sqrt(d) - tau_i |c_i - c_j| [blocked pairs: -inf]) v for projected qkv [B,Q,3E], tau [B,Q,H] ->
+        [B,Q,E]: the attention between in_proj and out_proj of inner_forward (racformer_transformer.py:296-336), with
+        autograd."""
+        B, Q, E3 = qkv.shape
+        E = E3 // 3
+        if self.fused_training_core and qkv.is_cuda and E == num_heads * 32 and query_bbox.shape[-1] >= 2:
+            from . import training   # csrc/sasa_train.cu: no [B,H,Q,Q] tensor in forward or backward
+            if training.SasaAttention.supported(qkv, tau, num_heads):
+                self._drop_counter = getattr(self, "_drop_counter", 0) + 1
+                seed = (torch.initial_seed() * 40503 + self._drop_counter * 2654435761) & 0xffffffff
+                return training.SasaAttention.apply(qkv, tau, query_bbox, pre_attn_mask, self.pc_range, num_heads, dropout_p, seed)
+        dist = self.calc_bbox_dists(theta_d2xy_coods(query_bbox))                         # [B,Q,Q], no grad
+        mask = dist[:, None, :, :] * tau.permute(0, 2, 1)[..., None]                      # [B,H,Q,Q]
+        if pre_attn_mask is not None:
+            mask = mask.masked_fill(pre_attn_mask[None, None], float("-inf"))
+        q, k, v = (t.reshape(B, Q, num_heads, E // num_heads).transpose(1, 2) for t in qkv.split(E, dim=-1))
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=dropout_p)
+        return out.transpose(1, 2).reshape(B, Q, E)
+
 
 def _use_fused_points(module, *tensors):
     """The fused CUDA point kernels are forward-only: use them when autograd is off and everything lives on a GPU."""
@@ -384,7 +406,15 @@ class BEVSelfAttention(nn.Module):
             return v.reshape(B * T, x3.rows // (B * T), self.num_heads, -1)
         if pos is not None:
             bev = bev + pos.view(1, 1, C, *bev.shape[3:])
-        v = self.value_proj(bev.reshape(B * T, C, -1).permute(0, 2, 1))
+        pixels = bev.reshape(B * T, C, -1).permute(0, 2, 1)
+        if (self.tensor_core_value_proj and torch.is_grad_enabled() and bev.is_cuda and bev.dtype == torch.float32
+                and C % 8 == 0 and pixels.shape[1] % 8 == 0):
+            from . import linear   # training on CUDA: forward, input and weight gradient on the tcgen05 Linear kernel
+            if getattr(self, "_train_value_proj", None) is None:
+                self._train_value_proj = linear.TrainableSplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
+            v = self._train_value_proj(pixels)
+        else:
+            v = self.value_proj(pixels)
         return v.reshape(B * T, v.shape[1], self.num_heads, -1)
 
     def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False, shared_grads=None):
@@ -839,6 +869,56 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         return (self.row_programs and not torch.is_grad_enabled() and not self.training and query_feat.is_cuda
                 and query_feat.dtype == torch.float32 and self.embed_dims % 4 == 0)
 
+    train_row_programs = True     # training on CUDA: the same chains with autograd (racformer_b200/rowtrain.py)
+
+    def _train_rows_ok(self, query_feat):
+        return (self.train_row_programs and torch.is_grad_enabled() and query_feat.is_cuda and query_feat.dtype == torch.float32
+                and self.embed_dims % 4 == 0 and self.embed_dims <= 384
+                and not (self.training and self.self_attn.activation_checkpoint))
+
+    def _seed(self):
+        """Seeds of the dropout masks of the row chains: a per-layer counter mixed with torch's seed (reproducible runs)."""
+        self._drop_counter = getattr(self, "_drop_counter", 0) + 1
+        return (torch.initial_seed() * 2654435761 + self._drop_counter * 40503) & 0x7fffffff
+
+    def _self_attn_rows_train(self, query_bbox, query_feat, attn_mask):
+        """Training counterpart of _self_attn_rows: two row chains with autograd around the attention core (the
+        scale-adaptive mask + attention of ScaleAdaptiveSelfAttention, racformer_transformer.py:296-336)."""
+        from . import rowtrain
+        mha = self.self_attn.attention.attn
+        E, H = self.embed_dims, mha.num_heads
+        if not mha._qkv_same_embed_dim or mha.in_proj_bias is None or mha.bias_k is not None or mha.add_zero_attn:
+            return None
+        B, Q, _ = query_feat.shape
+        pe = self.position_encoder
+        query_bbox = query_bbox.contiguous()
+        p = rowtrain.RowChain(B * Q, width=3 * E, num_bufs=3)
+        p.load(0, query_bbox, n=3)
+        p.linear(1, 0, pe[0])
+        p.layernorm(1, pe[1], relu=True)
+        p.linear(2, 1, pe[3])
+        p.layernorm(2, pe[4], relu=True)
+        p.load(0, query_feat.contiguous())
+        p.add(0, 2, E)
+        h_qpos = p.store(0, E)
+        p.linear(1, 0, mha, weight=mha.in_proj_weight, bias=mha.in_proj_bias)
+        h_qkv = p.store(1, 3 * E)
+        p.linear(2, 0, self.self_attn.gen_tau)
+        h_tau = p.store(2, H)
+        outs = p.run()
+        qpos, qkv, tau = outs[h_qpos], outs[h_qkv], outs[h_tau]
+        att = self.self_attn.attention_core(query_bbox, qkv.view(B, Q, 3 * E), tau.view(B, Q, H), attn_mask, H,
+                                            mha.dropout if self.training else 0.0)
+        p = rowtrain.RowChain(B * Q, width=E, num_bufs=2)
+        p.load(0, att.reshape(B * Q, E))
+        p.linear(1, 0, mha.out_proj)
+        p.dropout(1, E, self.self_attn.attention.proj_drop.p if self.training else 0.0, self._seed())
+        p.load(0, qpos)
+        p.add(1, 0, E)
+        p.layernorm(1, self.norm1)
+        h = p.store(1, E)
+        return p.run()[h].view(B, Q, E)
+
     def _pos_encode_rows(self, query_bbox, query_feat):
         """query_feat + position_encoder(query_bbox[..., :3]) as one launch (Linear-LN-ReLU-Linear-LN-ReLU + add)."""
         from . import rowops
@@ -896,13 +976,20 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         p.run()
         return out.view(B, Q, E)
 
-    def _tail_rows(self, mixed, query_feat, radar, lss):
+    def _tail_rows(self, mixed, query_feat, radar, lss, train=False):
         """Everything after the sampling ops of an iteration as ONE launch: norm2(mixed); per BEV branch the softmax queue
         fusion, output_proj, residual and norm; cat + fusion + norm_fusion; FFN + norm3; cls and reg branches.
-        radar / lss = (MSDA output [B*T,Q,C], queue logits [B,Q,T]). -> (query_feat, cls_score, reg delta)."""
+        radar / lss = (MSDA output [B*T,Q,C], queue logits [B,Q,T]). -> (query_feat, cls_score, reg delta).
+        train: the same chain with autograd (forward + generated backward row program) and the reference's dropouts."""
         from . import rowops
         B, Q, E = query_feat.shape
-        p = rowops.RowProgram(B * Q, width=3 * E, num_bufs=3)
+        if train:
+            from . import rowtrain
+            p = rowtrain.RowChain(B * Q, width=3 * E, num_bufs=3)
+            drop = (lambda buf, n, prob, col=0: p.dropout(buf, n, prob if self.training else 0.0, self._seed(), col))
+        else:
+            p = rowops.RowProgram(B * Q, width=3 * E, num_bufs=3)
+            drop = (lambda *a, **k: None)
         p.load(0, mixed.contiguous())
         p.layernorm(0, self.norm2)
         p.load(1, query_feat.contiguous())
@@ -911,12 +998,15 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
             col = (i + 1) * E
             p.load_queue(2, values, logits, Q, branch.attention.num_bev_queue)
             p.linear(0, 2, branch.attention.output_proj, dst_col=col)
+            drop(0, E, branch.attention.dropout.p, col)
             p.add(0, 1, E, dst_col=col)
             p.layernorm(0, norm, col=col)
         p.linear(1, 0, self.fusion)
         p.layernorm(1, self.norm_fusion)
         p.linear(2, 1, self.ffn.layers[0][0], relu=True)
+        drop(2, self.ffn.layers[0][0].out_features, self.ffn.layers[0][2].p)
         p.linear(0, 2, self.ffn.layers[1])
+        drop(0, E, self.ffn.layers[2].p)
         p.add(0, 1, E)
         p.layernorm(0, self.norm3)
         out_feat = p.store(0, E)
@@ -939,7 +1029,9 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
                     i += 2 if relu_after else 1
                 src = dst
             outs.append(p.store(src, mods[-1].out_features))
-        p.run()
+        res = p.run()
+        if train:
+            out_feat, outs = res[out_feat], [res[h] for h in outs]
         return out_feat.view(B, Q, E), outs[0].view(B, Q, -1), outs[1].view(B, Q, -1)
 
     def forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer=0,
@@ -961,7 +1053,11 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
     def _forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer,
                  prepared, rows):
         d_region = self.d_region_list[layer]
-        attended = self._self_attn_rows(query_bbox, query_feat) if rows and attn_mask is None else None
+        train_rows = not rows and self._train_rows_ok(query_feat)
+        if train_rows:
+            attended = self._self_attn_rows_train(query_bbox, query_feat, attn_mask)
+        else:
+            attended = self._self_attn_rows(query_bbox, query_feat) if rows and attn_mask is None else None
         if attended is not None:
             query_feat = attended
         else:
@@ -973,13 +1069,13 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
         heads = self._sampling_heads(query_feat) or (None, None, None)
         radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,
-                                        prepared=prep_radar, heads=heads[0], raw=rows)
+                                        prepared=prep_radar, heads=heads[0], raw=rows or train_rows)
         lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,
-                                    prepared=prep_lss, heads=heads[1], raw=rows)
+                                    prepared=prep_lss, heads=heads[1], raw=rows or train_rows)
         sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region, heads=heads[2])
         mixed = self.mixing(sampled, query_feat)
-        if rows:
-            query_feat, cls_score, delta = self._tail_rows(mixed, query_feat, radar, lss)
+        if rows or train_rows:
+            query_feat, cls_score, delta = self._tail_rows(mixed, query_feat, radar, lss, train=train_rows)
         else:
             radar, lss = self.norm_radar_bev(radar), self.norm_lss_bev(lss)
             query_feat = self.norm2(mixed)

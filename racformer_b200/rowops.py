@@ -16,8 +16,9 @@ from . import _lib
 _lib.load()
 
 LOAD, LOAD_QUEUE, STORE, ADD, LINEAR, LINEAR_NARROW, LAYERNORM = 1, 2, 3, 4, 5, 6, 7
-RELU = 1
-MAX_OPS = 40
+ZERO, RELU_MASK, DROPOUT, LAYERNORM_BWD, STORE_COLSUM, QUEUE_BWD = 8, 9, 10, 11, 12, 13
+RELU, ACCUM = 1, 2
+MAX_OPS = 128
 MAX_QUEUE = 16
 
 
@@ -26,7 +27,7 @@ class RowOp(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("dst", ctypes.c_int), ("dst_col", ctypes.c_int), ("src", ctypes.c_int),
                 ("src_col", ctypes.c_int), ("n", ctypes.c_int), ("k", ctypes.c_int), ("flags", ctypes.c_int),
                 ("ld", ctypes.c_int), ("aux", ctypes.c_int), ("eps", ctypes.c_float), ("p0", ctypes.c_void_p),
-                ("p1", ctypes.c_void_p), ("out", ctypes.c_void_p)]
+                ("p1", ctypes.c_void_p), ("out", ctypes.c_void_p), ("p2", ctypes.c_void_p), ("out2", ctypes.c_void_p)]
 
 
 _transposed = weakref.WeakKeyDictionary()     # module -> (key, W^T); dies with the module (ids are reused, modules are not)

@@ -176,3 +176,51 @@ class AdaptiveMixingCore(Function):
         x, params = ctx.saved_tensors
         gx, gp = points.adaptive_mixing_core_backward(x, params, grad_out.contiguous(), ctx.out_points)
         return gx, gp, None
+
+
+class SasaAttention(Function):
+    """Attention core of ScaleAdaptiveSelfAttention with autograd (csrc/sasa_train.cu): apply(qkv [B,Q,3E], tau [B,Q,H],
+    query_ray [B,Q,code], blocked (bool [Q,Q], True = query i may not see key j, or None), pc_range, num_heads, drop_p, seed)
+    -> [B,Q,E]. Saves qkv, tau, the output and one log-sum-exp per row; the [B,H,Q,Q] mask / probabilities never exist."""
+
+    @staticmethod
+    def supported(qkv, tau, num_heads):
+        return (qkv.is_cuda and qkv.dtype == torch.float32 and tau.dtype == torch.float32 and qkv.shape[-1] == 3 * num_heads * 32
+                and qkv.shape[1] <= 4096)
+
+    @staticmethod
+    def forward(ctx, qkv, tau, query_ray, blocked, pc_range, num_heads, drop_p, seed):
+        qkv, tau, query_ray = qkv.contiguous(), tau.contiguous(), query_ray.detach().contiguous()
+        B, Q, E3 = qkv.shape
+        E = E3 // 3
+        blocked_t = None if blocked is None else blocked.t().contiguous().to(torch.uint8)
+        out = torch.empty((B, Q, E), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((B, num_heads, Q), dtype=torch.float32, device=qkv.device)
+        pc = (ctypes.c_double * 6)(*[float(v) for v in pc_range])
+        with torch.cuda.device(qkv.device):
+            rc = _lib.load().racf_sasa_attention_train_forward(
+                qkv.data_ptr(), tau.data_ptr(), query_ray.data_ptr(), blocked_t.data_ptr() if blocked_t is not None else None, pc,
+                B, Q, num_heads, E // num_heads, query_ray.shape[2], float(drop_p), int(seed) & 0xffffffff, out.data_ptr(),
+                lse.data_ptr(), wrapper._stream(qkv.device))
+        _lib.check(rc, "racf_sasa_attention_train_forward")
+        ctx.save_for_backward(qkv, tau, query_ray, out, lse, *([blocked_t] if blocked_t is not None else []))
+        ctx.args = (tuple(float(v) for v in pc_range), num_heads, float(drop_p), int(seed) & 0xffffffff)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        qkv, tau, query_ray, out, lse, *rest = ctx.saved_tensors
+        blocked_t = rest[0] if rest else None
+        pc_range, num_heads, drop_p, seed = ctx.args
+        B, Q, E3 = qkv.shape
+        grad_out = grad_out.contiguous()
+        grad_qkv, grad_tau, dsum = torch.empty_like(qkv), torch.empty_like(tau), torch.empty_like(lse)
+        pc = (ctypes.c_double * 6)(*pc_range)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.load().racf_sasa_attention_train_backward(
+                qkv.data_ptr(), tau.data_ptr(), query_ray.data_ptr(), blocked_t.data_ptr() if blocked_t is not None else None, pc,
+                B, Q, num_heads, E3 // 3 // num_heads, query_ray.shape[2], drop_p, seed, out.data_ptr(), lse.data_ptr(),
+                grad_out.data_ptr(), dsum.data_ptr(), grad_qkv.data_ptr(), grad_tau.data_ptr(), wrapper._stream(qkv.device))
+        _lib.check(rc, "racf_sasa_attention_train_backward")
+        return grad_qkv, grad_tau, None, None, None, None, None, None
