@@ -153,9 +153,10 @@ def _main():
     ap.add_argument("--workload", default=os.environ.get("RACF_BENCH_WORKLOAD", "decoder_forward_f8"))
     ap.add_argument("--cpu-baseline-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--legs", default=os.environ.get("RACF_BENCH_LEGS", "ops,train,full_inference"),
+    ap.add_argument("--legs", default=os.environ.get("RACF_BENCH_LEGS", "ops,train,train_3cam,full_inference"),
                     help="secondary measurements added to the JSON line (comma list; '' = none): ops = config 1 op "
-                         "microbench (N=1 only), train = config 4 decoder training step, full_inference = config 3")
+                         "microbench (N=1 only), train = config 4 decoder training step, train_3cam = config 5, "
+                         "full_inference = config 3")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -278,7 +279,11 @@ def _main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl_config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": wl_unit, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "h2d_gbs_total": e2e_value * h2d_bytes / 1e9, "h2d_gbs_per_gpu": e2e_value * h2d_bytes / 1e9 / world,
+                    "note": "bounded by the host->device link: compare h2d_gbs with the measured concurrent pinned-copy "
+                            "ceiling of the box (profiles/r02_h2d_ceiling_*.json, tools/h2d_ceiling.py); the full_inference "
+                            "leg is the same path fed with its real input (95 MB of images / radar maps per sample)"},
             "gpu_launches": launches,
             "roofline": roof,
             "roofline_sampling_in_step": roof_sampling,

@@ -297,11 +297,13 @@ def _depth_base(d_region, depth_num, device):
     return t
 
 
-def _polar_depth_offsets(module, query_feat, d_region):
-    """linspace(-d, d, D) + learned jitter, shared by both samplers (racformer_transformer.py:395-396, 513-514)."""
+def _polar_depth_offsets(module, query_feat, d_region, ray_logits=None):
+    """linspace(-d, d, D) + learned jitter, shared by both samplers (racformer_transformer.py:395-396, 513-514).
+    ray_logits: ray_points_offset(query_feat) when the caller has already computed it."""
     D = module.depth_num
     base = torch.linspace(-d_region, d_region, D, device=query_feat.device, dtype=query_feat.dtype).view(1, 1, D)
-    return base + (module.ray_points_offset(query_feat).sigmoid() * 2 - 1) * d_region / D / 2
+    ray = module.ray_points_offset(query_feat) if ray_logits is None else ray_logits
+    return base + (ray.sigmoid() * 2 - 1) * d_region / D / 2
 
 
 class RaCFormerSampling(nn.Module):
@@ -339,19 +341,20 @@ class RaCFormerSampling(nn.Module):
             C = out.shape[2]
             return out.reshape(B, T, G, Q, C, Pn * D).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
         query_bbox = theta_d2xy_coods(query_ray)
-        offset = self.sampling_offset(query_feat).view(B, Q, G * Pn * D, 3)
+        off, ray, sw = heads if heads is not None else (self.sampling_offset(query_feat), None, None)
+        offset = off.view(B, Q, G * Pn * D, 3)
         pts = make_sample_points(query_bbox, offset, pr).reshape(B, Q, 1, G, Pn * D, 3).expand(B, Q, T, G, Pn * D, 3)
         # ego-motion-free warp by the query velocity
         shift = (query_ray[..., 8:].detach()[:, :, None, :] * meta["time_diff"][:, None, :, None])[:, :, :, None, None, :]
         x = (pts[..., 0:1] - shift[..., 0:1] - pr[0]) / (pr[3] - pr[0])
         y = (pts[..., 1:2] - shift[..., 1:2] - pr[1]) / (pr[4] - pr[1])
         polar = xy2theta_d_coods(torch.cat([x, y, pts[..., 2:3]], dim=-1)).reshape(B, Q, T, G, Pn, D, 3)
-        depth = _polar_depth_offsets(self, query_feat, d_region).view(B, Q, 1, 1, 1, D, 1)
+        depth = _polar_depth_offsets(self, query_feat, d_region, ray).view(B, Q, 1, 1, 1, D, 1)
         polar = torch.cat([polar[..., 0:1], polar[..., 1:2] + depth, polar[..., 2:]], dim=-1)
         cart = theta_d2xy_coods(polar.reshape(B, Q, T, G, Pn * D, 3))
         pts = torch.cat([cart[..., 0:1] * (pr[3] - pr[0]) + pr[0], cart[..., 1:2] * (pr[4] - pr[1]) + pr[1],
                          cart[..., 2:]], dim=-1)
-        w = self.scale_weights(query_feat).view(B, Q, G, T, D * Pn, self.num_levels)
+        w = (self.scale_weights(query_feat) if sw is None else sw).view(B, Q, G, T, D * Pn, self.num_levels)
         w = torch.softmax(w, dim=-1)
         return sampling_4d(ops, pts, mlvl_feats, w, meta["lidar2img"], meta["image_h"], meta["image_w"],
                            shared_grads=meta.get("shared_grads"))
@@ -417,12 +420,14 @@ class BEVSelfAttention(nn.Module):
             v = self.value_proj(pixels)
         return v.reshape(B * T, v.shape[1], self.num_heads, -1)
 
-    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False, shared_grads=None):
+    def forward(self, ops, query, value, sampling_locations, attention_weights, spatial_shapes, raw=False, shared_grads=None,
+                queue_logits=None):
         B, Q, C = query.shape
         T, M, L, P = self.num_bev_queue, self.num_heads, self.num_levels, self.num_points
         loc = sampling_locations.view(B, Q, M, T, L, P, 2).permute(3, 0, 1, 2, 4, 5, 6).reshape(B * T, Q, M, L, P, 2)
         aw = attention_weights.view(B, Q, M, T, L, P).permute(3, 0, 1, 2, 4, 5).reshape(B * T, Q, M, L, P)   # quirk (ii)
-        return self.attend(ops, query, value, loc, aw, spatial_shapes, raw=raw, shared_grads=shared_grads)
+        return self.attend(ops, query, value, loc, aw, spatial_shapes, raw=raw, shared_grads=shared_grads,
+                           queue_logits=queue_logits)
 
     def attend(self, ops, query, value, loc, aw, spatial_shapes, queue_logits=None, raw=False, shared_grads=None):
         """loc [T*B,Q,M,L,P,2] / aw [T*B,Q,M,L,P] already in the queue-major packing; queue_logits: bev_queue_weight(query)
@@ -588,19 +593,21 @@ class BEVSampling(nn.Module):
             return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw,
                                          shared_grads=meta.get("shared_grads"))
         query_bbox = theta_d2xy_coods(query_ray)
-        offset = self.sampling_offset(query_feat).view(B, Q, M * Pn * D, 2)
+        off, ray, sw, qw = heads if heads is not None else (self.sampling_offset(query_feat), None, None, None)
+        offset = off.view(B, Q, M * Pn * D, 2)
         offset = torch.cat([offset, torch.zeros_like(offset[..., 0:1])], dim=-1)
         pts = make_sample_points(query_bbox, offset, pr).reshape(B, Q, 1, M, Pn * D, 3).expand(B, Q, T, M, Pn * D, 3)
         shift = (query_ray[..., 8:].detach()[:, :, None, :] * meta["time_diff"][:, None, :, None])[:, :, :, None, None, :]
         x = (pts[..., 0:1] - shift[..., 0:1] - pr[0]) / (pr[3] - pr[0])
         y = (pts[..., 1:2] - shift[..., 1:2] - pr[1]) / (pr[4] - pr[1])
         polar = xy2theta_d_coods(torch.cat([x, y], dim=-1)).reshape(B, Q, T, M, Pn, D, 2)
-        depth = _polar_depth_offsets(self, query_feat, d_region).view(B, Q, 1, 1, 1, D, 1)
+        depth = _polar_depth_offsets(self, query_feat, d_region, ray).view(B, Q, 1, 1, 1, D, 1)
         polar = torch.cat([polar[..., 0:1], polar[..., 1:2] + depth], dim=-1).reshape(B, Q, T, M, Pn * D, 2)
         loc = theta_d2xy_coods(polar).permute(0, 1, 3, 2, 4, 5).contiguous()               # [B,Q,M,T,P,2]
-        w = self.scale_weights(query_feat).view(B, Q, M, 1, self.num_levels, D * Pn)
+        w = (self.scale_weights(query_feat) if sw is None else sw).view(B, Q, M, 1, self.num_levels, D * Pn)
         w = torch.softmax(w, dim=-1).expand(B, Q, M, T, self.num_levels, D * Pn).contiguous()
-        return self.attention(ops, query_feat, value, loc, w, hw, raw=raw, shared_grads=meta.get("shared_grads"))
+        return self.attention(ops, query_feat, value, loc, w, hw, raw=raw, shared_grads=meta.get("shared_grads"),
+                              queue_logits=qw)
 
     def forward(self, ops, query_ray, query_feat, bev_feats, meta, d_region=0.1, prepared=None, heads=None, raw=False):
         def fn(qr, qf, bev):
@@ -857,6 +864,28 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         outs = [o.view(B, Q, -1) for o in self._heads(query_feat)]
         return outs[0:4], outs[4:8], outs[8:11]
 
+    def _sampling_heads_train(self, query_feat):
+        """Training counterpart of _sampling_heads: the eleven sampling heads as ONE row chain with autograd (one forward
+        launch, one backward launch that also sums their input gradients, eleven weight-gradient GEMMs)."""
+        from . import rowtrain
+        radar, lss, img = self.sampling_radar_bev, self.sampling_lss_bev, self.sampling
+        if not (radar.attention.queue_weight and lss.attention.queue_weight):
+            return None
+        lins = [radar.sampling_offset, radar.ray_points_offset, radar.scale_weights, radar.attention.bev_queue_weight,
+                lss.sampling_offset, lss.ray_points_offset, lss.scale_weights, lss.attention.bev_queue_weight,
+                img.sampling_offset, img.ray_points_offset, img.scale_weights]
+        B, Q, E = query_feat.shape
+        width = max([E] + [-(-lin.out_features // 4) * 4 for lin in lins])
+        p = rowtrain.RowChain(B * Q, width=width, num_bufs=2)
+        p.load(0, query_feat.contiguous())
+        handles = []
+        for lin in lins:
+            p.linear(1, 0, lin)
+            handles.append(p.store(1, lin.out_features))
+        res = p.run()
+        outs = [res[h].view(B, Q, -1) for h in handles]
+        return outs[0:4], outs[4:8], outs[8:11]
+
     def refine_bbox(self, proposal, delta):
         dz = torch.sigmoid(delta[..., 1:3] + inverse_sigmoid(proposal[..., 1:3]))
         theta = proposal[..., 0:1] + (torch.sigmoid(delta[..., 0:1]) * 2 - 1) / self.num_ray
@@ -1067,7 +1096,7 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
                 query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
             query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
-        heads = self._sampling_heads(query_feat) or (None, None, None)
+        heads = (self._sampling_heads_train(query_feat) if train_rows else self._sampling_heads(query_feat)) or (None, None, None)
         radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,
                                         prepared=prep_radar, heads=heads[0], raw=rows or train_rows)
         lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,

@@ -16,7 +16,7 @@ def test_row_program_argument_errors_are_codes():
     ops = (RowOp * 1)(RowOp(kind=LOAD, dst=0, n=4, ld=4, p0=16))
     assert lib.racf_row_program_forward(None, 1, 8, 8, 1, 4, None) == -1
     assert lib.racf_row_program_forward(ops, 0, 8, 8, 1, 4, None) == -3
-    assert lib.racf_row_program_forward(ops, 41, 8, 8, 1, 4, None) == -3
+    assert lib.racf_row_program_forward(ops, 129, 8, 8, 1, 4, None) == -3         # more than RACF_ROW_MAX_OPS
     assert lib.racf_row_program_forward(ops, 1, 8, 5, 1, 4, None) == -6          # rows per CTA: 4 or 8
     assert lib.racf_row_program_forward(ops, 1, 8, 8, 1, 6, None) == -6          # width % 4
     bad = (RowOp * 1)(RowOp(kind=LOAD, dst=1, n=4, ld=4, p0=16))
@@ -27,8 +27,10 @@ def test_row_program_argument_errors_are_codes():
     assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -6          # in-place Linear
     bad = (RowOp * 1)(RowOp(kind=LOAD, dst=0, n=4, ld=4, p0=None))
     assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -1
-    bad = (RowOp * 1)(RowOp(kind=9, dst=0, n=4))
-    assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -6
+    bad = (RowOp * 1)(RowOp(kind=14, dst=0, n=4))
+    assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -6         # unknown operator kind
+    bad = (RowOp * 1)(RowOp(kind=11, dst=0, n=4, ld=4, p2=None))
+    assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -1         # LAYERNORM_BWD without the saved input
 
 
 def _rel_err(a, ref64):

@@ -131,7 +131,7 @@ def test_decoder_training_fused_bindings_match_plain_autograd():
         assert_close(p1[n], p0[n], 1e-3, 1e-4 * float(p0[n].abs().max()) + 1e-7, f"grad of {n}")
 
 
-@pytest.mark.parametrize("p_in", [96, 32, 128])
+@pytest.mark.parametrize("p_in", [96, 32, 128, 48])
 def test_adaptive_mixing_core_function_gradients_vs_fp64_autograd(p_in):
     """AdaptiveMixingCore (tcgen05 forward, recomputing CUDA-core backward) against the PyTorch chain of
     models/racformer_transformer.py:592-604 evaluated in fp64 with autograd."""

@@ -49,7 +49,32 @@ for e in evs:
     k = "<3us" if t < 3 else "3-10us" if t < 10 else "10-50us" if t < 50 else "50-200us" if t < 200 else ">200us"
     hist[k] += 1
     hist_ms[k] += t / 1e3
-print(json.dumps({"workload": name, "step_ms": step_ms, "gpu_busy_ms": total / 1e3, "num_gpu_kernels": sum(v[1] for v in agg.values()),
+def family(n):
+    if "racf::" in n:
+        return "ours (libracformer_ops.so)"
+    if n.startswith(("Memcpy", "Memset")):
+        return "memcpy / memset"
+    if "at::native" in n or "at_cuda_detail" in n or "Optimizer" in n:
+        return "pytorch (aten elementwise / reduce / copy kernels)"
+    return "library (cuDNN / cuBLAS / CUTLASS / NCCL)"
+
+
+shares = {}
+for k, v in agg.items():
+    f = shares.setdefault(family(k), {"ms": 0.0, "launches": 0})
+    f["ms"] += v[0] / 1e3
+    f["launches"] += v[1]
+for f in shares.values():
+    f["share_of_gpu_time"] = f["ms"] / (total / 1e3)
+ours = {}
+for k, v in agg.items():
+    if "racf::" in k:
+        short = k.split("racf::")[1].split("(")[0].split("<")[0]
+        o = ours.setdefault(short, {"ms": 0.0, "launches": 0})
+        o["ms"] += v[0] / 1e3
+        o["launches"] += v[1]
+print(json.dumps({"workload": name, "launch_shares": shares,
+                  "own_kernels": dict(sorted(ours.items(), key=lambda kv: -kv[1]["ms"])), "step_ms": step_ms, "gpu_busy_ms": total / 1e3, "num_gpu_kernels": sum(v[1] for v in agg.values()),
                   "duration_histogram_calls": hist, "duration_histogram_ms": hist_ms,
                   "largest_single_kernels": [{"name": e.name[:70], "us": (e.device_time if hasattr(e, "device_time") else e.cuda_time)} for e in single],
                   "top": [{"name": k, "ms": v[0] / 1e3, "calls": v[1]} for k, v in top]}, indent=1))
