@@ -267,6 +267,13 @@ int racf_adaptive_mixing_forward_split(const float* x, const float* params, int 
 int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
                                     int out_points, int channels, float eps, float* out, void* out3,
                                     int tiled_groups, racf_stream_t stream);
+/* The same with the kernel chosen explicitly (measurement and parity of both versions): variant 0 = default (the
+ * warp-specialised kernel csrc/mixing_ws.cu for in_points <= 96, else the phase-serial kernel csrc/mixing_tc.cu),
+ * 1 = phase-serial, 2 = warp-specialised (RACF_ERR_UNSUPPORTED for in_points > 96). Results agree to fp32 rounding of the
+ * layer-norm sums (different summation trees), not bit for bit. */
+int racf_adaptive_mixing_tc_forward_variant(const float* x, const float* params, int num_query_groups, int in_points,
+                                            int out_points, int channels, float eps, float* out, void* out3,
+                                            int tiled_groups, int variant, racf_stream_t stream);
 
 /*
  * Backward of the AdaptiveMixing core for training (autograd of models/racformer_transformer.py:592-604): given

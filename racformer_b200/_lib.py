@@ -48,6 +48,8 @@ SIGNATURES = {
                                                 _i, ctypes.c_void_p]),
     "racf_adaptive_mixing_tc_forward": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                              ctypes.c_void_p, _i, ctypes.c_void_p]),
+    "racf_adaptive_mixing_tc_forward_variant": (_i, [_c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
+                                                     ctypes.c_void_p, _i, _i, ctypes.c_void_p]),
     "racf_adaptive_mixing_backward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                            _c_float_p, ctypes.c_void_p]),
     "racf_linear_tiled_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _i]),

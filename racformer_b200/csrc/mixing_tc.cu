@@ -434,15 +434,24 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
 }  // namespace mixtc
 }  // namespace racf
 
+// Which kernel variant 0 selects for in_points <= 96 (tools/mixing_bench.py measures both).
+constexpr bool kDefaultWarpSpecialised = false;
+
+int racf_mixws_launch(const float* x, const float* params, int num_query_groups, int in_points, float eps, float* out,
+                      void* out3, int tiled_groups, int sms, cudaStream_t st);   // csrc/mixing_ws.cu
+
 // out (fp32 [QG, 128, 64]) or out3 (tiled pieces, tiled_groups = n_groups) -- exactly one of them non-NULL.
-extern "C" int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
-                                               int out_points, int channels, float eps, float* out, void* out3,
-                                               int tiled_groups, racf_stream_t stream) {
+// variant: 0 = the warp-specialised kernel (csrc/mixing_ws.cu) where it exists (in_points <= 96), else the phase-serial
+// kernel of this file; 1 = phase-serial; 2 = warp-specialised (RACF_ERR_UNSUPPORTED if in_points > 96).
+extern "C" int racf_adaptive_mixing_tc_forward_variant(const float* x, const float* params, int num_query_groups, int in_points,
+                                                       int out_points, int channels, float eps, float* out, void* out3,
+                                                       int tiled_groups, int variant, racf_stream_t stream) {
     using namespace racf::mixtc;
     if (!x || !params || (!out && !out3) || (out && out3)) return RACF_ERR_NULL_POINTER;
     if (num_query_groups <= 0) return RACF_ERR_BAD_SHAPE;
     if (channels != kC || out_points != kPout || in_points < 16 || in_points > 128 || (in_points & 15) != 0)
         return RACF_ERR_UNSUPPORTED;
+    if (variant < 0 || variant > 2 || (variant == 2 && in_points > 96)) return RACF_ERR_UNSUPPORTED;
     if (out3 && (tiled_groups <= 0 || num_query_groups % tiled_groups != 0)) return RACF_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(out) |
          reinterpret_cast<uintptr_t>(out3)) & 15u)
@@ -451,9 +460,11 @@ extern "C" int racf_adaptive_mixing_tc_forward(const float* x, const float* para
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return (int)e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (variant == 2 || (variant == 0 && kDefaultWarpSpecialised && in_points <= 96))
+        return racf_mixws_launch(x, params, num_query_groups, in_points, eps, out, out3, tiled_groups, sms, st);
     const int smem = kSmemBytes + 1024;
     const unsigned grid = (unsigned)(num_query_groups < sms ? num_query_groups : sms);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (out3) {
         e = cudaFuncSetAttribute(adaptive_mixing_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -465,4 +476,11 @@ extern "C" int racf_adaptive_mixing_tc_forward(const float* x, const float* para
         adaptive_mixing_tc_kernel<false><<<grid, kThreads, smem, st>>>(x, params, out, nullptr, 0, num_query_groups, in_points, eps);
     }
     return (int)cudaGetLastError();
+}
+
+extern "C" int racf_adaptive_mixing_tc_forward(const float* x, const float* params, int num_query_groups, int in_points,
+                                               int out_points, int channels, float eps, float* out, void* out3,
+                                               int tiled_groups, racf_stream_t stream) {
+    return racf_adaptive_mixing_tc_forward_variant(x, params, num_query_groups, in_points, out_points, channels, eps, out, out3,
+                                                   tiled_groups, 0, stream);
 }

@@ -118,13 +118,15 @@ def to_channels_last(x, concat_channels=0):
     return dense, both
 
 
-def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_groups=0, tensor_cores=True):
+def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_groups=0, tensor_cores=True, variant=0):
     """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
     (csrc/mixing.cu). With split=True the result comes back as its three bf16 pieces [3, QG, out_points, C] (their sum is
     the fp32 result exactly), or -- tiled_groups = n_groups -- as the linear.TiledOperand of the [QG / n_groups, n_groups *
     out_points * C] matrix out_proj multiplies. Returns None when the fused kernel does not exist for the shapes (callers
     use the PyTorch chain). tensor_cores: use csrc/mixing_tc.cu (tcgen05, bf16x3 operand splitting, fp32 accumulation)
-    where it exists (P_in % 16 == 0) for the fp32 and the tiled result; otherwise the CUDA-core kernel csrc/mixing.cu."""
+    where it exists (P_in % 16 == 0) for the fp32 and the tiled result; otherwise the CUDA-core kernel csrc/mixing.cu.
+    variant (tensor-core kernels only): 0 = default (warp-specialised csrc/mixing_ws.cu for P_in <= 96), 1 = phase-serial
+    csrc/mixing_tc.cu, 2 = warp-specialised."""
     _check(x, params)
     QG, P_in, C = x.shape
     if params.shape != (QG, C * C + out_points * P_in):
@@ -135,12 +137,14 @@ def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_gro
             if split:
                 from . import linear
                 out = linear.empty_tiled(QG // tiled_groups, tiled_groups * out_points * C, x.device)
-                rc = lib.racf_adaptive_mixing_tc_forward(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C, float(eps),
-                                                         None, out.buf.data_ptr(), int(tiled_groups), _stream(x.device))
+                rc = lib.racf_adaptive_mixing_tc_forward_variant(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C,
+                                                                 float(eps), None, out.buf.data_ptr(), int(tiled_groups),
+                                                                 int(variant), _stream(x.device))
             else:
                 out = torch.empty((QG, out_points, C), dtype=torch.float32, device=x.device)
-                rc = lib.racf_adaptive_mixing_tc_forward(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C, float(eps),
-                                                         out.data_ptr(), None, 0, _stream(x.device))
+                rc = lib.racf_adaptive_mixing_tc_forward_variant(x.data_ptr(), params.data_ptr(), QG, P_in, out_points, C,
+                                                                 float(eps), out.data_ptr(), None, 0, int(variant),
+                                                                 _stream(x.device))
         _lib.check(rc, "racf_adaptive_mixing_tc_forward")
         return out
     with torch.cuda.device(x.device):
