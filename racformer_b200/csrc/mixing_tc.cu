@@ -435,7 +435,7 @@ adaptive_mixing_tc_kernel(const float* __restrict__ x, const float* __restrict__
 }  // namespace racf
 
 // Which kernel variant 0 selects for in_points <= 96 (tools/mixing_bench.py measures both).
-constexpr bool kDefaultWarpSpecialised = false;
+constexpr bool kDefaultWarpSpecialised = true;     // 170 / 176 us vs 179 / 198 us (fp32 / tiled output) at the f8 shapes
 
 int racf_mixws_launch(const float* x, const float* params, int num_query_groups, int in_points, float eps, float* out,
                       void* out3, int tiled_groups, int sms, cudaStream_t st);   // csrc/mixing_ws.cu

@@ -40,11 +40,24 @@ namespace racf {
 namespace mixws {
 
 constexpr int kC = 64, kPout = 128, kMaxPin = 96;
-constexpr int kSplitWarp0 = 1, kSplitWarps = 7, kLn1Warp0 = 8, kLn2Warp0 = 16, kLnWarps = 8;    // kLnWarps per LN group
-constexpr int kThreads = 32 * (kLn2Warp0 + kLnWarps);         // 768
-constexpr int kSlotBytes = 4096, kSlotChunks = kSlotBytes / 32;   // a chunk = 8 consecutive fp32 = one 16-byte bf16 chunk
+#ifndef RACF_MIXWS_SPLIT_WARPS
+#define RACF_MIXWS_SPLIT_WARPS 14
+#endif
+#ifndef RACF_MIXWS_MERGED_LN
+#define RACF_MIXWS_MERGED_LN 1
+#endif
+constexpr bool kMergedLn = RACF_MIXWS_MERGED_LN != 0;         // one LayerNorm group does LN1(n) then LN2(n-1) instead of two groups
+constexpr int kSplitWarp0 = 1, kSplitWarps = RACF_MIXWS_SPLIT_WARPS, kLnWarps = 8;   // kLnWarps per LN group
+constexpr int kLn1Warp0 = kSplitWarp0 + kSplitWarps, kLn2Warp0 = kLn1Warp0 + (kMergedLn ? 0 : kLnWarps);
+constexpr int kThreads = 32 * (kLn2Warp0 + kLnWarps);         // 736 (14 splitter warps, one LN group)
+#ifndef RACF_MIXWS_SLOT_BYTES
+#define RACF_MIXWS_SLOT_BYTES 4096
+#endif
+constexpr int kSlotBytes = RACF_MIXWS_SLOT_BYTES, kSlotChunks = kSlotBytes / 32;   // a chunk = 8 consecutive fp32 = one 16-byte bf16 chunk
+constexpr int kCpt = kSlotChunks / 32;                        // chunks per thread and slot (a warp owns a whole slot)
+static_assert(kSlotBytes == 2048 || kSlotBytes == 4096, "slots hold whole 8-row groups of M");
 #ifndef RACF_MIXWS_RING
-#define RACF_MIXWS_RING 14
+#define RACF_MIXWS_RING (57344 / RACF_MIXWS_SLOT_BYTES)
 #endif
 constexpr int kRing = RACF_MIXWS_RING;
 // A ring slot must always be consumed by the same splitter warp: a warp that runs ahead of its neighbours would otherwise
@@ -62,7 +75,8 @@ constexpr int kRaw = kT3 + 3 * kTPiece;
 constexpr int kSmemBytes = kRaw + kRing * kSlotBytes;
 constexpr int kTmemCols = 512;                                // D1[b]: b*128 (+64 cross); D2[b]: 256 + b*128 (+64 cross)
 // Tuning aid (RACF_NVCC_DEFINES=-DRACF_MIXWS_EXP=n, results are then wrong): 1 = producer + splitters only (no MMA / LN, no
-// waits on the operand buffers), 2 = as 1 without the split arithmetic and stores, 3 = as 1 without the stores only.
+// waits on the operand buffers), 2 = as 1 without the split arithmetic and stores, 3 = as 1 without the stores only,
+// 4 = full kernel without the proxy fences, 5 = full kernel issuing only the a0*b0 piece products.
 #ifndef RACF_MIXWS_EXP
 #define RACF_MIXWS_EXP 0
 #endif
@@ -233,18 +247,20 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], uint8_t* tile,
 
 struct Bars {                       // all mbarriers of the CTA
     uint64_t raw_full[kRing];
-    uint64_t xm_ready, xm_free, s_ready, s_free, t_ready, t_free;
+    uint64_t xm_ready, s_ready, t_ready, t_free;
+    // "operand tile free" signals, one barrier per item modulo 4: a splitter warp does not own a slot of every kind in
+    // every item, so it may wait for a completion that is not the next one -- a single barrier's parity cannot express that
+    uint64_t xm_free[4], s_free[4];
     uint64_t d1_full[2], d1_free[2], d2_full[2], d2_free[2];
 };
 
 // sum over the eight warps of one LayerNorm group (fixed order -> deterministic): shuffles, one named barrier, 8 partials
-template <int kBarId>
-__device__ __forceinline__ float ln_group_sum(float v, float* red, int lw, int lane, int& flip) {
+__device__ __forceinline__ float ln_group_sum(int bar_id, float v, float* red, int lw, int lane, int& flip) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     float* r = red + flip * kLnWarps;
     if (lane == 0) r[lw] = v;
-    asm volatile("bar.sync %0, %1;" ::"n"(kBarId), "n"(kLnWarps * 32) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kLnWarps * 32) : "memory");
     const float4 a = *reinterpret_cast<const float4*>(r), b = *reinterpret_cast<const float4*>(r + 4);
     flip ^= 1;
     return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
@@ -311,8 +327,9 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
 
     if (tid == 0) {
         for (int s = 0; s < kRing; ++s) mbar_init(smem_u32(&bars.raw_full[s]), 1);
-        mbar_init(smem_u32(&bars.xm_ready), nx + nm); mbar_init(smem_u32(&bars.xm_free), 1);
-        mbar_init(smem_u32(&bars.s_ready), ns);       mbar_init(smem_u32(&bars.s_free), 1);
+        mbar_init(smem_u32(&bars.xm_ready), nx + nm);
+        mbar_init(smem_u32(&bars.s_ready), ns);
+        for (int b = 0; b < 4; ++b) { mbar_init(smem_u32(&bars.xm_free[b]), 1); mbar_init(smem_u32(&bars.s_free[b]), 1); }
         mbar_init(smem_u32(&bars.t_ready), kLnWarps); mbar_init(smem_u32(&bars.t_free), 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars.d1_full[b]), 1); mbar_init(smem_u32(&bars.d1_free[b]), kLnWarps);
@@ -350,7 +367,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                    for (int order = 2; order >= 1; --order)
+                    for (int order = (RACF_MIXWS_EXP == 5 ? 0 : 2); order >= 1; --order)
 #pragma unroll
                         for (int pa = 0; pa <= order; ++pa) {
                             umma_bf16(d_cross, desc_kmajor<128>(sm_addr + kX3 + pa * kXPiece + ks * 32),
@@ -359,7 +376,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                         }
                     umma_bf16(d_main, desc_kmajor<128>(sm_addr + kX3 + ks * 32), desc_kmajor<128>(sm_addr + kM3 + ks * 32), idesc, ks > 0);
                 }
-                umma_commit(smem_u32(&bars.xm_free));
+                umma_commit(smem_u32(&bars.xm_free[n & 3]));
                 umma_commit(smem_u32(&bars.d1_full[b]));
             };
             auto product2 = [&](int n) {       // D2[b] = S3 @ t
@@ -375,7 +392,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                     const uint32_t a_off = (ks >> 1) * 8192 + (ks & 1) * 32;
                     const uint32_t b_off = kTMajorMN ? ks * 2048 : (ks >> 1) * 4096 + (ks & 1) * 32;
 #pragma unroll
-                    for (int order = 2; order >= 1; --order)
+                    for (int order = (RACF_MIXWS_EXP == 5 ? 0 : 2); order >= 1; --order)
 #pragma unroll
                         for (int pa = 0; pa <= order; ++pa) {
                             const uint32_t ta = sm_addr + kT3 + (order - pa) * kTPiece + b_off;
@@ -387,7 +404,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                     umma_bf16(d_main, desc_kmajor<64>(sm_addr + kS3 + a_off), kTMajorMN ? desc_mnmajor_sw128(t0) : desc_kmajor<64>(t0),
                               idesc2, ks > 0);
                 }
-                umma_commit(smem_u32(&bars.s_free));
+                umma_commit(smem_u32(&bars.s_free[n & 3]));
                 umma_commit(smem_u32(&bars.t_free));
                 umma_commit(smem_u32(&bars.d2_full[b]));
             };
@@ -425,12 +442,15 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             bulk_load(sm_addr + kRaw + rs * kSlotBytes, src, (uint32_t)nb, smem_u32(&bars.raw_full[rs]));
         };
         int n = 0, w = sw;                                         // slot g = n * spi + w: being consumed
-        int nf = 0, wf = sw;                                       // slot g + 14 (or the prologue's slots): being fetched
-        if (lane == 0) {
+        int nf = 0, wf = sw;                                       // the slot being fetched (kRing ahead once the ring is primed)
+        while (wf >= spi) { wf -= spi; ++nf; }
+        if (lane == 0 && sw < total) {
             fetch(nf, wf, (uint32_t)sw);
-            wf += kSplitWarps;
-            while (wf >= spi) { wf -= spi; ++nf; }
-            if (sw + kSplitWarps < total) fetch(nf, wf, (uint32_t)(sw + kSplitWarps));
+            for (int j = 1; j < kRing / kSplitWarps; ++j) {
+                wf += kSplitWarps;
+                while (wf >= spi) { wf -= spi; ++nf; }
+                if (sw + j * kSplitWarps < total) fetch(nf, wf, (uint32_t)(sw + j * kSplitWarps));
+            }
         }
         for (int g = sw; g < total; g += kSplitWarps, w += kSplitWarps) {
             while (w >= spi) { w -= spi; ++n; }
@@ -438,13 +458,19 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             PROGRESS(g);
             const float* raw = reinterpret_cast<const float*>(sm + kRaw + rs * kSlotBytes);
             uint64_t* ready;
+#ifdef RACF_MIXWS_PROFILE
+            long long t_slot;
+#endif
             if (w < nx + nm) {
-                if (!RACF_MIXWS_SPLIT_ONLY) MBAR_WAIT(smem_u32(&bars.xm_free), (n & 1) ^ 1, 7);          // product 1 of item n-1 has read X3 / M3
+                if (!RACF_MIXWS_SPLIT_ONLY && n > 0) MBAR_WAIT(smem_u32(&bars.xm_free[(n - 1) & 3]), ((n - 1) >> 2) & 1, 7);          // product 1 of item n-1 has read X3 / M3
                 MBAR_WAIT(smem_u32(&bars.raw_full[rs]), rk & 1, 6);
+#ifdef RACF_MIXWS_PROFILE
+                t_slot = clock64();
+#endif
                 ready = &bars.xm_ready;
                 if (w < nx) {                                                  // 16 rows of x
 #pragma unroll 1
-                    for (int i0 = 0; i0 < 4; i0 += 2) {                        // two chunks at a time (register budget)
+                    for (int i0 = 0; i0 < kCpt; i0 += 2) {                     // two chunks at a time (register budget)
                         float4 a[2], b[2];
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
@@ -464,7 +490,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                 } else {                                                       // 16 rows c of M -> M3 = M^T: row c', 8 c per chunk
                     const int h = w - nx;
 #pragma unroll 1
-                    for (int cg = 0; cg < 2; ++cg) {                           // chunks lane + 32 i: c' = (lane + 32 i) & 63, c group i >> 1
+                    for (int cg = 0; cg < kCpt / 2; ++cg) {                    // chunks lane + 32 i: c' = (lane + 32 i) & 63, c group i >> 1
                         float f[2][8];
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
@@ -473,17 +499,20 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const int cp = lane + 32 * i;
-                            split_store8(f[i], sm + kM3, kMPiece, cp * 128 + (((h * 2 + cg) ^ (cp & 7)) << 4));
+                            split_store8(f[i], sm + kM3, kMPiece, cp * 128 + (((h * (kCpt / 2) + cg) ^ (cp & 7)) << 4));
                         }
                     }
                 }
             } else {
-                if (!RACF_MIXWS_SPLIT_ONLY) MBAR_WAIT(smem_u32(&bars.s_free), (n & 1) ^ 1, 8);           // product 2 of item n-1 has read S3
+                if (!RACF_MIXWS_SPLIT_ONLY && n > 0) MBAR_WAIT(smem_u32(&bars.s_free[(n - 1) & 3]), ((n - 1) >> 2) & 1, 8);           // product 2 of item n-1 has read S3
                 MBAR_WAIT(smem_u32(&bars.raw_full[rs]), rk & 1, 6);
+#ifdef RACF_MIXWS_PROFILE
+                t_slot = clock64();
+#endif
                 ready = &bars.s_ready;
                 const int g0 = (w - nx - nm) * kSlotChunks;
 #pragma unroll 1
-                for (int i0 = 0; i0 < 4; i0 += 2) {
+                for (int i0 = 0; i0 < kCpt; i0 += 2) {
                     float4 a[2], b[2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -501,8 +530,16 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                     }
                 }
             }
+#ifdef RACF_MIXWS_PROFILE
+            const long long t_split = clock64();
+#endif
             fence_async_smem();                                    // generic-proxy writes -> visible to the MMA (async proxy)
             __syncwarp();
+#ifdef RACF_MIXWS_PROFILE
+            const long long t_fence = clock64();
+            prof[0] += t_split - t_slot;     // LDS + split + STS issue
+            prof[1] += t_fence - t_split;    // proxy fence + warp sync
+#endif
             if (lane == 0) {
                 mbar_arrive(smem_u32(ready));
                 if (g + kRing < total) {                           // the slot's values have been used (see header): refill it
@@ -511,18 +548,26 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                     fetch(nf, wf, rs);
                 }
             }
+#ifdef RACF_MIXWS_PROFILE
+            prof[2] += clock64() - t_fence;  // arrive + refill issue
+#endif
         }
     } else if (RACF_MIXWS_SPLIT_ONLY) {
         // experiment: no LayerNorm roles
-    } else if (warp < kLn2Warp0) {
-        // ---------------------------------------------------------------- LayerNorm 1: D1 -> t (B operand of product 2)
-        const int lw = warp - kLn1Warp0, quarter = warp & 3, half = lw >> 2;   // TMEM lanes of a warp: 32 * (warp % 4)
-        const int row = quarter * 32 + lane;
-        const uint32_t tm_lane = tmem + ((uint32_t)(quarter * 32) << 16) + half * 32;
+    } else {
+        // ---------------------------------------------------------------- LayerNorm warps
+        // LN1: D1 -> t (B operand of product 2); LN2: D2 -> output. Two groups of eight warps, or (kMergedLn) one group
+        // that does LN1(n) and then LN2(n-1).
+        const int lw = (warp - kLn1Warp0) & (kLnWarps - 1), quarter = warp & 3, half = lw >> 2;   // TMEM lanes of a warp: 32 * (warp % 4)
+        const int row = quarter * 32 + lane, col0 = half * 32;
+        const uint32_t tm_row = tmem + ((uint32_t)(quarter * 32) << 16) + col0;
         const bool live = row < p_in;
-        const float cnt = (float)(p_in * kC);
+        const int bar2 = kMergedLn ? 1 : 2;
+        float* red2 = kMergedLn ? red[0] : red[1];
         int flip = 0;
-        for (int n = 0; n < n_local; ++n) {
+        auto ln1_item = [&](int n) {
+            const uint32_t tm_lane = tm_row;
+            const float cnt = (float)(p_in * kC);
             const int b = n & 1;
             float f[32];
             PROGRESS(n * 2);
@@ -533,9 +578,9 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.d1_free[b]));
             const float s = sum32(f);
-            const float mean = ln_group_sum<1>(live ? s : 0.f, red[0], lw, lane, flip) / cnt;
+            const float mean = ln_group_sum(1, live ? s : 0.f, red[0], lw, lane, flip) / cnt;
             const float q = sqdev32(f, mean);
-            const float rstd = rsqrtf(ln_group_sum<1>(live ? q : 0.f, red[0], lw, lane, flip) / cnt + eps);
+            const float rstd = rsqrtf(ln_group_sum(1, live ? q : 0.f, red[0], lw, lane, flip) / cnt + eps);
             PROGRESS(n * 2 + 1);
             MBAR_WAIT(smem_u32(&bars.t_free), (n & 1) ^ 1, 10);    // product 2 of item n-1 has read T3
             if (live) {
@@ -572,15 +617,10 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.t_ready));
-        }
-    } else {
-        // ---------------------------------------------------------------- LayerNorm 2: D2 -> output
-        const int lw = warp - kLn2Warp0, quarter = warp & 3, half = lw >> 2;
-        const int row = quarter * 32 + lane, col0 = half * 32;
-        const uint32_t tm_lane = tmem + ((uint32_t)(quarter * 32) << 16) + col0 + 256;
-        const float cnt = (float)(kPout * kC);
-        int flip = 0;
-        for (int n = 0; n < n_local; ++n) {
+        };
+        auto ln2_item = [&](int n) {
+            const uint32_t tm_lane = tm_row + 256;
+            const float cnt = (float)(kPout * kC);
             const int b = n & 1;
             float f[32];
             PROGRESS(n);
@@ -590,8 +630,8 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars.d2_free[b]));
-            const float mean = ln_group_sum<2>(sum32(f), red[1], lw, lane, flip) / cnt;
-            const float rstd = rsqrtf(ln_group_sum<2>(sqdev32(f, mean), red[1], lw, lane, flip) / cnt + eps);
+            const float mean = ln_group_sum(bar2, sum32(f), red2, lw, lane, flip) / cnt;
+            const float rstd = rsqrtf(ln_group_sum(bar2, sqdev32(f, mean), red2, lw, lane, flip) / cnt + eps);
             const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
             if constexpr (kSplitOut) {
                 // A operand of out_proj, tiled format (linear_tiled.cuh): matrix row = query, k = group * 8192 + o * 64 + c'.
@@ -631,11 +671,22 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                                   make_uint4(__float_as_uint(r[4]), __float_as_uint(r[5]), __float_as_uint(r[6]), __float_as_uint(r[7])));
                 }
             }
+        };
+        if (kMergedLn) {
+            for (int n = 0; n < n_local; ++n) {
+                ln1_item(n);
+                if (n > 0) ln2_item(n - 1);
+            }
+            ln2_item(n_local - 1);
+        } else if (warp < kLn2Warp0) {
+            for (int n = 0; n < n_local; ++n) ln1_item(n);
+        } else {
+            for (int n = 0; n < n_local; ++n) ln2_item(n);
         }
     }
 #ifdef RACF_MIXWS_PROFILE
-    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kSplitWarp0 || warp == kLn1Warp0 + 2 || warp == kLn2Warp0 + 2))
-        printf("mixws CTA0 warp %2d total %lld | raw_empty %lld | xm_ready %lld d1_free %lld s_ready %lld t_ready %lld d2_free %lld | "
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kSplitWarp0 || warp == kLn1Warp0 + 2 || warp == kLn2Warp0 + 3))
+        printf("mixws CTA0 warp %2d total %lld | [splitter: work fence refill | mma: - xm_ready d1_free] %lld %lld %lld s_ready %lld t_ready %lld d2_free %lld | "
                "raw_full %lld xm_free %lld s_free %lld | d1_full %lld t_free %lld d2_full %lld\n", warp, clock64() - t_start, prof[0],
                prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11]);
 #endif

@@ -171,6 +171,45 @@ def test_fused_adaptive_mixing_core_equals_pytorch_chain(p_in, tensor_cores):
     assert err_kernel <= max(2.0 * err_torch, 5e-6), (err_kernel, err_torch)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("qg,p_in", [(4, 96), (148 * 7 + 8, 96), (1000, 64), (40, 48), (40, 80), (52, 16), (300, 32)])
+def test_tensor_core_mixing_kernels_agree_and_are_fp32_grade(qg, p_in, variant):
+    """Both tcgen05 kernels -- phase-serial csrc/mixing_tc.cu (variant 1) and warp-specialised csrc/mixing_ws.cu (variant 2,
+    the default for P_in <= 96) -- on item counts that give a CTA 1..8 items (ring wrap-around, accumulator double buffers,
+    every slot kind of ragged P_in), fp32 and tiled output: error against an fp64 evaluation of
+    AdaptiveMixing.inner_forward (racformer_transformer.py:592-604) within the same bar as the PyTorch fp32 chain, the
+    tiled pieces are the exact split of the kernel's own fp32 result, and the launch is deterministic."""
+    import torch.nn.functional as F
+    from racformer_b200 import linear, points
+    g = torch.Generator(device="cuda").manual_seed(qg * 131 + p_in)
+    C, P_out = 64, 128
+    x = torch.randn(qg, p_in, C, device="cuda", generator=g)
+    params = torch.randn(qg, C * C + P_out * p_in, device="cuda", generator=g) * 0.2
+    m, s = params.double().split([C * C, P_out * p_in], 1)
+    t64 = F.relu(F.layer_norm(torch.matmul(x.double(), m.reshape(qg, C, C)), [p_in, C]))
+    ref64 = F.relu(F.layer_norm(torch.matmul(s.reshape(qg, P_out, p_in), t64), [P_out, C]))
+    got = points.adaptive_mixing_core(x, params, P_out, variant=variant)
+    assert float((got.double() - ref64).abs().max()) <= 5e-6
+    assert torch.equal(got, points.adaptive_mixing_core(x, params, P_out, variant=variant)), "deterministic"
+    tiled = points.adaptive_mixing_core(x, params, P_out, split=True, tiled_groups=4, variant=variant)
+    assert torch.equal(linear.untile(tiled).double().sum(0), got.reshape(qg // 4, -1).double())
+    # the pieces are the round-to-nearest split (largest piece = bf16(x)), as racf_split_bf16x3 produces it
+    assert torch.equal(linear.untile(tiled)[0], got.reshape(qg // 4, -1).to(torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_mixing_variant_selection_errors():
+    from racformer_b200 import _lib, points
+    x = torch.randn(8, 128, 64, device="cuda")
+    params = torch.randn(8, 64 * 64 + 128 * 128, device="cuda")
+    assert points.adaptive_mixing_core(x, params, 128, variant=0) is not None        # falls back to the phase-serial kernel
+    with pytest.raises(RuntimeError):
+        points.adaptive_mixing_core(x, params, 128, variant=2)                       # warp-specialised: P_in <= 96 only
+    with pytest.raises(RuntimeError):
+        points.adaptive_mixing_core(x[:, :96].contiguous(), params[:, :64 * 64 + 128 * 96].contiguous(), 128, variant=7)
+
+
 def test_fused_adaptive_mixing_core_declines_unsupported_shapes():
     from racformer_b200 import points
     x = torch.randn(4, 10, 64, device="cuda")          # in_points not a multiple of 4

@@ -110,8 +110,8 @@ __global__ void check_kernel(const float* __restrict__ in, int n, int* bad_sum, 
 }
 
 int main() {
-    const int blocks = 148 * 8, threads = 256, iters = 2000;
-    const int n = blocks * threads * 8;
+    const int max_blocks = 148 * 8, threads = 256, iters = 2000;
+    const int n = max_blocks * threads * 8;
     std::vector<float> h(n);
     uint32_t s = 12345;
     for (int i = 0; i < n; ++i) {
@@ -121,35 +121,42 @@ int main() {
         h[i] = m * exp2f((float)((int)((s >> 20) & 31) - 16));
     }
     float* in; uint32_t* out; long long* cyc; int* cnt;
-    cudaMalloc(&in, n * 4); cudaMalloc(&out, (size_t)blocks * threads * 12); cudaMalloc(&cyc, 8); cudaMalloc(&cnt, 8);
+    cudaMalloc(&in, n * 4); cudaMalloc(&out, (size_t)max_blocks * threads * 12); cudaMalloc(&cyc, 8); cudaMalloc(&cnt, 8);
     cudaMemcpy(in, h.data(), n * 4, cudaMemcpyHostToDevice);
     printf("{\n");
-    for (int mode = 0; mode < 4; ++mode) {
-        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int rep = 0; rep < 2; ++rep) {
-            cudaEventRecord(e0);
-            if (mode == 0) split_kernel<0><<<blocks, threads>>>(in, out, iters, cyc);
-            if (mode == 1) split_kernel<1><<<blocks, threads>>>(in, out, iters, cyc);
-            if (mode == 2) split_kernel<2><<<blocks, threads>>>(in, out, iters, cyc);
-            if (mode == 3) split_kernel<3><<<blocks, threads>>>(in, out, iters, cyc);
-            cudaEventRecord(e1);
-            cudaEventSynchronize(e1);
+    // occupancy sweep: warps per SM = 64 (8 CTAs x 8 warps), 8, 4, 1 -- the mixing kernels run the split in 7-16 warps per SM
+    const int cfg[4][2] = {{148 * 8, 256}, {148, 256}, {148, 128}, {148, 32}};
+    for (int c = 0; c < 4; ++c) {
+        const int blocks = cfg[c][0], th = cfg[c][1];
+        for (int mode = 0; mode < 4; ++mode) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaEventRecord(e0);
+                if (mode == 0) split_kernel<0><<<blocks, th>>>(in, out, iters, cyc);
+                if (mode == 1) split_kernel<1><<<blocks, th>>>(in, out, iters, cyc);
+                if (mode == 2) split_kernel<2><<<blocks, th>>>(in, out, iters, cyc);
+                if (mode == 3) split_kernel<3><<<blocks, th>>>(in, out, iters, cyc);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+            }
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            long long hcyc = 0;
+            cudaMemcpy(&hcyc, cyc, 8, cudaMemcpyDeviceToHost);
+            int hc[2] = {0, 0};
+            if (mode > 0 && c == 0) {
+                cudaMemset(cnt, 0, 8);
+                if (mode == 1) check_kernel<1><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
+                if (mode == 2) check_kernel<2><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
+                if (mode == 3) check_kernel<3><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
+                cudaMemcpy(hc, cnt, 8, cudaMemcpyDeviceToHost);
+            }
+            const double values = (double)blocks * th * 8 * iters;
+            printf(" \"warps_per_sm_%d_mode%d\": {\"ms\": %.4f, \"values_per_clk_per_sm\": %.2f, \"cycles_per_8_values_per_warp\": %.1f, "
+                   "\"sum_not_exact\": %d, \"pieces_differ_from_cvt\": %d},\n", blocks * th / 32 / 148, mode, ms,
+                   values / (ms * 1e-3) / 148.0 / 1.965e9, (double)hcyc / iters, hc[0], hc[1]);
         }
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        int hc[2] = {0, 0};
-        if (mode > 0) {
-            cudaMemset(cnt, 0, 8);
-            if (mode == 1) check_kernel<1><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
-            if (mode == 2) check_kernel<2><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
-            if (mode == 3) check_kernel<3><<<(n / 2 + 255) / 256, 256>>>(in, n, cnt, cnt + 1);
-            cudaMemcpy(hc, cnt, 8, cudaMemcpyDeviceToHost);
-        }
-        const double values = (double)blocks * threads * 8 * iters;
-        // 8 resident CTAs of 256 threads per SM = 64 warps: full occupancy; values per clock per SM at 1.965 GHz
-        printf(" \"mode%d\": {\"ms\": %.4f, \"values_per_clk_per_sm\": %.2f, \"sum_not_exact\": %d, \"pieces_differ_from_cvt\": %d}%s\n", mode, ms,
-               values / (ms * 1e-3) / 148.0 / 1.965e9, hc[0], hc[1], mode < 3 ? "," : "");
     }
-    printf("}\n");
+    printf(" \"modes\": \"0 cvt.rn.bf16x2 (F2FP), 1 Veltkamp scalar, 2 Veltkamp f32x2, 3 integer RNE\"\n}\n");
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
