@@ -408,10 +408,22 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                 umma_commit(smem_u32(&bars.t_free));
                 umma_commit(smem_u32(&bars.d2_full[b]));
             };
-            product1(0);
-            for (int n = 0; n < n_local; ++n) {
-                if (n + 1 < n_local) product1(n + 1);
-                product2(n);
+            // Issue whichever product is ready, product 2 first (it is on the critical path: S3 and T3 are single-buffered
+            // and free only when it has completed). A fixed order -- product 1 of item n+1 before product 2 of item n --
+            // parks product 2 behind the splitters' x / M slots of the NEXT item (measured: 171 -> see DESIGN.md 3a).
+            auto ready1 = [&](int n) {
+                return mbar_try_wait(smem_u32(&bars.xm_ready), n & 1) && mbar_try_wait(smem_u32(&bars.d1_free[n & 1]), ((n >> 1) & 1) ^ 1);
+            };
+            auto ready2 = [&](int n) {
+                return mbar_try_wait(smem_u32(&bars.s_ready), n & 1) && mbar_try_wait(smem_u32(&bars.t_ready), n & 1) &&
+                       mbar_try_wait(smem_u32(&bars.d2_free[n & 1]), ((n >> 1) & 1) ^ 1);
+            };
+            int n1 = 0, n2 = 0;                     // next product 1 / product 2 to issue
+            uint32_t idle = 0;
+            while (n2 < n_local) {
+                if (n2 < n1 && ready2(n2)) { product2(n2); ++n2; idle = 0; }
+                else if (n1 < n_local && n1 < n2 + 2 && ready1(n1)) { product1(n1); ++n1; idle = 0; }
+                else if (++idle > (1u << 24)) mbar_timeout(smem_u32(&bars.xm_ready), (uint32_t)(n1 & 1), 1);
             }
         }
     } else if (warp < kLn1Warp0) {
