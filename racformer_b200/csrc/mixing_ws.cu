@@ -129,15 +129,18 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int t
 #ifndef RACF_MIXWS_BACKOFF_NS
 #define RACF_MIXWS_BACKOFF_NS 64
 #endif
-// wait sites 0 (raw_empty), 6 (raw_full): ring hand-offs; 1-5: MMA issuer; the rest: splitters / LayerNorm on MMA results
-#define mbar_wait(bar, parity, tag) mbar_wait_t<((tag) == 0 || (tag) == 6 || ((tag) >= 1 && (tag) <= 5)) ? 0 : RACF_MIXWS_BACKOFF_NS>(bar, parity, tag)
+// wait sites 1-5: MMA issuer; 6 (raw_full), 7 (xm_free), 8 (s_free): splitters; 9-11: LayerNorm warps waiting for MMA results
+#ifndef RACF_MIXWS_NOSLEEP_MAX_TAG
+#define RACF_MIXWS_NOSLEEP_MAX_TAG 6
+#endif
+#define mbar_wait(bar, parity, tag) mbar_wait_t<((tag) <= RACF_MIXWS_NOSLEEP_MAX_TAG) ? 0 : RACF_MIXWS_BACKOFF_NS>(bar, parity, tag)
 #ifdef RACF_MIXWS_PROFILE      // tuning aid: cycles each role of CTA 0 spends waiting on each barrier (RACF_NVCC_DEFINES=-DRACF_MIXWS_PROFILE)
 #define MBAR_WAIT(bar, parity, slot) do { const long long t_ = clock64(); mbar_wait(bar, parity, slot); prof[slot] += clock64() - t_; } while (0)
 #else
 #define MBAR_WAIT(bar, parity, slot) mbar_wait(bar, parity, slot)
 #endif
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
