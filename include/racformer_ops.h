@@ -299,7 +299,10 @@ int racf_adaptive_mixing_backward(const float* x, const float* params, const flo
  *   [3][N][K] (nn.Linear's weight layout), products a_i * w_j with i + j <= max_order accumulated in fp32 (4: all nine,
  *   2: six). bias may be NULL. K % 8 == 0. workspace: split_k * M * N floats when split_k > 1 (else may be NULL).
  *   variant: 0 = plain pieces through tensor maps, 32-wide K blocks / 64-byte swizzle / 2 stages; 1 = the same with
- *   64-wide K blocks / 128-byte swizzle / 1 stage; 2 = a3 and w3 are in the tiled format (bulk copies, any K).
+ *   64-wide K blocks / 128-byte swizzle / 1 stage; 2 = a3 and w3 are in the tiled format (bulk copies, any K);
+ *   3 = tiled operands, 128 x 256 output tiles on persistent warp-specialised CTAs (csrc/linear_wide.cu: 25 % less
+ *   L2 -> SM operand traffic, the binding resource of variant 2). Variants 2 and 3 issue the same MMAs in the same order
+ *   per accumulator and give bit-identical results.
  */
 int racf_split_bf16x3(const float* x, long long count, void* out3, racf_stream_t stream);
 /* (in [batch][channels][positions] + pos [channels][positions] (may be NULL)) -> out3 [3][batch * positions][channels]:

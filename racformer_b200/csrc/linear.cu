@@ -120,6 +120,38 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ bool elect_one_lane() {      // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_plain(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// All MMAs of one K block of kBK: piece products a_i * w_j with i + j <= kMaxOrder, smallest terms first; the cross terms
+// accumulate in TMEM columns [128,256), a0 * w0 in [0,128). a_desc / w_desc: descriptors of piece 0, K step 0 of the
+// stage; the other tiles are constant offsets (address field in 16-byte units). first == 0: overwrite.
+template <int kBK, int kPieceBytes, int kMaxOrder>
+__device__ __forceinline__ void issue_kblock(uint32_t tmem, uint64_t a_desc, uint64_t w_desc, uint32_t idesc, uint32_t first) {
+    uint32_t acc_cross = first;
+#pragma unroll
+    for (int ks = 0; ks < kBK / 16; ++ks) {
+#pragma unroll
+        for (int order = kMaxOrder; order >= 1; --order) {
+#pragma unroll
+            for (int pa = 0; pa <= 2; ++pa) {
+                const int pw = order - pa;
+                if (pw < 0 || pw > 2) continue;
+                umma_bf16(tmem + kLinBN, a_desc + (uint64_t)((pa * kPieceBytes + ks * 32) >> 4),
+                          w_desc + (uint64_t)((pw * kPieceBytes + ks * 32) >> 4), idesc, acc_cross);
+                acc_cross = 1;
+            }
+        }
+        umma_bf16(tmem, a_desc + (uint64_t)((ks * 32) >> 4), w_desc + (uint64_t)((ks * 32) >> 4), idesc, (ks > 0) ? 1u : first);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // GEMM kernel
 // ---------------------------------------------------------------------------------------------------------------------
@@ -209,34 +241,34 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 tma_load_3d(dst + 3 * kPieceBytes, &map_w, k0, n0, 0, full_bar(s));
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
+        // The whole warp walks the (warp-uniform) loop and one elected lane issues; the term loops are unrolled at compile
+        // time for the usual orders and a tile's descriptor is the stage's base descriptor plus a constant. Issued from a
+        // single divergent lane with run-time term loops, every tcgen05.mma cost ~190 cycles of descriptor arithmetic in the
+        // uniform datapath inside a compiler-generated convergence loop (csrc/linear_wide.cu measured it): three MMAs' worth.
         constexpr uint32_t idesc = umma_idesc_bf16(kLinBM, kLinBN);
-        const uint32_t d_main = tmem_base, d_cross = tmem_base + kLinBN;
-        uint32_t acc_cross = 0;
+        const uint64_t desc0 = umma_desc<kRowBytes>(smem_base);
         for (int i = 0; i < num_kb; ++i) {
             const int s = i % kStages;
             mbar_wait(full_bar(s), (i / kStages) & 1);
             tcgen05_fence_after();
-            const uint32_t a_base = smem_base + s * kStageBytes, w_base = a_base + 3 * kPieceBytes;
-#pragma unroll
-            for (int ks = 0; ks < kBK / 16; ++ks) {
-                // smallest terms first; a 16-element K step is 32 bytes further inside the swizzle span
-                for (int order = args.max_order; order >= 1; --order) {
-                    for (int pa = 0; pa <= 2; ++pa) {
-                        const int pw = order - pa;
-                        if (pw < 0 || pw > 2) continue;
-                        umma_bf16(d_cross, umma_desc<kRowBytes>(a_base + pa * kPieceBytes + ks * 32),
-                                  umma_desc<kRowBytes>(w_base + pw * kPieceBytes + ks * 32), idesc, acc_cross);
-                        acc_cross = 1;
-                    }
+            if (elect_one_lane()) {
+                const uint64_t a_desc = desc0 + (uint64_t)((s * kStageBytes) >> 4), w_desc = a_desc + (uint64_t)((3 * kPieceBytes) >> 4);
+                const uint32_t first = i == 0 ? 0u : 1u;
+                switch (args.max_order) {
+                    case 2: issue_kblock<kBK, kPieceBytes, 2>(tmem_base, a_desc, w_desc, idesc, first); break;
+                    case 4: issue_kblock<kBK, kPieceBytes, 4>(tmem_base, a_desc, w_desc, idesc, first); break;
+                    case 0: issue_kblock<kBK, kPieceBytes, 0>(tmem_base, a_desc, w_desc, idesc, first); break;
+                    case 1: issue_kblock<kBK, kPieceBytes, 1>(tmem_base, a_desc, w_desc, idesc, first); break;
+                    default: issue_kblock<kBK, kPieceBytes, 3>(tmem_base, a_desc, w_desc, idesc, first); break;
                 }
-                umma_bf16(d_main, umma_desc<kRowBytes>(a_base + ks * 32), umma_desc<kRowBytes>(w_base + ks * 32), idesc,
-                          (i > 0 || ks > 0) ? 1u : 0u);
+                umma_commit(empty_bar(s));     // the stage may be refilled once these MMAs have read it
+                if (i == num_kb - 1) umma_commit(tmem_full_bar);        // accumulators complete
             }
-            umma_commit(empty_bar(s));     // the stage may be refilled once these MMAs have read it
+            __syncwarp();
         }
-        umma_commit(tmem_full_bar);        // accumulators complete
+        if (num_kb == 0 && lane == 0) mbar_arrive_plain(tmem_full_bar);   // nothing to wait for (cannot happen: no empty splits)
     }
     __syncwarp();
 
@@ -534,14 +566,17 @@ extern "C" int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long l
     return RACF_OK;
 }
 
+int racf_linear_wide_launch(const void* a_tiled, const void* w_tiled, const float* bias, float* out, int M, int N, int num_kblocks,
+                            int kblocks_per_split, int num_splits, int max_order, cudaStream_t st);   // csrc/linear_wide.cu
+
 extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
                                           int max_order, int split_k, int variant, float* workspace, float* out,
                                           racf_stream_t stream) {
     using namespace racf;
     if (!a3 || !w3 || !out) return RACF_ERR_NULL_POINTER;
     if (M <= 0 || N <= 0 || K <= 0 || split_k <= 0) return RACF_ERR_BAD_SHAPE;
-    if (variant < 0 || variant > 2 || max_order < 0 || max_order > 4) return RACF_ERR_UNSUPPORTED;
-    if (variant != 2 && (K & 7) != 0) return RACF_ERR_UNSUPPORTED;                     // tensor maps: 16-byte global strides
+    if (variant < 0 || variant > 3 || max_order < 0 || max_order > 4) return RACF_ERR_UNSUPPORTED;
+    if (variant < 2 && (K & 7) != 0) return RACF_ERR_UNSUPPORTED;                      // tensor maps: 16-byte global strides
     if ((reinterpret_cast<uintptr_t>(a3) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(out)) & 15u)
         return RACF_ERR_UNSUPPORTED;
     if (split_k > 1 && (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15u))) return RACF_ERR_NULL_POINTER;
@@ -553,7 +588,19 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
 
     CUtensorMap ma, mw;
     int rc = 0;
-    if (variant != 2) {
+    if (variant == 3) {                  // 128 x 256 tiles, persistent CTAs (csrc/linear_wide.cu); tiled operands
+        cudaStream_t st3 = static_cast<cudaStream_t>(stream);
+        rc = racf_linear_wide_launch(a3, w3, bias, split_k > 1 ? workspace : out, M, N, num_kblocks, kbps, split_k, max_order, st3);
+        if (rc != 0) return rc;
+        if (split_k > 1) {
+            const long long mn = (long long)M * N;
+            const long long threads = (mn + 3) / 4;
+            linear_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st3>>>(workspace, bias, out, mn, N, split_k);
+            return (int)cudaGetLastError();
+        }
+        return RACF_OK;
+    }
+    if (variant < 2) {
         rc = make_operand_map(&ma, a3, M, K, bk);
         if (rc != 0) return rc;
         rc = make_operand_map(&mw, w3, N, K, bk);

@@ -248,6 +248,12 @@ __device__ __forceinline__ void split_store8(const float (&f)[8], uint8_t* tile,
 #endif
 }
 
+__device__ __forceinline__ bool elect_one() {      // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 struct Bars {                       // all mbarriers of the CTA
     uint64_t raw_full[kRing];
     uint64_t xm_ready, s_ready, t_ready, t_free;
@@ -355,57 +361,55 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
 
     if (warp == 0) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0 && !RACF_MIXWS_SPLIT_ONLY) {
+        // The whole warp runs the (warp-uniform) event loop and one elected lane issues the MMAs: from a single divergent
+        // lane the compiler wraps every tcgen05.mma in a convergence loop and rebuilds both descriptors in the uniform
+        // datapath (~190 cycles per MMA, measured in csrc/linear_wide.cu; 60 MMAs per item). Descriptors are a base
+        // descriptor plus compile-time constants (address field in 16-byte units).
+        if (!RACF_MIXWS_SPLIT_ONLY) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             constexpr uint32_t idesc2 = idesc | (kTMajorMN ? (1u << 16) : 0u);
+            constexpr int kOrder = RACF_MIXWS_EXP == 5 ? 0 : 2;
             const int ksteps2 = p_in >> 4;
-            auto product1 = [&](int n) {       // D1[b] = X3 @ M3^T
+            const uint64_t dx = desc_kmajor<128>(sm_addr + kX3), dm = desc_kmajor<128>(sm_addr + kM3);
+            const uint64_t ds = desc_kmajor<64>(sm_addr + kS3);
+            const uint64_t dt = kTMajorMN ? desc_mnmajor_sw128(sm_addr + kT3) : desc_kmajor<64>(sm_addr + kT3);
+            auto product1 = [&](int n) {       // D1[b] = X3 @ M3^T   (one elected lane)
                 const int b = n & 1;
-                PROGRESS(n * 2);
-                MBAR_WAIT(smem_u32(&bars.xm_ready), n & 1, 1);
-                MBAR_WAIT(smem_u32(&bars.d1_free[b]), ((n >> 1) & 1) ^ 1, 2);
                 tc_fence_after();
                 const uint32_t d_main = tmem + b * 128, d_cross = d_main + 64;
                 uint32_t acc_cross = 0;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                    for (int order = (RACF_MIXWS_EXP == 5 ? 0 : 2); order >= 1; --order)
+                    for (int order = kOrder; order >= 1; --order)
 #pragma unroll
                         for (int pa = 0; pa <= order; ++pa) {
-                            umma_bf16(d_cross, desc_kmajor<128>(sm_addr + kX3 + pa * kXPiece + ks * 32),
-                                      desc_kmajor<128>(sm_addr + kM3 + (order - pa) * kMPiece + ks * 32), idesc, acc_cross);
+                            umma_bf16(d_cross, dx + (uint64_t)((pa * kXPiece + ks * 32) >> 4),
+                                      dm + (uint64_t)(((order - pa) * kMPiece + ks * 32) >> 4), idesc, acc_cross);
                             acc_cross = 1;
                         }
-                    umma_bf16(d_main, desc_kmajor<128>(sm_addr + kX3 + ks * 32), desc_kmajor<128>(sm_addr + kM3 + ks * 32), idesc, ks > 0);
+                    umma_bf16(d_main, dx + (uint64_t)((ks * 32) >> 4), dm + (uint64_t)((ks * 32) >> 4), idesc, ks > 0);
                 }
                 umma_commit(smem_u32(&bars.xm_free[n & 3]));
                 umma_commit(smem_u32(&bars.d1_full[b]));
             };
             auto product2 = [&](int n) {       // D2[b] = S3 @ t
                 const int b = n & 1;
-                PROGRESS(n * 2 + 1);
-                MBAR_WAIT(smem_u32(&bars.s_ready), n & 1, 3);
-                MBAR_WAIT(smem_u32(&bars.t_ready), n & 1, 4);
-                MBAR_WAIT(smem_u32(&bars.d2_free[b]), ((n >> 1) & 1) ^ 1, 5);
                 tc_fence_after();
                 const uint32_t d_main = tmem + 256 + b * 128, d_cross = d_main + 64;
                 uint32_t acc_cross = 0;
                 for (int ks = 0; ks < ksteps2; ++ks) {
-                    const uint32_t a_off = (ks >> 1) * 8192 + (ks & 1) * 32;
-                    const uint32_t b_off = kTMajorMN ? ks * 2048 : (ks >> 1) * 4096 + (ks & 1) * 32;
+                    const uint64_t a_off = (uint64_t)(((ks >> 1) * 8192 + (ks & 1) * 32) >> 4);
+                    const uint64_t b_off = (uint64_t)((kTMajorMN ? ks * 2048 : (ks >> 1) * 4096 + (ks & 1) * 32) >> 4);
 #pragma unroll
-                    for (int order = (RACF_MIXWS_EXP == 5 ? 0 : 2); order >= 1; --order)
+                    for (int order = kOrder; order >= 1; --order)
 #pragma unroll
                         for (int pa = 0; pa <= order; ++pa) {
-                            const uint32_t ta = sm_addr + kT3 + (order - pa) * kTPiece + b_off;
-                            umma_bf16(d_cross, desc_kmajor<64>(sm_addr + kS3 + pa * kSPiece + a_off),
-                                      kTMajorMN ? desc_mnmajor_sw128(ta) : desc_kmajor<64>(ta), idesc2, acc_cross);
+                            umma_bf16(d_cross, ds + a_off + (uint64_t)((pa * kSPiece) >> 4), dt + b_off + (uint64_t)(((order - pa) * kTPiece) >> 4),
+                                      idesc2, acc_cross);
                             acc_cross = 1;
                         }
-                    const uint32_t t0 = sm_addr + kT3 + b_off;
-                    umma_bf16(d_main, desc_kmajor<64>(sm_addr + kS3 + a_off), kTMajorMN ? desc_mnmajor_sw128(t0) : desc_kmajor<64>(t0),
-                              idesc2, ks > 0);
+                    umma_bf16(d_main, ds + a_off, dt + b_off, idesc2, ks > 0);
                 }
                 umma_commit(smem_u32(&bars.s_free[n & 3]));
                 umma_commit(smem_u32(&bars.t_free));
@@ -413,7 +417,7 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             };
             // Issue whichever product is ready, product 2 first (it is on the critical path: S3 and T3 are single-buffered
             // and free only when it has completed). A fixed order -- product 1 of item n+1 before product 2 of item n --
-            // parks product 2 behind the splitters' x / M slots of the NEXT item (measured: 171 -> see DESIGN.md 3a).
+            // parks product 2 behind the splitters' x / M slots of the NEXT item (measured: 176 -> 137 us).
             auto ready1 = [&](int n) {
                 return mbar_try_wait(smem_u32(&bars.xm_ready), n & 1) && mbar_try_wait(smem_u32(&bars.d1_free[n & 1]), ((n >> 1) & 1) ^ 1);
             };
@@ -424,9 +428,22 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
             int n1 = 0, n2 = 0;                     // next product 1 / product 2 to issue
             uint32_t idle = 0;
             while (n2 < n_local) {
-                if (n2 < n1 && ready2(n2)) { product2(n2); ++n2; idle = 0; }
-                else if (n1 < n_local && n1 < n2 + 2 && ready1(n1)) { product1(n1); ++n1; idle = 0; }
-                else if (++idle > (1u << 24)) mbar_timeout(smem_u32(&bars.xm_ready), (uint32_t)(n1 & 1), 1);
+                // the readiness tests are made warp-uniform: a barrier may complete between two lanes' polls
+                const bool r2 = n2 < n1 && __all_sync(0xffffffffu, ready2(n2));
+                const bool r1 = !r2 && n1 < n_local && n1 < n2 + 2 && __all_sync(0xffffffffu, ready1(n1));
+                if (r2) {
+                    PROGRESS(n2 * 2 + 1);
+                    if (elect_one()) product2(n2);
+                    __syncwarp();
+                    ++n2; idle = 0;
+                } else if (r1) {
+                    PROGRESS(n1 * 2);
+                    if (elect_one()) product1(n1);
+                    __syncwarp();
+                    ++n1; idle = 0;
+                } else if (++idle > (1u << 24)) {
+                    mbar_timeout(smem_u32(&bars.xm_ready), (uint32_t)(n1 & 1), 1);
+                }
             }
         }
     } else if (warp < kLn1Warp0) {

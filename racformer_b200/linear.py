@@ -116,13 +116,18 @@ def plan(M, N, K):
     return s.value, w.value
 
 
+WIDE_TILES = True     # TiledOperands: 128 x 256 tiles on persistent CTAs (csrc/linear_wide.cu) instead of 128 x 128 tiles
+
+
 def linear_bf16x3(a3, w3, bias=None, max_order=ALL_TERMS, split_k=None, variant=0):
     """a3 [3, M, K], w3 [3, N, K] (bf16 pieces from split_bf16x3) or two TiledOperands, bias [N] fp32 or None
-    -> [M, N] fp32."""
+    -> [M, N] fp32. TiledOperands run as variant 3 (wide tiles; bit-identical to variant 2) when N > 128 unless the module
+    switch WIDE_TILES is off; `variant` only selects between the two plain-piece kernels (0 / 1)."""
     if isinstance(a3, TiledOperand) or isinstance(w3, TiledOperand):
         if not (isinstance(a3, TiledOperand) and isinstance(w3, TiledOperand)) or a3.K != w3.K or a3.device != w3.device:
             raise RuntimeError("linear_bf16x3: both operands must be TiledOperands with the same K on one device")
-        M, K, N, variant = a3.rows, a3.K, w3.rows, 2
+        M, K, N = a3.rows, a3.K, w3.rows
+        variant = 3 if (WIDE_TILES and N > 128) else 2
         a_ptr, w_ptr, dev = a3.buf.data_ptr(), w3.buf.data_ptr(), a3.device
     else:
         if not (a3.is_cuda and w3.is_cuda and a3.dtype == torch.bfloat16 and w3.dtype == torch.bfloat16
