@@ -567,7 +567,7 @@ extern "C" int racf_linear_bf16x3_plan(int M, int N, int K, int* split_k, long l
 }
 
 int racf_linear_wide_launch(const void* a_tiled, const void* w_tiled, const float* bias, float* out, int M, int N, int num_kblocks,
-                            int kblocks_per_split, int num_splits, int max_order, cudaStream_t st);   // csrc/linear_wide.cu
+                            int kblocks_per_pass, int kblocks_per_split, int num_splits, int max_order, cudaStream_t st);   // csrc/linear_wide.cu
 
 extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const float* bias, int M, int N, int K,
                                           int max_order, int split_k, int variant, float* workspace, float* out,
@@ -590,12 +590,25 @@ extern "C" int racf_linear_bf16x3_forward(const void* a3, const void* w3, const 
     int rc = 0;
     if (variant == 3) {                  // 128 x 256 tiles, persistent CTAs (csrc/linear_wide.cu); tiled operands
         cudaStream_t st3 = static_cast<cudaStream_t>(stream);
-        rc = racf_linear_wide_launch(a3, w3, bias, split_k > 1 ? workspace : out, M, N, num_kblocks, kbps, split_k, max_order, st3);
+        // split_k passes of kbps K blocks (<= 512 of K per tensor-memory accumulator). A work item takes several consecutive
+        // passes and adds them in registers: as few work items as still fill the SMs once, and a workspace / reduction
+        // that is as many times smaller (the caller's workspace is sized for split_k slabs; the first `splits` are used).
+        int dev = 0, sms = 0;
+        cudaError_t e3 = cudaGetDevice(&dev);
+        if (e3 == cudaSuccess) e3 = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e3 != cudaSuccess) return (int)e3;
+        const long long base_tiles = (long long)((M + 127) / 128) * (((N + 127) / 128 + 1) / 2);
+        long long ppi = ((long long)split_k * base_tiles + sms - 1) / sms;          // passes per work item
+        if (ppi < 1) ppi = 1;
+        if (ppi > split_k) ppi = split_k;
+        const int splits = (int)((split_k + ppi - 1) / ppi);
+        rc = racf_linear_wide_launch(a3, w3, bias, splits > 1 ? workspace : out, M, N, num_kblocks, kbps, (int)ppi * kbps, splits,
+                                     max_order, st3);
         if (rc != 0) return rc;
-        if (split_k > 1) {
+        if (splits > 1) {
             const long long mn = (long long)M * N;
             const long long threads = (mn + 3) / 4;
-            linear_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st3>>>(workspace, bias, out, mn, N, split_k);
+            linear_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st3>>>(workspace, bias, out, mn, N, splits);
             return (int)cudaGetLastError();
         }
         return RACF_OK;

@@ -12,8 +12,8 @@
 //     (cross terms): all 512 columns, so one CTA per SM. The MMAs read 12 KB of shared memory per 256 columns instead of
 //     16 KB -- the tensor pipe of these small-K-block MMAs is fed at the shared-memory bandwidth;
 //   * the CTA is persistent (tile = blockIdx.x + i * gridDim.x, m fastest so that concurrent CTAs share W blocks in L2)
-//     and warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-9 = epilogue. The producer runs
-//     ahead into the NEXT tile while the epilogue drains tensor memory, so the operand stream -- the binding resource --
+//     and warp-specialised: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2-17 = epilogue. The producer runs
+//     ahead into the NEXT tile while the epilogue (warps 2-17) drains tensor memory, so the operand stream -- the binding resource --
 //     does not stop at tile boundaries (linear_bf16x3_kernel relies on a second CTA per SM for that);
 //   * the epilogue first drains tensor memory into registers (128 values per thread) and hands it back to the MMA warp,
 //     then writes the tile through a small staging block per warp (8 rows x 32 columns) in 128-byte row segments.
@@ -33,7 +33,7 @@ constexpr int kBM = 128, kStages = 2;                            // tile 128 x 2
 constexpr int kPieceBytes = kTilePieceElems * 2;                 // 8 KB: [128 rows][32 k] bf16, 64-byte rows, 64-byte swizzle
 constexpr int kABytes = 3 * kPieceBytes, kWHalfBytes = 3 * kPieceBytes;
 constexpr int kStageBytes = kABytes + 2 * kWHalfBytes;           // 72 KB
-constexpr int kEpiWarps = 8, kThreads = 32 * (2 + kEpiWarps);    // 320
+constexpr int kEpiWarps = 16, kThreads = 32 * (2 + kEpiWarps);   // 576: an epilogue thread owns 64 columns of one row
 constexpr int kStgRows = 32, kStgStride = 36;                    // epilogue staging: 32 rows x 32 columns per warp (+4: conflict-free)
 constexpr int kStgBytes = kStgRows * kStgStride * 4;
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStgBytes;
@@ -46,7 +46,11 @@ struct Args {
     float* out;               // [M, N] (num_splits == 1) or workspace [num_splits, M, N]
     int M, N;
     int m_tiles, n_tiles128, n_pairs;
-    int num_kblocks, kblocks_per_split, num_splits;
+    int num_kblocks;
+    int kblocks_per_pass;     // K blocks accumulated in tensor memory before the epilogue takes the partial sum (<= 16: K <= 512
+                              // per accumulator, see csrc/linear.cu on the truncating accumulation)
+    int kblocks_per_split;    // K blocks of one work item = passes_per_split * kblocks_per_pass; its passes are added in registers
+    int num_splits;
     int max_order;
     int num_tiles;            // m_tiles * n_pairs * num_splits
 };
@@ -108,6 +112,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major [128 rows][32 k] bf16 tile, 64-byte rows, 64-byte swizzle: 8-row groups 512 bytes apart
@@ -175,22 +184,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
 #endif
 
     // tile -> (m_tile, n_pair, split): m fastest
-    auto decode = [&](int tile, int& m_tile, int& n_pair, int& kb_begin, int& num_kb, int& split) {
-        m_tile = tile % args.m_tiles;
-        const int rest = tile / args.m_tiles;
-        n_pair = rest % args.n_pairs;
-        split = rest / args.n_pairs;
-        kb_begin = split * args.kblocks_per_split;
-        num_kb = min(kb_begin + args.kblocks_per_split, args.num_kblocks) - kb_begin;
-    };
+#define LINW_DECODE(tile)                                                                                   \
+    const int m_tile = (tile) % args.m_tiles, rest_ = (tile) / args.m_tiles;                                \
+    const int n_pair = rest_ % args.n_pairs, split = rest_ / args.n_pairs;                                  \
+    const int kb_begin = split * args.kblocks_per_split;                                                    \
+    const int num_kb = min(kb_begin + args.kblocks_per_split, args.num_kblocks) - kb_begin;
 
     if (warp == 0) {
         // ===== bulk-copy producer: runs ahead of the MMA warp across tile boundaries =====
         if (lane == 0) {
             uint32_t it = 0;                       // K blocks issued so far (ring position)
             for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-                int m_tile, n_pair, kb_begin, num_kb, split;
-                decode(tile, m_tile, n_pair, kb_begin, num_kb, split);
+                LINW_DECODE(tile)
                 const bool two = 2 * n_pair + 1 < args.n_tiles128;
                 const uint8_t* a_src = args.a_tiled + ((long long)m_tile * args.num_kblocks + kb_begin) * kTileStageBytes;
                 const uint8_t* w_src = args.w_tiled + ((long long)(2 * n_pair) * args.num_kblocks + kb_begin) * kTileStageBytes;
@@ -223,71 +228,82 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
         constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         constexpr uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         const uint64_t desc0 = umma_desc64(smem_base);
-        uint32_t it = 0, tile_iter = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++tile_iter) {
-            int m_tile, n_pair, kb_begin, num_kb, split;
-            decode(tile, m_tile, n_pair, kb_begin, num_kb, split);
+        uint32_t it = 0, pass_iter = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            LINW_DECODE(tile)
             const bool two = 2 * n_pair + 1 < args.n_tiles128;
-            MBAR_WAIT(tmem_empty, (tile_iter & 1) ^ 1, 1);         // the epilogue has read the previous tile's accumulators
-            tc_fence_after();
-            for (int i = 0; i < num_kb; ++i, ++it) {
-                const int s = it % kStages;
-                MBAR_WAIT(full_bar(s), (it / kStages) & 1, 2);
+            for (int p0 = 0; p0 < num_kb; p0 += args.kblocks_per_pass, ++pass_iter) {
+                const int pass_kb = min(args.kblocks_per_pass, num_kb - p0);
+                MBAR_WAIT(tmem_empty, (pass_iter & 1) ^ 1, 1);     // the epilogue has read the previous pass's accumulators
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t a_desc = desc0 + (uint64_t)((s * kStageBytes) >> 4), w_desc = a_desc + (kABytes >> 4);
-                    const uint32_t first = i == 0 ? 0u : 1u;
-                    const uint32_t idesc = two ? idesc256 : idesc128;     // N = 256: both 128-row blocks of W in one MMA
-                    if (args.max_order == 2) issue_kblock<2>(tmem, a_desc, w_desc, idesc, first);
-                    else if (args.max_order == 4) issue_kblock<4>(tmem, a_desc, w_desc, idesc, first);
-                    else if (args.max_order == 0) issue_kblock<0>(tmem, a_desc, w_desc, idesc, first);
-                    else if (args.max_order == 1) issue_kblock<1>(tmem, a_desc, w_desc, idesc, first);
-                    else issue_kblock<3>(tmem, a_desc, w_desc, idesc, first);
-                    umma_commit(empty_bar(s));     // the stage may be refilled once these MMAs have read it
-                    if (i == num_kb - 1) umma_commit(tmem_full);   // accumulators of this tile complete
+                for (int i = 0; i < pass_kb; ++i, ++it) {
+                    const int s = it % kStages;
+                    MBAR_WAIT(full_bar(s), (it / kStages) & 1, 2);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a_desc = desc0 + (uint64_t)((s * kStageBytes) >> 4), w_desc = a_desc + (kABytes >> 4);
+                        const uint32_t first = i == 0 ? 0u : 1u;
+                        const uint32_t idesc = two ? idesc256 : idesc128;     // N = 256: both 128-row blocks of W in one MMA
+                        if (args.max_order == 2) issue_kblock<2>(tmem, a_desc, w_desc, idesc, first);
+                        else if (args.max_order == 4) issue_kblock<4>(tmem, a_desc, w_desc, idesc, first);
+                        else if (args.max_order == 0) issue_kblock<0>(tmem, a_desc, w_desc, idesc, first);
+                        else if (args.max_order == 1) issue_kblock<1>(tmem, a_desc, w_desc, idesc, first);
+                        else issue_kblock<3>(tmem, a_desc, w_desc, idesc, first);
+                        umma_commit(empty_bar(s));     // the stage may be refilled once these MMAs have read it
+                        if (i == pass_kb - 1) umma_commit(tmem_full);   // accumulators of this pass complete
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
-        // ===== epilogue: warp e owns TMEM lanes 32 * (warp % 4) and the 128-column half e / 4 of the tile =====
-        const int e = warp - 2, quarter = warp & 3, half = e >> 2;
+        // ===== epilogue: warp e owns TMEM lanes 32 * (warp % 4) and 64 of the tile's 256 columns =====
+        const int e = warp - 2, quarter = warp & 3, cq = e >> 2, half = cq >> 1;     // cq: column quarter, half: 128-row block of W
         float* stg = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kStages * kStageBytes + e * kStgBytes);
-        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + half * 128;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + cq * 64;
         const bool has_cross = args.max_order >= 1;
-        uint32_t tile_iter = 0;
-        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++tile_iter) {
-            int m_tile, n_pair, kb_begin, num_kb, split;
-            decode(tile, m_tile, n_pair, kb_begin, num_kb, split);
+        uint32_t pass_iter = 0;
+        for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+            LINW_DECODE(tile)
             const int n_tile = 2 * n_pair + half;
             const bool active = n_tile < args.n_tiles128;
-            MBAR_WAIT(tmem_full, tile_iter & 1, 3);
-            tc_fence_after();
-#ifdef RACF_LINW_PROFILE
-            const long long t_ready = clock64();
-#endif
             float* outp = args.out + (long long)split * args.M * args.N;
             const float* biasp = args.num_splits == 1 ? args.bias : nullptr;
             const int m0 = m_tile * kBM + quarter * 32;
-            // Drain tensor memory into registers first (128 values per thread: the launch bound leaves 204 registers) and hand
-            // it back to the MMA warp BEFORE the stores: the accumulators are single-buffered (all 512 columns), so whatever
-            // the epilogue does while it still holds them is serial with the next tile's MMAs.
-            float f[4][32];
-            if (active) {
+            // Drain tensor memory into registers (64 values per thread) and hand it back to the MMA warp BEFORE the stores:
+            // the accumulators are single-buffered (all 512 columns), so whatever the epilogue does while it still holds
+            // them is serial with the next MMAs. The passes of a work item (K > 512 per split) are added here in fp32,
+            // in order -- fewer, longer work items and a K-split workspace that is passes_per_split times smaller.
+            float f[2][32];
+            for (int p0 = 0; p0 < num_kb; p0 += args.kblocks_per_pass, ++pass_iter) {
+                MBAR_WAIT(tmem_full, pass_iter & 1, 3);
+                tc_fence_after();
+#ifdef RACF_LINW_PROFILE
+                const long long t_ready = clock64();
+#endif
+                if (active) {
+                    const bool first_pass = p0 == 0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {                       // 16 columns at a time (register budget)
-                    uint32_t v[16], u[16];
-                    tmem_ld16(lane_addr + c * 16, v);
-                    if (has_cross) tmem_ld16(lane_addr + 256 + c * 16, u);
-                    tmem_ld_wait();
+                    for (int c = 0; c < 8; ++c) {                       // 8 columns at a time (register budget: 64 live sums)
+                        uint32_t v[8], u[8];
+                        tmem_ld8(lane_addr + c * 8, v);
+                        if (has_cross) tmem_ld8(lane_addr + 256 + c * 8, u);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        f[c >> 1][(c & 1) * 16 + j] = has_cross ? __uint_as_float(v[j]) + __uint_as_float(u[j]) : __uint_as_float(v[j]);
+                        for (int j = 0; j < 8; ++j) {
+                            const float x = has_cross ? __uint_as_float(v[j]) + __uint_as_float(u[j]) : __uint_as_float(v[j]);
+                            float& acc = f[c >> 2][(c & 3) * 8 + j];
+                            acc = first_pass ? x : acc + x;
+                        }
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
+#ifdef RACF_LINW_PROFILE
+                prof[0] += clock64() - t_ready;      // epilogue: tensor memory -> registers
+#endif
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
 #ifdef RACF_LINW_PROFILE
             const long long t_drained = clock64();
 #endif
@@ -296,8 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
             // 256 KB apart at N = 65536: measured 1300 cycles per store instruction, the epilogue became the bottleneck).
             if (active) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int gn = n_tile * 128 + c * 32 + (lane & 7) * 4;
+                for (int c = 0; c < 2; ++c) {
+                    const int gn = n_tile * 128 + (cq & 1) * 64 + c * 32 + (lane & 7) * 4;
                     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (biasp != nullptr) {
                         if (gn + 0 < args.N) b4.x = __ldg(biasp + gn + 0);
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
                         *reinterpret_cast<float4*>(stg + lane * kStgStride + j * 4) =
                             make_float4(f[c][4 * j], f[c][4 * j + 1], f[c][4 * j + 2], f[c][4 * j + 3]);
                     __syncwarp();
-#pragma unroll
+#pragma unroll 2
                     for (int r0 = 0; r0 < 32; r0 += 4) {             // 8 lanes x 16 bytes = one 128-byte row segment, 4 rows per store
                         const int r = r0 + (lane >> 3), gm = m0 + r;
                         if (gm < args.M && gn < args.N) {
@@ -332,7 +348,6 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
                 }
             }
 #ifdef RACF_LINW_PROFILE
-            prof[0] += t_drained - t_ready;      // epilogue: tensor memory -> registers
             prof[1] += clock64() - t_drained;    // epilogue: stores
 #endif
         }
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_bf16x3_wide_kernel(const A
 // Launcher used by racf_linear_bf16x3_forward (variant 3; csrc/linear.cu validates the arguments and runs the K-split
 // reduction). The operands are TiledOperands; partial tiles of a K split go to `out` = workspace [num_splits, M, N].
 int racf_linear_wide_launch(const void* a_tiled, const void* w_tiled, const float* bias, float* out, int M, int N, int num_kblocks,
-                            int kblocks_per_split, int num_splits, int max_order, cudaStream_t st) {
+                            int kblocks_per_pass, int kblocks_per_split, int num_splits, int max_order, cudaStream_t st) {
     using namespace racf::linwide;
     Args args;
     args.a_tiled = static_cast<const uint8_t*>(a_tiled);
@@ -367,6 +382,7 @@ int racf_linear_wide_launch(const void* a_tiled, const void* w_tiled, const floa
     args.n_tiles128 = (N + 127) / 128;
     args.n_pairs = (args.n_tiles128 + 1) / 2;
     args.num_kblocks = num_kblocks;
+    args.kblocks_per_pass = kblocks_per_pass;
     args.kblocks_per_split = kblocks_per_split;
     args.num_splits = num_splits;
     args.max_order = max_order;
