@@ -348,6 +348,8 @@ class DecoderWorkload:
             ops = SamplingOps(msmv=lambda *a: self._timed("msmv_fwd", base.msmv, a),
                               msda=lambda *a: self._timed("msda_fwd", base.msda, a),
                               msmv_grouped=lambda *a: self._timed("msmv_fwd", base.msmv_grouped, a))
+            if base.msda_pair is not None:      # both BEV branches of an iteration in one launch: one "msda_fwd" entry per pair
+                ops.msda_pair = lambda *a: self._timed("msda_fwd", base.msda_pair, a)
         else:   # CPU baseline leg: the oracle's port of the reference's PyTorch ops (never used for the GPU numbers)
             from oracle import reference_port
             ops = SamplingOps(msmv=reference_port.msmv_sampling_torch_channel_last,
@@ -543,7 +545,7 @@ class DecoderWorkload:
             per_family = {}
             for key, pairs in self.timers.items():
                 ms = [a.elapsed_time(b) for a, b in pairs]
-                passes = max(1, len(ms) // max(1, {"msda_fwd": 2, "row_programs": 3}.get(key, 1) * self.layers))
+                passes = max(1, len(ms) // max(1, {"msda_fwd": 1, "row_programs": 3}.get(key, 1) * self.layers))
                 per_family[key] = (ms, passes)
             rep["kernel_timing"] = "CUDA events around each launch in an eager pass after the timed region"
         for key, (ms, passes) in per_family.items():
@@ -646,7 +648,11 @@ class DecoderWorkload:
                 e.update({"algorithmic_bytes": k["algorithmic_bytes"], "algorithmic_gbs": k["algorithmic_gbs"],
                           "frac_algorithmic": k["algorithmic_gbs"] / hbm_peak})
             if traffic.get(key):
-                e.update({"dram_traffic_bytes": traffic[key], "frac_dram": traffic[key] / (k["avg_us"] * 1e-6) / 1e9 / hbm_peak})
+                t = traffic[key]
+                if key == "msda_fwd" and k["launches_per_step"] <= self.layers:
+                    t, e["note"] = 2 * t, ("one launch serves both BEV branches of an iteration (racf_msda_forward_pair): "
+                                            "twice the captured single-branch DRAM bytes per launch")
+                e.update({"dram_traffic_bytes": t, "frac_dram": t / (k["avg_us"] * 1e-6) / 1e9 / hbm_peak})
             out[key] = e
         return out
 

@@ -145,6 +145,17 @@ int racf_msda_forward(const float* value, const int64_t* spatial_shapes, const i
                       float* out, racf_stream_t stream);
 
 /*
+ * Two MSDA forward problems of identical geometry (the radar and the LSS BEV branch of a decoder iteration,
+ * models/racformer_transformer.py:229-236: same spatial_shapes, batch, heads, queries, points; different value maps, sampling
+ * locations and attention weights) in ONE launch (grid.y = 2): same arithmetic as two racf_msda_forward calls, bit for bit.
+ */
+int racf_msda_forward_pair(const float* value_a, const float* loc_a, const float* attn_a, float* out_a,
+                           const float* value_b, const float* loc_b, const float* attn_b, float* out_b,
+                           const int64_t* spatial_shapes, const int64_t* level_start_index, int batch,
+                           int spatial_size, int num_heads, int head_dim, int num_levels, int num_query,
+                           int num_point, int im2col_step, racf_stream_t stream);
+
+/*
  * Multi-scale deformable attention, backward.
  *   grad_out   : [B, Q, M*D]
  *   grad_value : [B, S, M, D]          accumulated with atomics into the caller's (pre-zeroed) buffer,

@@ -31,6 +31,8 @@ SIGNATURES = {
                                  ctypes.c_void_p, ctypes.c_void_p]),
     "racf_msda_forward": (_i, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _c_float_p,
                                _i, _i, _i, _i, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_msda_forward_pair": (_i, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                    ctypes.c_void_p, ctypes.c_void_p] + [_i] * 8 + [ctypes.c_void_p]),
     "racf_msda_backward": (_i, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _c_float_p, _c_float_p, _c_float_p,
                                 ctypes.c_void_p]),

@@ -30,6 +30,11 @@ struct MsdaArgs {
     float* grad_loc;
     float* grad_attn;
     int B, S, M, D, L, Q, P;
+    // second problem of identical geometry served by the same launch (blockIdx.y == 1): racf_msda_forward_pair
+    const float* value2;
+    const float* loc2;
+    const float* attn2;
+    float* out2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -42,15 +47,17 @@ __global__ void __launch_bounds__(kMsdaWarps * 32) msda_fwd_d64_kernel(const Msd
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long bqm = (long long)blockIdx.x * kMsdaWarps + warp;
     if (bqm >= (long long)a.B * a.Q * a.M) return;
+    const bool second = blockIdx.y != 0;             // the other BEV branch of the pair (same shapes, other tensors)
+    const float* value = second ? a.value2 : a.value;
     const int m = (int)(bqm % a.M);
     const int b = (int)(bqm / ((long long)a.Q * a.M));
     const int slot = lane >> 4, j = lane & 15;
     const int px = a.M * 16;  // float4 stride between x-neighbours
     const float4* base =
-        reinterpret_cast<const float4*>(a.value + ((size_t)b * a.S * a.M + m) * 64) + slot * px + j;
+        reinterpret_cast<const float4*>(value + ((size_t)b * a.S * a.M + m) * 64) + slot * px + j;
     const int T = a.L * a.P;
-    const float* loc_q = a.loc + bqm * T * 2;
-    const float* aw_q = a.attn + bqm * T;
+    const float* loc_q = (second ? a.loc2 : a.loc) + bqm * T * 2;
+    const float* aw_q = (second ? a.attn2 : a.attn) + bqm * T;
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t0 = 0; t0 < T; t0 += 32) {
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(kMsdaWarps * 32) msda_fwd_d64_kernel(const Msd
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
     acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-    if (slot == 0) reinterpret_cast<float4*>(a.out + bqm * 64)[j] = acc;
+    if (slot == 0) reinterpret_cast<float4*>((second ? a.out2 : a.out) + bqm * 64)[j] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,6 +333,38 @@ extern "C" int racf_msda_forward(const float* value, const int64_t* spatial_shap
         const long long total = (long long)batch * num_query * num_heads * head_dim;
         msda_fwd_generic_kernel<<<capped_grid(total, 256, 64LL * sm_count()), 256, 0, st>>>(a);
     }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int racf_msda_forward_pair(const float* value_a, const float* loc_a, const float* attn_a, float* out_a,
+                                      const float* value_b, const float* loc_b, const float* attn_b, float* out_b,
+                                      const int64_t* spatial_shapes, const int64_t* level_start_index, int batch,
+                                      int spatial_size, int num_heads, int head_dim, int num_levels, int num_query,
+                                      int num_point, int im2col_step, racf_stream_t stream) {
+    int rc = check_msda(value_a, spatial_shapes, level_start_index, loc_a, attn_a, batch, spatial_size, num_heads, head_dim,
+                        num_levels, num_query, num_point, im2col_step);
+    if (rc == RACF_OK)
+        rc = check_msda(value_b, spatial_shapes, level_start_index, loc_b, attn_b, batch, spatial_size, num_heads, head_dim,
+                        num_levels, num_query, num_point, im2col_step);
+    if (rc != RACF_OK) return rc;
+    if (!out_a || !out_b) return RACF_ERR_NULL_POINTER;
+    const bool fast = head_dim == 64 && aligned16p(value_a) && aligned16p(value_b) && aligned16p(out_a) && aligned16p(out_b) &&
+                      ((reinterpret_cast<uintptr_t>(loc_a) | reinterpret_cast<uintptr_t>(loc_b)) & 7u) == 0;
+    if (!fast) {       // no paired generic kernel: two launches
+        rc = racf_msda_forward(value_a, spatial_shapes, level_start_index, loc_a, attn_a, batch, spatial_size, num_heads, head_dim,
+                               num_levels, num_query, num_point, im2col_step, out_a, stream);
+        if (rc != RACF_OK) return rc;
+        return racf_msda_forward(value_b, spatial_shapes, level_start_index, loc_b, attn_b, batch, spatial_size, num_heads,
+                                 head_dim, num_levels, num_query, num_point, im2col_step, out_b, stream);
+    }
+    MsdaArgs a{};
+    a.value = value_a; a.loc = loc_a; a.attn = attn_a; a.out = out_a;
+    a.value2 = value_b; a.loc2 = loc_b; a.attn2 = attn_b; a.out2 = out_b;
+    a.shapes = spatial_shapes; a.lsi = level_start_index;
+    a.B = batch; a.S = spatial_size; a.M = num_heads; a.D = head_dim; a.L = num_levels; a.Q = num_query; a.P = num_point;
+    const long long nw = (long long)batch * num_query * num_heads;
+    const dim3 grid((unsigned)((nw + kMsdaWarps - 1) / kMsdaWarps), 2, 1);
+    msda_fwd_d64_kernel<<<grid, kMsdaWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }
 

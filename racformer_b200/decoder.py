@@ -38,13 +38,15 @@ class SamplingOps:
     """msmv(feats_channel_last, loc, w) -> [B',Q,C,P];  msda(value, shapes, lsi, loc, aw, im2col_step) -> [B,Q,M*D]."""
 
     def __init__(self, msmv=None, msda=None, msmv_grouped=None):
+        self.msda_pair = None      # inference: both BEV branches of an iteration in one launch (racf_msda_forward_pair)
         if msmv is None or msda is None:
             from . import wrapper
-            from .multi_scale_deformable_attn_function import MultiScaleDeformableAttnFunction_fp32
+            from .multi_scale_deformable_attn_function import MultiScaleDeformableAttnFunction_fp32, msda_forward_pair
             if msmv is None and msmv_grouped is None:
                 msmv_grouped = wrapper.msmv_forward_grouped     # inference-only variant with the un-packing fused in
             msmv = msmv or wrapper.msmv_sampling
-            msda = msda or MultiScaleDeformableAttnFunction_fp32.apply
+            if msda is None:
+                msda, self.msda_pair = MultiScaleDeformableAttnFunction_fp32.apply, msda_forward_pair
         self.msmv, self.msda, self.msmv_grouped = msmv, msda, msmv_grouped
 
 
@@ -580,16 +582,22 @@ class BEVSampling(nn.Module):
             return self.attention.project_value(bev_feats, pos.reshape(C, H, W)), (H, W)
         return self.attention.project_value(bev_feats + pos.view(B, 1, C, H, W)), (H, W)
 
+    def fused_point_tensors(self, query_ray, query_feat, meta, d_region, heads=None):
+        """Sampling locations, attention weights (queue-major packing) and queue logits from the fused point kernel."""
+        from . import points
+        T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
+        off, ray, sw, qw = heads if heads is not None else (self.sampling_offset(query_feat),
+                                                            self.ray_points_offset(query_feat),
+                                                            self.scale_weights(query_feat), None)
+        loc, aw = points.bev_points(query_ray.contiguous(), off, ray, sw, meta["time_diff"],
+                                    _depth_base(d_region, D, query_feat.device), pr, d_region, T, M, Pn, D)
+        return loc, aw, qw
+
     def sample(self, ops, query_ray, query_feat, value, hw, meta, d_region, heads=None, raw=False):
         B, Q, _ = query_ray.shape
         T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
         if self.num_levels == 1 and _use_fused_points(self, query_ray, query_feat, value):
-            from . import points
-            off, ray, sw, qw = heads if heads is not None else (self.sampling_offset(query_feat),
-                                                                self.ray_points_offset(query_feat),
-                                                                self.scale_weights(query_feat), None)
-            loc, aw = points.bev_points(query_ray.contiguous(), off, ray, sw, meta["time_diff"],
-                                        _depth_base(d_region, D, query_feat.device), pr, d_region, T, M, Pn, D)
+            loc, aw, qw = self.fused_point_tensors(query_ray, query_feat, meta, d_region, heads)
             return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw,
                                          shared_grads=meta.get("shared_grads"))
         query_bbox = theta_d2xy_coods(query_ray)
@@ -1079,6 +1087,35 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         return self._forward(ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta,
                              layer, prepared, False)
 
+    bev_pair_launch = True     # inference: the radar and the LSS MSDA of an iteration as one launch
+
+    def _bev_pair(self, ops, query_bbox, query_feat, prep_radar, prep_lss, meta, d_region, heads):
+        """(radar, lss) = ((MSDA output [B*T,Q,C], queue logits), ...) as BEVSampling.forward(raw=True) returns them, with the
+        two MSDA forwards -- same geometry, different value maps / locations / weights -- in ONE launch
+        (racf_msda_forward_pair). None when the configuration does not allow it (the caller runs the branches one by one)."""
+        r, l = self.sampling_radar_bev, self.sampling_lss_bev
+        if (not self.bev_pair_launch or getattr(ops, "msda_pair", None) is None or prep_radar is None or prep_lss is None
+                or torch.is_grad_enabled() or r.num_levels != 1 or l.num_levels != 1):
+            return None
+        (value_r, hw_r), (value_l, hw_l) = prep_radar, prep_lss
+        if (tuple(hw_r) != tuple(hw_l) or value_r.shape != value_l.shape
+                or (r.num_frames, r.num_heads, r.num_points, r.depth_num) != (l.num_frames, l.num_heads, l.num_points, l.depth_num)
+                or not (_use_fused_points(r, query_bbox, query_feat, value_r) and _use_fused_points(l, query_bbox, query_feat, value_l))
+                or r.attention.im2col_step != l.attention.im2col_step):
+            return None
+        loc_r, aw_r, qw_r = r.fused_point_tensors(query_bbox, query_feat, meta, d_region, heads[0])
+        loc_l, aw_l, qw_l = l.fused_point_tensors(query_bbox, query_feat, meta, d_region, heads[1])
+        shapes = _const_long((tuple(int(v) for v in hw_r),), value_r.device)
+        lsi = _const_long((0,), value_r.device)
+        out_r, out_l = ops.msda_pair(value_r, loc_r.contiguous(), aw_r.contiguous(), value_l, loc_l.contiguous(), aw_l.contiguous(),
+                                     shapes, lsi, r.attention.im2col_step)
+
+        def logits(branch, qw):
+            if not branch.attention.queue_weight:
+                return None
+            return qw if qw is not None else branch.attention.bev_queue_weight(query_feat)
+        return (out_r, logits(r, qw_r)), (out_l, logits(l, qw_l))
+
     def _forward(self, ops, query_bbox, query_feat, mlvl_feats, lss_bev_feats, radar_bev_feats, attn_mask, meta, layer,
                  prepared, rows):
         d_region = self.d_region_list[layer]
@@ -1097,10 +1134,14 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
             query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
         heads = (self._sampling_heads_train(query_feat) if train_rows else self._sampling_heads(query_feat)) or (None, None, None)
-        radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,
-                                        prepared=prep_radar, heads=heads[0], raw=rows or train_rows)
-        lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,
-                                    prepared=prep_lss, heads=heads[1], raw=rows or train_rows)
+        pair = self._bev_pair(ops, query_bbox, query_feat, prep_radar, prep_lss, meta, d_region, heads) if rows else None
+        if pair is not None:
+            radar, lss = pair
+        else:
+            radar = self.sampling_radar_bev(ops, query_bbox, query_feat, radar_bev_feats, meta, d_region=d_region,
+                                            prepared=prep_radar, heads=heads[0], raw=rows or train_rows)
+            lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,
+                                        prepared=prep_lss, heads=heads[1], raw=rows or train_rows)
         sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region, heads=heads[2])
         mixed = self.mixing(sampled, query_feat)
         if rows or train_rows:

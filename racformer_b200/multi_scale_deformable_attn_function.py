@@ -100,6 +100,27 @@ class _ExtModule:
 ext_module = _ExtModule()
 
 
+def msda_forward_pair(value_a, loc_a, attn_a, value_b, loc_b, attn_b, spatial_shapes, level_start_index, im2col_step=64):
+    """Two forward problems of identical geometry -- the radar and the LSS BEV branch of a decoder iteration
+    (models/racformer_transformer.py:229-236) -- in one launch; inference only (no autograd). Returns (out_a, out_b),
+    bit-identical to two ext_module.ms_deform_attn_forward calls."""
+    B, S, M, D, L, Q, P = _check(value_a, spatial_shapes, level_start_index, loc_a, attn_a, im2col_step)
+    _require(_check(value_b, spatial_shapes, level_start_index, loc_b, attn_b, im2col_step) == (B, S, M, D, L, Q, P)
+             and value_b.device == value_a.device, "msda_forward_pair: the two problems must have the same shapes and device")
+    out_a = torch.empty((B, Q, M * D), dtype=torch.float32, device=value_a.device)
+    out_b = torch.empty_like(out_a)
+    if out_a.numel() == 0:
+        return out_a, out_b
+    with torch.cuda.device(value_a.device):
+        rc = _lib.load().racf_msda_forward_pair(
+            value_a.data_ptr(), loc_a.data_ptr(), attn_a.data_ptr(), out_a.data_ptr(),
+            value_b.data_ptr(), loc_b.data_ptr(), attn_b.data_ptr(), out_b.data_ptr(),
+            spatial_shapes.data_ptr(), level_start_index.data_ptr(), B, S, M, D, L, Q, P, int(im2col_step),
+            _stream(value_a.device))
+    _lib.check(rc, "racf_msda_forward_pair")
+    return out_a, out_b
+
+
 def msda_tap_masks(spatial_shapes, sampling_loc):
     """Debug entry: uint8 [bs, Q, M, L, P]; bit0 = tap in range, bit1..4 = corners read."""
     _require(sampling_loc.is_cuda and sampling_loc.is_contiguous() and sampling_loc.dtype == torch.float32,

@@ -320,3 +320,53 @@ def test_decoder_training_gradients_tensor_core_linears_match_sgemm():
     for name, a, b in zip(("cls", "box", "grad_query", "grad_feat0", "grad_param_gen_w", "grad_out_proj_w"), *results):
         tol = 1e-4 * float(b.abs().max()) + 1e-6
         assert float((a - b).abs().max()) <= tol, (name, float((a - b).abs().max()), tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,bias", [(128, 256, 32, False), (77, 200, 40, True), (300, 384, 256, True), (900, 640, 96, True),
+                                        (130, 1152, 512, True), (257, 129, 64, False)])
+def test_wide_tile_linear_is_bit_identical_to_the_128x128_kernel(M, N, K, bias):
+    """csrc/linear_wide.cu (128 x 256 tiles on persistent CTAs, N = 256 MMAs, variant 3 -- the default for tiled operands with
+    N > 128) issues the same piece products in the same order per accumulator as csrc/linear.cu: identical bits while a
+    work item is one K pass (K <= 512), including odd numbers of 128-column blocks, ragged M / N / K and the bias."""
+    from racformer_b200 import linear
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda") if bias else None
+    a3, w3 = linear.split_tiled(a), linear.split_tiled(w)
+    try:
+        linear.WIDE_TILES = False
+        narrow = linear.linear_bf16x3(a3, w3, b)
+        linear.WIDE_TILES = True
+        wide = linear.linear_bf16x3(a3, w3, b)
+    finally:
+        linear.WIDE_TILES = True
+    assert torch.equal(narrow, wide)
+    ref = a.double() @ w.double().t() + (b.double() if bias else 0)
+    scale = a.double().abs() @ w.double().abs().t() + (b.double().abs() if bias else 0)
+    assert float(((wide.double() - ref).abs() / scale).max()) <= 6e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(900, 256, 32768), (200, 384, 2048), (64, 256, 1536)])
+def test_wide_tile_linear_multi_pass_split_k_is_fp32_grade_and_deterministic(M, N, K):
+    """K > 512: a work item of the wide kernel adds several 512-wide passes in registers (fewer K splits than the 128 x 128
+    kernel, other grouping of the same fp32 additions): same error bar against an fp64 product, run-to-run identical."""
+    from racformer_b200 import linear
+    torch.manual_seed(K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    a3, w3 = linear.split_tiled(a), linear.split_tiled(w)
+    y = linear.linear_bf16x3(a3, w3, b)
+    assert torch.equal(y, linear.linear_bf16x3(a3, w3, b))
+    try:
+        linear.WIDE_TILES = False
+        narrow = linear.linear_bf16x3(a3, w3, b)
+    finally:
+        linear.WIDE_TILES = True
+    ref = a.double() @ w.double().t() + b.double()
+    scale = a.double().abs() @ w.double().abs().t() + b.double().abs()
+    err, err_n = float(((y.double() - ref).abs() / scale).max()), float(((narrow.double() - ref).abs() / scale).max())
+    assert err <= 6e-7 and err <= 2.0 * err_n + 1e-8, (err, err_n)

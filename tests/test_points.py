@@ -37,6 +37,7 @@ class Spy(SamplingOps):
             return real_grouped(feats, loc, w, T, G)
 
         self.msmv, self.msda, self.msmv_grouped = msmv, msda, grouped
+        self.msda_pair = None      # record every MSDA call: the paired launch (tested on its own below) bypasses self.msda
 
 
 def _run(cfg, inputs, fused, seed=3):
@@ -249,3 +250,43 @@ def test_to_sampling_layout_f16_is_bit_identical_to_upcast_then_relayout(channel
     want = x.float().reshape(B, T, N, G, C, H, W).permute(0, 1, 3, 2, 5, 6, 4).reshape(B * T * G, N, H, W, C).contiguous()
     assert torch.equal(got, want)
     assert torch.equal(to_sampling_layout(x, N, G), want)
+
+
+def test_msda_forward_pair_equals_two_forwards_bit_for_bit():
+    """racf_msda_forward_pair: the radar and the LSS BEV branch of an iteration in one launch (grid.y = 2)."""
+    from racformer_b200.multi_scale_deformable_attn_function import ext_module, msda_forward_pair
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, W, M, D, Q, P = 8, 32, 48, 4, 64, 77, 20
+    shapes = torch.tensor([[H, W]], dtype=torch.long, device="cuda")
+    lsi = torch.zeros(1, dtype=torch.long, device="cuda")
+    probs = []
+    for _ in range(2):
+        value = torch.randn(B, H * W, M, D, device="cuda", generator=g)
+        loc = torch.rand(B, Q, M, 1, P, 2, device="cuda", generator=g) * 1.2 - 0.1        # some taps outside the map
+        aw = torch.softmax(torch.randn(B, Q, M, 1, P, device="cuda", generator=g), -1)
+        probs.append((value, loc, aw))
+    (va, la, aa), (vb, lb, ab) = probs
+    out_a, out_b = msda_forward_pair(va, la, aa, vb, lb, ab, shapes, lsi, 64)
+    assert torch.equal(out_a, ext_module.ms_deform_attn_forward(va, shapes, lsi, la, aa, 64))
+    assert torch.equal(out_b, ext_module.ms_deform_attn_forward(vb, shapes, lsi, lb, ab, 64))
+    with pytest.raises(RuntimeError):
+        msda_forward_pair(va, la, aa, vb[:, :100].contiguous(), lb, ab, shapes, lsi, 64)
+
+
+def test_decoder_layer_paired_bev_launch_equals_separate_launches():
+    """DecoderLayer._bev_pair (one MSDA launch for both BEV branches) against the branch-by-branch path: identical outputs."""
+    model = RaCFormerTransformer(**SMALL)
+    model.init_weights()
+    fill_parameters_by_name(model, seed=3)
+    model.eval().cuda()
+    d = small_inputs(device="cuda")
+    args = (d["query_bbox"], d["query_feat"], d["mlvl_feats"], d["lss_bev"], d["radar_bev"], None, d["img_metas"])
+    layer = model.decoder.decoder_layer
+    assert layer.bev_pair_launch and model.ops.msda_pair is not None
+    with torch.no_grad():
+        paired = model(*args)
+        layer.bev_pair_launch = False
+        separate = model(*args)
+        layer.bev_pair_launch = True
+    for a, b in zip(paired, separate):
+        assert torch.equal(a, b)
