@@ -209,6 +209,30 @@ int racf_bev_points_forward(const float* query_ray, const float* offset, const f
                             racf_stream_t stream);
 
 /*
+ * Training (autograd) counterparts: backward of the two point kernels. They take the forward's inputs and outputs and the
+ * location / weight gradients the sampling ops' backward returns, and write the gradients of the Linear heads' outputs
+ * (fully overwritten): grad_offset like offset, grad_ray_logit [B,Q,D], grad_scale_raw / grad_attn_raw like scale_raw /
+ * attn_raw, and -- when grad_ray is not NULL -- grad_ray [B,Q,10] (the velocity columns are detached in the reference's warp,
+ * models/racformer_transformer.py:381, so they get 0). The camera view of a point is not differentiable; it is read back
+ * from loc[...,2]. grad_loc [B*T*G,Q,Pn*D,3] (the third component is ignored) / grad_weights [B*G*T,Q,Pn*D,L] are what
+ * racf_msmv_backward produces; grad_loc [T*B,Q,M,1,Pn*D,2] / grad_attn [T*B,Q,M,1,Pn*D] what racf_msda_backward produces.
+ */
+int racf_msmv_points_backward(const float* query_ray, const float* offset, const float* ray_logit,
+                              const float* time_diff, const float* lidar2img, const float* depth_base,
+                              const double* pc_range, float d_region, float image_w, float image_h, float eps,
+                              int batch, int num_query, int num_frames, int num_groups, int num_points,
+                              int depth_num, int num_views, int num_levels, const float* loc,
+                              const float* weights, const float* grad_loc, const float* grad_weights,
+                              float* grad_ray, float* grad_offset, float* grad_ray_logit, float* grad_scale_raw,
+                              racf_stream_t stream);
+int racf_bev_points_backward(const float* query_ray, const float* offset, const float* ray_logit,
+                             const float* time_diff, const float* depth_base, const double* pc_range,
+                             float d_region, int batch, int num_query, int num_frames, int num_heads,
+                             int num_points, int depth_num, const float* attn, const float* grad_loc,
+                             const float* grad_attn, float* grad_ray, float* grad_offset, float* grad_ray_logit,
+                             float* grad_attn_raw, racf_stream_t stream);
+
+/*
  * "next" row: channel-last re-layout of one FPN level,
  * in [B, T*N, G*C, H, W] -> out [B*T*G, N, H, W, C] (models/racformer_transformer.py:112-124), C == 64.
  */
@@ -409,6 +433,12 @@ int racf_sasa_attention_train_backward(const float* qkv, const float* tau, const
 int racf_refine_bbox_forward(const float* proposal, const float* delta, const float* time_diff, int batch,
                              int num_query, int num_frames, int code_size, float num_ray, float* pred,
                              float* pred_xy, racf_stream_t stream);
+
+/* Backward of racf_refine_bbox_forward w.r.t. its pred_xy output (pred feeds the next iteration detached,
+ * models/racformer_transformer.py:132): grad_delta [rows, code_size] and, when not NULL, grad_proposal (both overwritten). */
+int racf_refine_bbox_backward(const float* proposal, const float* delta, const float* time_diff,
+                              const float* grad_pred_xy, int batch, int num_query, int num_frames, int code_size,
+                              float num_ray, float* grad_delta, float* grad_proposal, racf_stream_t stream);
 
 /*
  * Call-site row: the row-wise operators between the sampling ops of one decoder iteration

@@ -77,6 +77,11 @@ SIGNATURES = {
                                                 _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "racf_refine_bbox_forward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                       _c_float_p, ctypes.c_void_p]),
+    "racf_refine_bbox_backward": (_i, [_c_float_p] * 4 + [_i, _i, _i, _i, ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "racf_msmv_points_backward": (_i, [_c_float_p] * 6 + [ctypes.POINTER(ctypes.c_double)] + [ctypes.c_float] * 4 + [_i] * 8
+                                  + [_c_float_p] * 8 + [ctypes.c_void_p]),
+    "racf_bev_points_backward": (_i, [_c_float_p] * 5 + [ctypes.POINTER(ctypes.c_double), ctypes.c_float] + [_i] * 6
+                                 + [_c_float_p] * 7 + [ctypes.c_void_p]),
     "racf_row_program_forward": (_i, [ctypes.c_void_p, _i, _i, _i, _i, _i, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
 }

@@ -159,7 +159,13 @@ def sampling_4d(ops, sample_points, mlvl_feats, scale_weights, lidar2img, image_
 
     w = scale_weights.reshape(B, Q, G, T, P, -1).permute(0, 2, 3, 1, 4, 5).reshape(B * G * T, Q, P, -1)  # quirk (i)
 
-    loc, w = loc.contiguous(), w.contiguous()
+    return _msmv_packed(ops, mlvl_feats, loc.contiguous(), w.contiguous(), B, T, G, shared_grads)
+
+
+def _msmv_packed(ops, mlvl_feats, loc, w, B, T, G, shared_grads=None):
+    """msmv_sampling on the packed tensors (loc [B*T*G,Q,P,3], w [B*G*T,Q,P,L]) + sampling_4d's un-packing
+    (sparsebev_sampling.py:122-134) -> [B,Q,G,T*P,C]."""
+    Q, P = loc.shape[1], loc.shape[2]
     if shared_grads is not None and getattr(ops, "msmv_grouped", None) is not None:
         from . import training   # training on CUDA: grouped output + grouped grad_out, feature gradients accumulated in place
         if training.msmv_grouped_supported(mlvl_feats, loc, w):
@@ -290,6 +296,12 @@ def _use_fused_points(module, *tensors):
             and all(t.is_cuda and t.dtype == torch.float32 for t in tensors))
 
 
+def _use_fused_points_train(module, *tensors):
+    """Training on CUDA: the same point kernels with a fused backward (racformer_b200/training.py, csrc/points_train.cu)."""
+    return (getattr(module, "fused_points", True) and getattr(module, "fused_points_train", True) and torch.is_grad_enabled()
+            and all(t.is_cuda and t.dtype == torch.float32 for t in tensors))
+
+
 def _depth_base(d_region, depth_num, device):
     key = ("linspace", str(device), float(d_region), int(depth_num))
     t = _CONST_CACHE.get(key)
@@ -342,6 +354,15 @@ class RaCFormerSampling(nn.Module):
             out = ops.msmv(mlvl_feats, loc, w)                                         # [B*T*G,Q,C,P]
             C = out.shape[2]
             return out.reshape(B, T, G, Q, C, Pn * D).permute(0, 3, 2, 1, 5, 4).flatten(3, 4)
+        if _use_fused_points_train(self, query_ray, query_feat, meta["lidar2img"], meta["time_diff"]):
+            from . import training   # one forward + one backward launch instead of ~400 autograd nodes
+            off, ray, sw = heads if heads is not None else (self.sampling_offset(query_feat),
+                                                            self.ray_points_offset(query_feat),
+                                                            self.scale_weights(query_feat))
+            loc, w = training.MSMVPoints.apply(
+                query_ray, off, ray, sw, meta["time_diff"], meta["lidar2img"], _depth_base(d_region, D, query_feat.device),
+                (tuple(pr), d_region, meta["image_w"], meta["image_h"], T, G, Pn, D, self.num_levels))
+            return _msmv_packed(ops, mlvl_feats, loc, w, B, T, G, meta.get("shared_grads"))
         query_bbox = theta_d2xy_coods(query_ray)
         off, ray, sw = heads if heads is not None else (self.sampling_offset(query_feat), None, None)
         offset = off.view(B, Q, G * Pn * D, 3)
@@ -598,6 +619,15 @@ class BEVSampling(nn.Module):
         T, M, Pn, D, pr = self.num_frames, self.num_heads, self.num_points, self.depth_num, self.pc_range
         if self.num_levels == 1 and _use_fused_points(self, query_ray, query_feat, value):
             loc, aw, qw = self.fused_point_tensors(query_ray, query_feat, meta, d_region, heads)
+            return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw,
+                                         shared_grads=meta.get("shared_grads"))
+        if self.num_levels == 1 and _use_fused_points_train(self, query_ray, query_feat, value, meta["time_diff"]):
+            from . import training
+            off, ray, sw, qw = heads if heads is not None else (self.sampling_offset(query_feat),
+                                                                self.ray_points_offset(query_feat),
+                                                                self.scale_weights(query_feat), None)
+            loc, aw = training.BEVPoints.apply(query_ray, off, ray, sw, meta["time_diff"],
+                                               _depth_base(d_region, D, query_feat.device), (tuple(pr), d_region, T, M, Pn, D))
             return self.attention.attend(ops, query_feat, value, loc, aw, hw, queue_logits=qw, raw=raw,
                                          shared_grads=meta.get("shared_grads"))
         query_bbox = theta_d2xy_coods(query_ray)
@@ -899,6 +929,7 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
         theta = proposal[..., 0:1] + (torch.sigmoid(delta[..., 0:1]) * 2 - 1) / self.num_ray
         return torch.cat([theta, dz, delta[..., 3:]], dim=-1)
 
+    fused_refine_train = True   # training on CUDA: refine_bbox + output transform as one forward and one backward launch
     row_programs = True     # inference on CUDA: the row-wise operator chains run as row programs (csrc/rowops.cu)
 
     def _rows_ok(self, query_feat):
@@ -1159,6 +1190,11 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
             bbox_pred, bbox_xy = points.refine_bbox(query_bbox.contiguous(), delta.contiguous(), time_diff.contiguous(),
                                                     self.num_ray)
             return query_feat, cls_score, bbox_pred, bbox_xy
+        if (self.fused_refine_train and torch.is_grad_enabled() and self.code_size >= 8 and delta.is_cuda
+                and delta.dtype == torch.float32 and query_bbox.dtype == torch.float32):
+            from . import training   # the same launch with a backward kernel (csrc/points_train.cu)
+            bbox_pred, bbox_xy = training.RefineBBox.apply(query_bbox, delta, time_diff, self.num_ray)
+            return query_feat, cls_score, bbox_pred, bbox_xy
         bbox_pred = self.refine_bbox(query_bbox, delta)
         if time_diff.shape[1] > 1:   # relative -> absolute velocity
             td = torch.where(time_diff < 1e-5, torch.ones_like(time_diff), time_diff)
@@ -1263,10 +1299,13 @@ class RaCFormerTransformer(nn.Module):
         self.decoder.init_weights()
 
     def set_fused_points(self, enabled):
-        """Toggle the fused CUDA point-generation kernels (inference only; eager PyTorch chain when False)."""
+        """Toggle the fused CUDA point-generation / box-refinement kernels, inference and training (eager PyTorch chain
+        when False)."""
         for m in self.modules():
             if isinstance(m, (RaCFormerSampling, BEVSampling)):
                 m.fused_points = enabled
+            elif isinstance(m, RaCFormerTransformerDecoderLayer):
+                m.fused_refine_train = enabled
 
     def set_mixing_precision(self, precision):
         """"bf16x6" (default) / "bf16x9": tcgen05 kernel with exact bf16 operand splitting (fp32-grade, csrc/linear.cu);

@@ -1,5 +1,6 @@
-"""Python binding of the fused sampling-point kernels (racformer_b200/csrc/points.cu). Forward only:
-they are used by the decoder harness when autograd is off; training keeps the PyTorch op chain."""
+"""Python binding of the fused sampling-point kernels (racformer_b200/csrc/points.cu, csrc/points_train.cu).
+The forward functions are what the decoder harness calls when autograd is off; racformer_b200/training.py wraps them and
+the *_backward functions below into autograd Functions for training."""
 import ctypes
 
 import torch
@@ -63,6 +64,59 @@ def bev_points(query_ray, offset, ray_logit, attn_raw, time_diff, depth_base, pc
             _stream(query_ray.device))
     _lib.check(rc, "racf_bev_points_forward")
     return loc, attn
+
+
+def msmv_points_backward(query_ray, offset, ray_logit, time_diff, lidar2img, depth_base, pc_range, d_region, image_w, image_h,
+                         num_frames, num_groups, num_points, depth_num, num_levels, loc, weights, grad_loc, grad_weights,
+                         need_ray_grad=False, eps=1e-5):
+    """Backward of msmv_points: (grad_ray or None, grad_offset, grad_ray_logit, grad_scale_raw [B,Q,G,T,Pn*D,L])."""
+    _check(query_ray, offset, ray_logit, time_diff, lidar2img, depth_base, loc, weights, grad_loc, grad_weights)
+    B, Q, _ = query_ray.shape
+    T, G, Pn, D, L = num_frames, num_groups, num_points, depth_num, num_levels
+    N = lidar2img.shape[1] // T
+    P = Pn * D
+    if loc.shape != (B * T * G, Q, P, 3) or grad_loc.shape != loc.shape or weights.shape != (B * G * T, Q, P, L) \
+            or grad_weights.shape != weights.shape or offset.numel() != B * Q * G * P * 3 or ray_logit.numel() != B * Q * D:
+        raise RuntimeError("msmv_points_backward: inconsistent input sizes")
+    dev = query_ray.device
+    g_ray = torch.empty((B, Q, 10), dtype=torch.float32, device=dev) if need_ray_grad else None
+    g_off = torch.empty_like(offset)
+    g_logit = torch.empty((B, Q, D), dtype=torch.float32, device=dev)
+    g_scale = torch.empty((B, Q, G, T, P, L), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().racf_msmv_points_backward(
+            query_ray.data_ptr(), offset.data_ptr(), ray_logit.data_ptr(), time_diff.data_ptr(), lidar2img.data_ptr(),
+            depth_base.data_ptr(), _pc(pc_range), float(d_region), float(image_w), float(image_h), float(eps), B, Q, T, G, Pn, D,
+            N, L, loc.data_ptr(), weights.data_ptr(), grad_loc.data_ptr(), grad_weights.data_ptr(),
+            g_ray.data_ptr() if g_ray is not None else None, g_off.data_ptr(), g_logit.data_ptr(), g_scale.data_ptr(),
+            _stream(dev))
+    _lib.check(rc, "racf_msmv_points_backward")
+    return g_ray, g_off, g_logit, g_scale
+
+
+def bev_points_backward(query_ray, offset, ray_logit, time_diff, depth_base, pc_range, d_region, num_frames, num_heads,
+                        num_points, depth_num, attn, grad_loc, grad_attn, need_ray_grad=False):
+    """Backward of bev_points: (grad_ray or None, grad_offset, grad_ray_logit, grad_attn_raw [B,Q,M,Pn*D])."""
+    _check(query_ray, offset, ray_logit, time_diff, depth_base, attn, grad_loc, grad_attn)
+    B, Q, _ = query_ray.shape
+    T, M, Pn, D = num_frames, num_heads, num_points, depth_num
+    P = Pn * D
+    if attn.shape != (T * B, Q, M, 1, P) or grad_attn.shape != attn.shape or grad_loc.shape != (T * B, Q, M, 1, P, 2) \
+            or offset.numel() != B * Q * M * P * 2 or ray_logit.numel() != B * Q * D:
+        raise RuntimeError("bev_points_backward: inconsistent input sizes")
+    dev = query_ray.device
+    g_ray = torch.empty((B, Q, 10), dtype=torch.float32, device=dev) if need_ray_grad else None
+    g_off = torch.empty_like(offset)
+    g_logit = torch.empty((B, Q, D), dtype=torch.float32, device=dev)
+    g_attn_raw = torch.empty((B, Q, M, P), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().racf_bev_points_backward(
+            query_ray.data_ptr(), offset.data_ptr(), ray_logit.data_ptr(), time_diff.data_ptr(), depth_base.data_ptr(),
+            _pc(pc_range), float(d_region), B, Q, T, M, Pn, D, attn.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+            g_ray.data_ptr() if g_ray is not None else None, g_off.data_ptr(), g_logit.data_ptr(), g_attn_raw.data_ptr(),
+            _stream(dev))
+    _lib.check(rc, "racf_bev_points_backward")
+    return g_ray, g_off, g_logit, g_attn_raw
 
 
 def to_sampling_layout(feat, num_cams, num_groups=4):
@@ -204,6 +258,22 @@ def refine_bbox(proposal, delta, time_diff, num_ray):
                                                   float(num_ray), pred.data_ptr(), pred_xy.data_ptr(), _stream(proposal.device))
     _lib.check(rc, "racf_refine_bbox_forward")
     return pred, pred_xy
+
+
+def refine_bbox_backward(proposal, delta, time_diff, num_ray, grad_pred_xy, need_proposal_grad=False):
+    """Backward of refine_bbox w.r.t. its second output: (grad_delta, grad_proposal or None)."""
+    _check(proposal, delta, grad_pred_xy)
+    B, Q, code = proposal.shape
+    T = 1 if time_diff is None else time_diff.shape[1]
+    g_delta = torch.empty_like(delta)
+    g_prop = torch.empty_like(proposal) if need_proposal_grad else None
+    with torch.cuda.device(proposal.device):
+        rc = _lib.load().racf_refine_bbox_backward(
+            proposal.data_ptr(), delta.data_ptr(), time_diff.data_ptr() if time_diff is not None else None,
+            grad_pred_xy.data_ptr(), B, Q, T, code, float(num_ray), g_delta.data_ptr(),
+            g_prop.data_ptr() if g_prop is not None else None, _stream(proposal.device))
+    _lib.check(rc, "racf_refine_bbox_backward")
+    return g_delta, g_prop
 
 
 def sasa_attention(qkv, tau, query_ray, pc_range, num_heads):

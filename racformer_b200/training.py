@@ -14,6 +14,10 @@ for features / locations / weights) and add what the B200 path needs to stop re-
                           and add them pairwise; here every backward scatters into one shared buffer (one zero-fill) and only
                           the last backward to run hands the buffer to autograd (the others return None = zero).
 * `MSDAShared`          : MultiScaleDeformableAttnFunction_fp32 with the value gradient accumulated the same way.
+* `MSMVPoints` / `BEVPoints` / `RefineBBox` : the point-generation chains in front of the two sampling ops and the box
+                          refinement behind the reg branch (racformer_transformer.py:361-408, 493-529, 255-279) as one
+                          forward and one backward launch each (csrc/points.cu, csrc/points_train.cu) instead of ~400
+                          autograd nodes per branch and iteration.
 
 No CPU fallback; nothing here imports `oracle/`.
 """
@@ -224,3 +228,90 @@ class SasaAttention(Function):
                 grad_out.data_ptr(), dsum.data_ptr(), grad_qkv.data_ptr(), grad_tau.data_ptr(), wrapper._stream(qkv.device))
         _lib.check(rc, "racf_sasa_attention_train_backward")
         return grad_qkv, grad_tau, None, None, None, None, None, None
+
+
+class MSMVPoints(Function):
+    """Image-branch point generation with autograd: apply(query_ray [B,Q,10], offset [B,Q,G*Pn*D*3], ray_logit [B,Q,D],
+    scale_raw [B,Q,G*T*Pn*D*L], time_diff [B,T], lidar2img [B,T*N,4,4], depth_base [D], geom) -> (loc [B*T*G,Q,P,3],
+    weights [B*G*T,Q,P,L]) -- the tensors sampling_4d hands to msmv_sampling. geom = (pc_range, d_region, image_w, image_h,
+    T, G, Pn, D, L). The camera view (loc[...,2]) is a discrete choice: no gradient flows through it, as in the reference,
+    whose argmax / gather pick it (sparsebev_sampling.py:96-107)."""
+
+    @staticmethod
+    def forward(ctx, query_ray, offset, ray_logit, scale_raw, time_diff, lidar2img, depth_base, geom):
+        pc_range, d_region, image_w, image_h, T, G, Pn, D, L = geom
+        query_ray, offset, ray_logit, scale_raw = (t.contiguous() for t in (query_ray, offset, ray_logit, scale_raw))
+        time_diff, lidar2img = time_diff.contiguous(), lidar2img.contiguous()
+        loc, weights = points.msmv_points(query_ray, offset, ray_logit, scale_raw, time_diff, lidar2img, depth_base, pc_range,
+                                          d_region, image_w, image_h, T, G, Pn, D, L)
+        ctx.save_for_backward(query_ray, offset, ray_logit, time_diff, lidar2img, depth_base, loc, weights)
+        ctx.geom = geom
+        ctx.shapes = (offset.shape, ray_logit.shape, scale_raw.shape)
+        return loc, weights
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loc, grad_weights):
+        query_ray, offset, ray_logit, time_diff, lidar2img, depth_base, loc, weights = ctx.saved_tensors
+        pc_range, d_region, image_w, image_h, T, G, Pn, D, L = ctx.geom
+        grad_loc = torch.zeros_like(loc) if grad_loc is None else grad_loc.contiguous()
+        grad_weights = torch.zeros_like(weights) if grad_weights is None else grad_weights.contiguous()
+        g_ray, g_off, g_logit, g_scale = points.msmv_points_backward(
+            query_ray, offset, ray_logit, time_diff, lidar2img, depth_base, pc_range, d_region, image_w, image_h, T, G, Pn, D, L,
+            loc, weights, grad_loc, grad_weights, need_ray_grad=ctx.needs_input_grad[0])
+        return g_ray, g_off.view(ctx.shapes[0]), g_logit.view(ctx.shapes[1]), g_scale.view(ctx.shapes[2]), None, None, None, None
+
+
+class BEVPoints(Function):
+    """BEV-branch point generation with autograd: apply(query_ray, offset [B,Q,M*Pn*D*2], ray_logit [B,Q,D], attn_raw
+    [B,Q,M*Pn*D], time_diff, depth_base, geom) -> (loc [T*B,Q,M,1,P,2], attn [T*B,Q,M,1,P]), queue-major as
+    BEVSelfAttention hands them to MSDA. geom = (pc_range, d_region, T, M, Pn, D)."""
+
+    @staticmethod
+    def forward(ctx, query_ray, offset, ray_logit, attn_raw, time_diff, depth_base, geom):
+        pc_range, d_region, T, M, Pn, D = geom
+        query_ray, offset, ray_logit, attn_raw = (t.contiguous() for t in (query_ray, offset, ray_logit, attn_raw))
+        time_diff = time_diff.contiguous()
+        loc, attn = points.bev_points(query_ray, offset, ray_logit, attn_raw, time_diff, depth_base, pc_range, d_region, T, M,
+                                      Pn, D)
+        ctx.save_for_backward(query_ray, offset, ray_logit, time_diff, depth_base, attn)
+        ctx.geom = geom
+        ctx.shapes = (offset.shape, ray_logit.shape, attn_raw.shape, loc.shape)
+        return loc, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loc, grad_attn):
+        query_ray, offset, ray_logit, time_diff, depth_base, attn = ctx.saved_tensors
+        pc_range, d_region, T, M, Pn, D = ctx.geom
+        grad_loc = (torch.zeros(ctx.shapes[3], dtype=torch.float32, device=attn.device) if grad_loc is None
+                    else grad_loc.contiguous())
+        grad_attn = torch.zeros_like(attn) if grad_attn is None else grad_attn.contiguous()
+        g_ray, g_off, g_logit, g_raw = points.bev_points_backward(
+            query_ray, offset, ray_logit, time_diff, depth_base, pc_range, d_region, T, M, Pn, D, attn, grad_loc, grad_attn,
+            need_ray_grad=ctx.needs_input_grad[0])
+        return g_ray, g_off.view(ctx.shapes[0]), g_logit.view(ctx.shapes[1]), g_raw.view(ctx.shapes[2]), None, None, None
+
+
+class RefineBBox(Function):
+    """Box refinement + velocity scaling + polar -> cartesian output transform (racformer_transformer.py:255-279) with
+    autograd: apply(proposal [B,Q,code], delta [B,Q,code], time_diff [B,T], num_ray) -> (bbox_pred, bbox_xy). bbox_pred (the
+    next iteration's query rays, which the reference detaches, :132) is marked non-differentiable; gradients flow from
+    bbox_xy to delta and the proposal."""
+
+    @staticmethod
+    def forward(ctx, proposal, delta, time_diff, num_ray):
+        proposal, delta, time_diff = proposal.contiguous(), delta.contiguous(), time_diff.contiguous()
+        pred, pred_xy = points.refine_bbox(proposal, delta, time_diff, num_ray)
+        ctx.save_for_backward(proposal, delta, time_diff)
+        ctx.num_ray = num_ray
+        ctx.mark_non_differentiable(pred)
+        return pred, pred_xy
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _grad_pred, grad_xy):
+        proposal, delta, time_diff = ctx.saved_tensors
+        g_delta, g_prop = points.refine_bbox_backward(proposal, delta, time_diff, ctx.num_ray, grad_xy.contiguous(),
+                                                      need_proposal_grad=ctx.needs_input_grad[0])
+        return g_prop, g_delta, None, None
