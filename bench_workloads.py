@@ -752,12 +752,9 @@ class DecoderTrainWorkload(DecoderWorkload):
         self.proj_box = torch.randn(6, batch, q, 10, generator=g).to(self.device)
         self.opt = torch.optim.AdamW(self.model.parameters(), lr=4e-4, weight_decay=0.01)
         self.reducer = GradientAllReducer(list(self.model.parameters()))
-        self.launches_per_step = 3 * self.layers * (3 if checkpoint else 2)   # forward, (checkpoint recompute,) backward
-        if mixing_precision.startswith("bf16") and not checkpoint:
-            # AdaptiveMixing's two Linear layers with autograd on the tcgen05 kernel: per iteration 5 launches forward
-            # (2 operand splits, 2 GEMMs, 1 split-K reduce) and 13 backward (6 splits, 4 GEMMs, 3 reduces), plus the
-            # splits of W and W^T of both layers once per step
-            self.launches_per_step += 18 * self.layers + 4
+        # own launches per step: counted live in step() as the C-ABI calls of the step (each launches at least one kernel;
+        # torch.profiler counts 914 kernels of this library per step at f8, profiles/r02d_train_launch_shares.json)
+        self.launches_per_step = 0
         self.allreduce_bytes = 0
 
     def config(self):
@@ -771,6 +768,8 @@ class DecoderTrainWorkload(DecoderWorkload):
     overlap_allreduce = True
 
     def step(self, time_kernels=False):
+        from racformer_b200 import _lib
+        calls0 = _lib.CALLS[0]
         self._time_kernels = time_kernels
         inp = self.inp
         for t in [inp["lss_bev"], inp["radar_bev"]] + inp["mlvl_feats"]:
@@ -788,6 +787,7 @@ class DecoderTrainWorkload(DecoderWorkload):
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 35.0)
         self.opt.step()
         self._time_kernels = False
+        self.launches_per_step = _lib.CALLS[0] - calls0
         return loss.detach()
 
     def time_allreduce_alone(self, reps=5):
@@ -850,7 +850,7 @@ def train_leg(device, rank, world, parallel, steps=6, warmup=2, name="decoder_tr
     alone = wl.time_allreduce_alone()
     out = {"workload": name, "metric": wl.metric, "value": world * wl.samples_per_step * 1e3 / ms, "unit": "samples/s",
            "ms_per_step": ms, "n_gpus": world, "steps": steps, "warmup": warmup, "scaling": "weak",
-           "loss_finite": bool(torch.isfinite(loss)), "config": wl.config(),
+           "loss_finite": bool(torch.isfinite(loss)), "config": wl.config(), "own_abi_calls_per_step": wl.launches_per_step,
            "allreduce": {"bytes_per_step": wl.reducer.nbytes, "buckets": len(wl.reducer.buckets),
                          "buckets_launched_inside_backward": launched, "alone": alone}}
     del wl

@@ -124,8 +124,12 @@ class Unsupported(RuntimeError):
     GPU path for the same computation (e.g. the decoder's PyTorch operator chain) catch this and use it."""
 
 
+CALLS = [0]   # C-ABI calls that went through check(): each launched at least one kernel (bench.py's launch count in training)
+
+
 def check(code, what):
     """Turn a non-zero status into the RuntimeError the reference's ATen asserts would raise."""
+    CALLS[0] += 1
     if code == -6:
         raise Unsupported(f"{what}: {status_string(code)} (status {code})")
     if code != 0:

@@ -12,7 +12,7 @@
 // every 32-wide tile) added at the end, the bias last (the order of a GEMM epilogue). Weights are kept by the host as
 // chunked transposes W^T [N/256][K][256]; a [32 k][256 column] tile is one contiguous 32 KB block that ONE thread moves
 // into shared memory with cp.async.bulk (TMA engine) behind full / empty mbarriers -- a dedicated producer warp runs
-// the whole program's tile stream through a four-deep ring, across operator boundaries, while 16 consumer warps compute. Every CTA reads the same <= 0.8 MB per Linear from L2: L2 -> SM bandwidth and the FMA pipe bound the
+// the whole program's tile stream through a four-deep ring, across operator boundaries, while 8 consumer warps compute. Every CTA reads the same <= 0.8 MB per Linear from L2: L2 -> SM bandwidth and the FMA pipe bound the
 // kernel, not HBM (a first version with per-thread LDG weight loads was latency-bound at 40 us per 256x256 layer).
 #include <cuda_runtime.h>
 #include <math.h>

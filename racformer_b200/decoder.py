@@ -31,6 +31,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint as _torch_checkpoint
+from .caches import cache_epoch as _cache_epoch
 
 
 # ---------------------------------------------------------------------------------------------- op binding
@@ -682,7 +683,7 @@ class _SplitTF32Linear:
 
     def _weights(self):
         lin = self.linear
-        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version, _cache_epoch())
         if self._key != key:
             w = torch.cat([lin.weight.detach(), lin.bias.detach()[:, None]], dim=1)          # bias as one more K column
             k = w.shape[1]
@@ -783,7 +784,7 @@ class AdaptiveMixing(nn.Module):
             if self._split_gen is None:
                 self._split_gen = _SplitTF32Linear(lin)
             return self._split_gen(query)
-        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+        key = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version, _cache_epoch())
         if self._folded is None or self._folded[0] != key:
             self._folded = (key, torch.cat([lin.weight.detach(), lin.bias.detach()[:, None]], dim=1).contiguous())
         ones = torch.ones_like(query[..., :1])
@@ -1297,6 +1298,17 @@ class RaCFormerTransformer(nn.Module):
     @torch.no_grad()
     def init_weights(self):
         self.decoder.init_weights()
+
+    def load_state_dict(self, *args, **kwargs):
+        from .caches import invalidate_weight_caches   # in-place parameter copies under no_grad: drop the operand splits
+        invalidate_weight_caches()
+        return super().load_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        from .caches import invalidate_weight_caches   # EMA / weight-averaging utilities write through .data between modes
+        if mode != self.training:
+            invalidate_weight_caches()
+        return super().train(mode)
 
     def set_fused_points(self, enabled):
         """Toggle the fused CUDA point-generation / box-refinement kernels, inference and training (eager PyTorch chain

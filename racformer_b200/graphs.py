@@ -31,6 +31,8 @@ class GraphedDecoderForward:
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from .caches import cache_epoch
+        self.epoch = cache_epoch()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.outputs = self._run()
@@ -49,6 +51,11 @@ class GraphedDecoderForward:
                 dst.copy_(src, non_blocking=non_blocking)
 
     def __call__(self, inputs=None):
+        from .caches import cache_epoch
+        if cache_epoch() != self.epoch:
+            raise RuntimeError("GraphedDecoderForward: the weight caches were invalidated after capture (load_state_dict / "
+                               "train() / invalidate_weight_caches()); the graph holds pointers to the old operand splits -- "
+                               "capture a new one")
         if inputs is not None:
             self.load(inputs)
         self.graph.replay()
@@ -93,5 +100,6 @@ class PipelinedDecoderForward:
         return i
 
     def result(self, ticket):
+        """The sample's outputs as fresh host tensors (the slot's pinned buffers are overwritten `depth` submits later)."""
         self.done[ticket].synchronize()
-        return self.host_out[ticket]
+        return [h.clone() for h in self.host_out[ticket]]

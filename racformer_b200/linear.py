@@ -56,6 +56,9 @@ def empty_tiled(rows, K, device):
     return TiledOperand(torch.empty(tiled_bytes(rows, K) // 2, dtype=torch.bfloat16, device=device), rows, K)
 
 
+from .caches import cache_epoch, invalidate_weight_caches  # noqa: E402,F401  (re-exported)
+
+
 def split_tiled(x, addend=None):
     """fp32 CUDA matrix [rows, K] (+ addend [rows_a, K], broadcast with period rows_a over the rows) -> TiledOperand
     (the K tail of the last 32-wide block is zero-filled)."""
@@ -171,7 +174,7 @@ class SplitLinear:
 
     def weight_pieces(self):
         w = self.linear.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), w._version, w.device, cache_epoch())
         if self._key != key:
             self._w3 = self._split(w.detach().contiguous())
             self._key = key
@@ -242,7 +245,7 @@ class TrainableSplitLinear:
 
     def _version_key(self):
         w = self.linear.weight
-        return (w.data_ptr(), w._version, w.device)
+        return (w.data_ptr(), w._version, w.device, cache_epoch())
 
     def weight_pieces(self):
         key = self._version_key()
@@ -282,7 +285,7 @@ class MultiSplitLinear:
         self._key, self._w3 = None, None
 
     def weight_pieces(self):
-        key = tuple((lin.weight.data_ptr(), lin.weight._version) for lin in self.linears)
+        key = tuple((lin.weight.data_ptr(), lin.weight._version) for lin in self.linears) + (cache_epoch(),)
         if self._key != key:
             rows = []
             for lin in self.linears:

@@ -55,7 +55,30 @@ def _check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, 
              "attn_weight must be [bs, num_queries, num_heads, num_levels, num_points]")
     step = min(B, int(im2col_step))
     _require(step > 0 and B % step == 0, f"batch({B}) must divide im2col_step({step})")
+    _check_level_metadata(spatial_shapes, level_start_index, S)
     return B, S, M, D, L, Q, P
+
+
+_VALIDATED_METADATA = {}
+
+
+def _check_level_metadata(spatial_shapes, level_start_index, num_keys):
+    """Every level must lie inside the value map: level_start_index[l] + H_l * W_l <= num_keys. The kernels compute pixel
+    offsets from this device-side metadata, so inconsistent values would read (forward) or `red.add` (backward) out of
+    bounds. The check costs one device -> host copy, so it runs once per metadata tensor pair (keyed on pointer and
+    version counter; the decoder's shapes are cached constants) and is skipped while a CUDA graph is being captured."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version,
+           int(num_keys), str(spatial_shapes.device))
+    if key in _VALIDATED_METADATA or torch.cuda.is_current_stream_capturing():
+        return
+    hw = spatial_shapes.detach().cpu().tolist()
+    lsi = level_start_index.detach().cpu().tolist()
+    for (h, w), start in zip(hw, lsi):
+        _require(h > 0 and w > 0 and start >= 0 and start + h * w <= num_keys,
+                 f"level metadata outside the value map: start {start} + {h} x {w} > num_keys {num_keys}")
+    if len(_VALIDATED_METADATA) > 256:
+        _VALIDATED_METADATA.clear()
+    _VALIDATED_METADATA[key] = True
 
 
 class _ExtModule:
@@ -125,7 +148,11 @@ def msda_tap_masks(spatial_shapes, sampling_loc):
     """Debug entry: uint8 [bs, Q, M, L, P]; bit0 = tap in range, bit1..4 = corners read."""
     _require(sampling_loc.is_cuda and sampling_loc.is_contiguous() and sampling_loc.dtype == torch.float32,
              "sampling_loc must be a contiguous CUDA float tensor")
+    _require(sampling_loc.dim() == 6 and sampling_loc.shape[5] == 2, "sampling_loc must be [bs, Q, M, L, P, 2]")
     B, Q, M, L, P, _ = sampling_loc.shape
+    _require(spatial_shapes.is_cuda and spatial_shapes.device == sampling_loc.device and spatial_shapes.dtype == torch.int64
+             and spatial_shapes.is_contiguous() and tuple(spatial_shapes.shape) == (L, 2),
+             "spatial_shapes must be a contiguous int64 [num_levels, 2] tensor on sampling_loc's device")
     mask = torch.empty((B, Q, M, L, P), dtype=torch.uint8, device=sampling_loc.device)
     with torch.cuda.device(sampling_loc.device):
         rc = _lib.load().racf_msda_tap_masks(spatial_shapes.data_ptr(), sampling_loc.data_ptr(), B, M, L, Q, P,

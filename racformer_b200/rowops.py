@@ -12,6 +12,7 @@ import weakref
 import torch
 
 from . import _lib
+from .caches import cache_epoch as _cache_epoch
 
 _lib.load()
 
@@ -50,7 +51,7 @@ def weight_t(owner, w=None):
     """Weight [N, K] of `owner` (an nn.Linear, or any module holding the parameter `w`) -> its cached chunked transpose
     (rebuilt when the parameter changes)."""
     w = owner.weight if w is None else w
-    key = (w.data_ptr(), w._version, w.device)
+    key = (w.data_ptr(), w._version, w.device, _cache_epoch())
     hit = _transposed.get(owner)
     if hit is None or hit[0] != key:
         hit = _transposed[owner] = (key, chunked_transpose(w.detach()))

@@ -20,6 +20,7 @@ import ctypes
 import torch
 
 from . import _lib, linear as tc_linear, rowops
+from .caches import cache_epoch as _cache_epoch
 from .rowops import (ACCUM, ADD, DROPOUT, LAYERNORM, LAYERNORM_BWD, LINEAR, LINEAR_NARROW, LOAD, LOAD_QUEUE, QUEUE_BWD, RELU,
                      RELU_MASK, STORE, STORE_COLSUM, ZERO, RowOp, chunked_transpose)
 
@@ -97,7 +98,7 @@ _dgrad_cache = {}
 
 def _weight_bwd(e, w):
     """Operand of the input-gradient Linear gx = gy @ W: the chunked transpose of W^T, i.e. W's rows in 256-column chunks."""
-    key = (id(e["owner"]), w.data_ptr(), w._version)
+    key = (id(e["owner"]), w.data_ptr(), w._version, _cache_epoch())
     hit = _dgrad_cache.get(id(e["owner"]))
     if hit is None or hit[0] != key:
         hit = _dgrad_cache[id(e["owner"])] = (key, chunked_transpose(w.detach().t()))

@@ -356,3 +356,31 @@ def test_decoder_parameters_as_views_into_a_flat_buffer_gpu():
                     ref_inp["radar_bev"], None, ref_inp["img_metas"])
     _close(got[0], want[0], "cls, flat-buffer parameter views", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
     _close(got[1], want[1], "box, flat-buffer parameter views", rtol=1e-3, atol=1e-3, max_outlier_frac=0.005)
+
+
+@pytest.mark.gpu
+def test_weight_caches_follow_data_updates_after_invalidation_and_graph_refuses_stale_replay():
+    """updates through `.data` do not bump autograd's version counter, so the bf16x3 operand splits / transposes
+    need the explicit epoch (racformer_b200/caches.py); a graph captured before the invalidation must not replay."""
+    from racformer_b200 import caches
+    from racformer_b200.graphs import GraphedDecoderForward
+    model = _my_model().cuda()
+    inp = small_inputs(seed=2, device="cuda")
+    args = (inp["query_bbox"], inp["query_feat"], inp["mlvl_feats"], inp["lss_bev"], inp["radar_bev"], None, inp["img_metas"])
+    with torch.no_grad():
+        before = [t.clone() for t in model(*args)]
+        graphed = GraphedDecoderForward(model, inp)
+        for p in model.parameters():
+            p.data.mul_(1.05)                      # EMA-style update: invisible to the version counter
+        caches.invalidate_weight_caches()
+        after = model(*args)
+        model.set_mixing_precision("fp32")          # cuBLAS SGEMM path: no weight-derived caches in the mixing layers
+        model.decoder.decoder_layer.row_programs = False
+        model.decoder.decoder_layer.stacked_heads = False
+        plain = model(*args)
+    assert float((after[0] - before[0]).abs().max()) > 1e-4, "the update must change the output"
+    for a, b in zip(after, plain):
+        bad = (a - b).abs() > 1e-3 + 1e-3 * b.abs()
+        assert float(bad.float().mean()) <= 5e-3
+    with pytest.raises(RuntimeError, match="invalidated after capture"):
+        graphed()

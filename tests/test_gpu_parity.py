@@ -321,6 +321,13 @@ def test_msda_errors():
     with pytest.raises(RuntimeError, match="contiguous"):
         strided = torch.zeros(6, 16, 1, 128, device=DEV)[..., ::2]
         msda.ext_module.ms_deform_attn_forward(strided, sp, lsi, loc, aw, im2col_step=64)
+    # level metadata that does not fit the value map (would read / red.add out of bounds) is refused
+    with pytest.raises(RuntimeError, match="outside the value map"):
+        msda.ext_module.ms_deform_attn_forward(value, torch.tensor([[5, 4]], device=DEV), lsi, loc, aw, im2col_step=64)
+    with pytest.raises(RuntimeError, match="outside the value map"):
+        msda.ext_module.ms_deform_attn_forward(value, sp, torch.tensor([1], device=DEV), loc, aw, im2col_step=64)
+    with pytest.raises(RuntimeError, match="spatial_shapes"):
+        msda.msda_tap_masks(sp.int(), loc)
 
 
 # ------------------------------------------------------------------------------------------------ guard bands
