@@ -479,7 +479,7 @@ int racf_refine_bbox_backward(const float* proposal, const float* delta, const f
  *                  (gradient of the logits; skipped when p1 == NULL)
  * LOAD_QUEUE needs n, ld, dst_col multiples of 4 and a 16-byte aligned p0.
  * fp32 FMA on the CUDA cores, bias added last. `ops` is a HOST array, copied into the kernel parameters
- * (capture-safe). rows_per_cta is 4 or 8; 128 KB (weight tiles) + (num_bufs * width + 768) * rows_per_cta * 4 bytes <= 226 KB.
+ * (capture-safe). rows_per_cta is 4 .. 8; 128 KB (weight tiles) + (num_bufs * width + 768) * rows_per_cta * 4 bytes <= 226 KB.
  */
 #define RACF_ROW_MAX_OPS        128
 #define RACF_ROW_MAX_QUEUE      16

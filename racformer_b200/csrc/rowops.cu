@@ -714,7 +714,7 @@ extern "C" int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, i
     using namespace racf;
     if (!ops) return RACF_ERR_NULL_POINTER;
     if (num_ops <= 0 || num_ops > RACF_ROW_MAX_OPS || rows <= 0 || num_bufs <= 0 || width <= 0) return RACF_ERR_BAD_SHAPE;
-    if ((width & 3) != 0 || (rows_per_cta != 4 && rows_per_cta != 8)) return RACF_ERR_UNSUPPORTED;
+    if ((width & 3) != 0 || rows_per_cta < 4 || rows_per_cta > 8) return RACF_ERR_UNSUPPORTED;
     RowProgram prog;
     for (int i = 0; i < num_ops; ++i) {
         const int rc = validate(ops[i], width, num_bufs);
@@ -726,5 +726,11 @@ extern "C" int racf_row_program_forward(const racf_row_op_t* ops, int num_ops, i
     prog.width = width;
     prog.num_bufs = num_bufs;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return rows_per_cta == 4 ? launch<4>(prog, st) : launch<8>(prog, st);
+    switch (rows_per_cta) {
+        case 4: return launch<4>(prog, st);
+        case 5: return launch<5>(prog, st);
+        case 6: return launch<6>(prog, st);
+        case 7: return launch<7>(prog, st);
+        default: return launch<8>(prog, st);
+    }
 }

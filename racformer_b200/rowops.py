@@ -62,12 +62,33 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_sm_count = {}
+
+
+def choose_rows_per_cta(rows, num_bufs, width, device=None):
+    """Rows a CTA carries through the chain (4..8). A CTA's time grows with its rows (the FMA work; every CTA streams the same
+    weights), and CTAs run one per SM in waves, so the cost of a launch is waves x rows_per_cta: 900 rows -> 7 (129 CTAs, one
+    wave on 148 SMs, instead of 113 CTAs of 8), 2440 rows -> 6 (407 CTAs, three waves of 6, instead of 305 CTAs = two full
+    waves + 9 CTAs of 8). Ties go to the larger tile (fewer weight re-reads). The row buffers and the k-group scratch share
+    the 98 KB of shared memory the weight-tile ring leaves."""
+    per_row = int(num_bufs) * int(width) * 4 + 3 * CHUNK_COLS * 4
+    fits = [r for r in range(4, 9) if r * per_row <= ROW_BUFFER_BYTES + 3 * CHUNK_COLS * 4 * 8]
+    if not fits:
+        return 4
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    sms = _sm_count.get(dev)
+    if sms is None:
+        sms = _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count if torch.cuda.is_available() else 148
+    cost = lambda r: (-(-(-(-int(rows) // r)) // sms)) * r
+    return min(fits, key=lambda r: (cost(r), -r))
+
+
 class RowProgram:
     """Builds and launches one row program over `rows` rows. Buffers are numbered 0..num_bufs-1, `width` floats each."""
 
     def __init__(self, rows, width, num_bufs=3, rows_per_cta=None, device=None):
-        if rows_per_cta is None:      # the row buffers share ~74 KB of shared memory with the weight-tile ring
-            rows_per_cta = 8 if int(num_bufs) * int(width) * 8 * 4 <= ROW_BUFFER_BYTES else 4
+        if rows_per_cta is None:
+            rows_per_cta = choose_rows_per_cta(rows, num_bufs, width, device)
         self.rows, self.width, self.num_bufs, self.rows_per_cta = int(rows), int(width), int(num_bufs), int(rows_per_cta)
         self.device = device
         self.ops, self._keep = [], []

@@ -108,7 +108,7 @@ def _weight_bwd(e, w):
 def _launch(ops, rows, num_bufs, width, device):
     if len(ops) > rowops.MAX_OPS:
         raise _lib.Unsupported(f"row program of {len(ops)} operators (limit {rowops.MAX_OPS})")
-    rows_per_cta = 8 if num_bufs * width * 8 * 4 <= rowops.ROW_BUFFER_BYTES else 4
+    rows_per_cta = rowops.choose_rows_per_cta(rows, num_bufs, width, device)
     arr = (RowOp * len(ops))(*ops)
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -38,7 +38,7 @@ def _rel_err(a, ref64):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rows,rows_per_cta", [(900, 8), (13, 8), (1, 4), (2440, 4)])
+@pytest.mark.parametrize("rows,rows_per_cta", [(900, 8), (13, 8), (1, 4), (2440, 4), (900, 7), (2440, 6), (33, 5), (900, None)])
 def test_mlp_chain_matches_torch_and_fp64(rows, rows_per_cta):
     from racformer_b200 import rowops
     dev = torch.device("cuda", 0)

@@ -26,7 +26,7 @@ if [ "$WHAT" = decoder ] || [ "$WHAT" = all ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/${TAG}_decoder_launches.csv $CMD > $OUT/${TAG}_ncu_decoder_launch.log 2>&1
   $CMD > $OUT/${TAG}_plain_decoder2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:'msmv_fwd|msda_fwd|adaptive_mixing_tc|linear_bf16x3_kernel|row_program|sasa_attention' -c 40 -f -o $OUT/${TAG}_decoder $CMD > $OUT/${TAG}_ncu_decoder.log 2>&1
+      -k regex:'msmv_fwd|msda_fwd|adaptive_mixing_ws|linear_bf16x3_wide|row_program|sasa_attention' -c 40 -f -o $OUT/${TAG}_decoder $CMD > $OUT/${TAG}_ncu_decoder.log 2>&1
   tail -1 $OUT/${TAG}_ncu_decoder.log
   ncu -i $OUT/${TAG}_decoder.ncu-rep --page raw --csv > $OUT/${TAG}_decoder_raw.csv 2>/dev/null
   python tools/ncu_raw_summary.py $OUT/${TAG}_decoder_raw.csv > $OUT/${TAG}_decoder_summary.json

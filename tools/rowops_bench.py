@@ -104,6 +104,14 @@ def main():
         res["self_attn_torch_graph_us"], _ = graph_time(
             lambda: layer.norm1(layer.self_attn(qb, qf + layer.position_encoder(qb[..., :3]), None)))
         res["tail_torch_graph_us"], _ = graph_time(torch_tail)
+        # rows per CTA (the default is rowops.choose_rows_per_cta: waves x rows)
+        auto = rowops.choose_rows_per_cta
+        res["tail_rows_per_cta_auto"] = auto(B * Q, 3, 3 * E, dev)
+        for rpc in (8, 7, 6, 5):
+            rowops.choose_rows_per_cta = lambda *a, _r=rpc, **k: _r
+            res[f"tail_rows_graph_rows{rpc}_us"], _ = graph_time(lambda: layer._tail_rows(mixed, qf, radar, lss))
+            res[f"self_attn_fused_graph_rows{rpc}_us"], _ = graph_time(lambda: layer._self_attn_rows(qb, qf))
+        rowops.choose_rows_per_cta = auto
     print(json.dumps(res, indent=1))
 
 
