@@ -320,6 +320,12 @@ int racf_adaptive_mixing_tc_forward_variant(const float* x, const float* params,
 int racf_adaptive_mixing_backward(const float* x, const float* params, const float* grad_out, int num_query_groups,
                                   int in_points, int out_points, int channels, float eps, float* grad_x,
                                   float* grad_params, racf_stream_t stream);
+/* The same with an explicit kernel choice: variant 0 = default, 1 = fp32 FMA on the CUDA cores (csrc/mixing_bwd.cu),
+ * 2 = all six products on the tensor cores (tcgen05, exact bf16x3 operand splitting, csrc/mixing_bwd_tc.cu; in_points <= 96,
+ * else RACF_ERR_UNSUPPORTED). Results agree to fp32 rounding of the products. */
+int racf_adaptive_mixing_backward_variant(const float* x, const float* params, const float* grad_out, int num_query_groups,
+                                          int in_points, int out_points, int channels, float eps, float* grad_x,
+                                          float* grad_params, int variant, racf_stream_t stream);
 
 
 /*

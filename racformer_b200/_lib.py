@@ -54,6 +54,8 @@ SIGNATURES = {
                                                      ctypes.c_void_p, _i, _i, ctypes.c_void_p]),
     "racf_adaptive_mixing_backward": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
                                            _c_float_p, ctypes.c_void_p]),
+    "racf_adaptive_mixing_backward_variant": (_i, [_c_float_p, _c_float_p, _c_float_p, _i, _i, _i, _i, ctypes.c_float, _c_float_p,
+                                                   _c_float_p, _i, ctypes.c_void_p]),
     "racf_linear_tiled_bytes": (ctypes.c_longlong, [ctypes.c_longlong, _i]),
     "racf_split_bf16x3_tiled": (_i, [_c_float_p, ctypes.c_longlong, _i, ctypes.c_void_p, ctypes.c_void_p]),
     "racf_split_bf16x3_tiled_add": (_i, [_c_float_p, ctypes.c_longlong, _i, _c_float_p, ctypes.c_longlong, ctypes.c_void_p,

@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.environ.get("RACF_LIB_PATH") or os.path.join(LIB_DIR, "libracformer_ops.so")   # override: tuning experiments
 STAMP = LIB_PATH + ".srchash"
 
-SOURCES = ["msmv.cu", "msda.cu", "points.cu", "points_train.cu", "layout.cu", "bev_pool.cu", "mixing.cu", "mixing_bwd.cu", "mixing_tc.cu", "mixing_ws.cu", "linear.cu", "linear_wide.cu", "rowops.cu", "sasa.cu", "sasa_train.cu"]
+SOURCES = ["msmv.cu", "msda.cu", "points.cu", "points_train.cu", "layout.cu", "bev_pool.cu", "mixing.cu", "mixing_bwd.cu", "mixing_bwd_tc.cu", "mixing_tc.cu", "mixing_ws.cu", "linear.cu", "linear_wide.cu", "rowops.cu", "sasa.cu", "sasa_train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

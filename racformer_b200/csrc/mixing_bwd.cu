@@ -306,23 +306,46 @@ adaptive_mixing_bwd_kernel(const float* __restrict__ x, const float* __restrict_
 }  // namespace mixbwd
 }  // namespace racf
 
-extern "C" int racf_adaptive_mixing_backward(const float* x, const float* params, const float* grad_out, int num_query_groups,
-                                             int in_points, int out_points, int channels, float eps, float* grad_x,
-                                             float* grad_params, racf_stream_t stream) {
+int racf_mixbwd_tc_launch(const float* x, const float* params, const float* grad_out, int num_query_groups, int in_points, float eps,
+                          float* grad_x, float* grad_params, int sms, cudaStream_t st);   // csrc/mixing_bwd_tc.cu
+
+// Which kernel variant 0 selects where both exist (in_points <= 96): tools/mixing_bwd_check.py measures both.
+constexpr bool kDefaultTensorCores = true;     // 1.40 ms vs 2.67 ms for 9760 items at P_in = 96 (profiles/r02f_mixing_bwd_check.json)
+
+// variant: 0 = default, 1 = CUDA-core kernel of this file, 2 = tcgen05 kernel (csrc/mixing_bwd_tc.cu; RACF_ERR_UNSUPPORTED for
+// in_points > 96).
+extern "C" int racf_adaptive_mixing_backward_variant(const float* x, const float* params, const float* grad_out,
+                                                     int num_query_groups, int in_points, int out_points, int channels, float eps,
+                                                     float* grad_x, float* grad_params, int variant, racf_stream_t stream) {
     using namespace racf::mixbwd;
     if (!x || !params || !grad_out || !grad_x || !grad_params) return RACF_ERR_NULL_POINTER;
     if (num_query_groups <= 0) return RACF_ERR_BAD_SHAPE;
     if (channels != kC || out_points != kPout || in_points < 16 || in_points > 128 || (in_points & 15) != 0)
         return RACF_ERR_UNSUPPORTED;
+    if (variant < 0 || variant > 2 || (variant == 2 && in_points > 96)) return RACF_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grad_out) |
          reinterpret_cast<uintptr_t>(grad_x) | reinterpret_cast<uintptr_t>(grad_params)) & 15u)
         return RACF_ERR_UNSUPPORTED;
-    const size_t smem = sizeof(float) * (size_t)(2 * in_points * kC + kC * kC + kC * kMtStride + kPout * in_points + kPout * kC);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (variant == 2 || (variant == 0 && kDefaultTensorCores && in_points <= 96)) {
+        int dev = 0, sms = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        return racf_mixbwd_tc_launch(x, params, grad_out, num_query_groups, in_points, eps, grad_x, grad_params, sms, st);
+    }
+    const size_t smem = sizeof(float) * (size_t)(2 * in_points * kC + kC * kC + kC * kMtStride + kPout * in_points + kPout * kC);
     // TY = 16 (256 threads): measured 2.65 ms for 9760 items at P_in = 96 against 2.83 ms with TY = 32 (512 threads halve the
     // rows a thread amortises each shared-memory operand load over; the shared-memory pipe then limits)
     cudaError_t e = cudaFuncSetAttribute(adaptive_mixing_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     adaptive_mixing_bwd_kernel<16><<<(unsigned)num_query_groups, 256, smem, st>>>(x, params, grad_out, grad_x, grad_params, in_points, eps);
     return (int)cudaGetLastError();
+}
+
+extern "C" int racf_adaptive_mixing_backward(const float* x, const float* params, const float* grad_out, int num_query_groups,
+                                             int in_points, int out_points, int channels, float eps, float* grad_x,
+                                             float* grad_params, racf_stream_t stream) {
+    return racf_adaptive_mixing_backward_variant(x, params, grad_out, num_query_groups, in_points, out_points, channels, eps, grad_x,
+                                                 grad_params, 0, stream);
 }

@@ -221,18 +221,19 @@ def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_gro
     return out
 
 
-def adaptive_mixing_core_backward(x, params, grad_out, out_points, eps=1e-5):
+def adaptive_mixing_core_backward(x, params, grad_out, out_points, eps=1e-5, variant=0):
     """Backward of adaptive_mixing_core: (grad_x like x, grad_params like params); None when the kernel does not exist for
-    the shapes. Recomputes the forward from x and params (csrc/mixing_bwd.cu)."""
+    the shapes. Recomputes the forward from x and params. variant: 0 = default, 1 = CUDA cores (csrc/mixing_bwd.cu),
+    2 = tensor cores (csrc/mixing_bwd_tc.cu, P_in <= 96)."""
     _check(x, params, grad_out)
     QG, P_in, C = x.shape
     if not (C == 64 and out_points == 128 and P_in % 16 == 0 and 16 <= P_in <= 128):
         return None
     grad_x, grad_params = torch.empty_like(x), torch.empty_like(params)
     with torch.cuda.device(x.device):
-        rc = _lib.load().racf_adaptive_mixing_backward(x.data_ptr(), params.data_ptr(), grad_out.data_ptr(), QG, P_in,
-                                                       out_points, C, float(eps), grad_x.data_ptr(), grad_params.data_ptr(),
-                                                       _stream(x.device))
+        rc = _lib.load().racf_adaptive_mixing_backward_variant(x.data_ptr(), params.data_ptr(), grad_out.data_ptr(), QG, P_in,
+                                                               out_points, C, float(eps), grad_x.data_ptr(),
+                                                               grad_params.data_ptr(), int(variant), _stream(x.device))
     _lib.check(rc, "racf_adaptive_mixing_backward")
     return grad_x, grad_params
 

@@ -165,6 +165,32 @@ def test_adaptive_mixing_core_function_gradients_vs_fp64_autograd(p_in):
         assert err <= max(3 * err_eager, 2e-5), (name, err, err_eager)
 
 
+@pytest.mark.parametrize("QG,p_in", [(3, 96), (449, 96), (40, 16), (40, 80)])
+def test_adaptive_mixing_backward_tensor_core_and_cuda_core_kernels_agree_with_fp64(QG, p_in):
+    """Both backward kernels (csrc/mixing_bwd_tc.cu: all six products as tcgen05 MMAs on exact bf16x3 pieces; csrc/mixing_bwd.cu:
+    fp32 FMA) against fp64 autograd of the chain, per gradient: 2e-6 of the gradient's largest magnitude."""
+    import torch.nn.functional as F
+    from racformer_b200 import points
+    g = torch.Generator(device="cuda").manual_seed(5)
+    C, P_out = 64, 128
+    x = torch.randn(QG, p_in, C, device="cuda", generator=g)
+    params = torch.randn(QG, C * C + P_out * p_in, device="cuda", generator=g) * 0.2
+    gy = torch.randn(QG, P_out, C, device="cuda", generator=g)
+    x64, p64 = x.double().requires_grad_(), params.double().requires_grad_()
+    m, s = p64.split([C * C, P_out * p_in], 1)
+    t = F.relu(F.layer_norm(torch.matmul(x64, m.reshape(QG, C, C)), [p_in, C]))
+    F.relu(F.layer_norm(torch.matmul(s.reshape(QG, P_out, p_in), t), [P_out, C])).backward(gy.double())
+    for variant in (1, 2):
+        gx, gp = points.adaptive_mixing_core_backward(x, params, gy, P_out, variant=variant)
+        for name, got, want in (("g_x", gx, x64.grad), ("g_M", gp[:, :C * C], p64.grad[:, :C * C]),
+                                ("g_S", gp[:, C * C:], p64.grad[:, C * C:])):
+            err = float((got.double() - want).abs().max() / want.abs().max())
+            assert err < 2e-6, (variant, name, err)
+    with pytest.raises(RuntimeError):       # the tensor-core kernel holds P_in <= 96 rows per tile
+        points.adaptive_mixing_core_backward(torch.randn(2, 128, C, device="cuda"), torch.randn(2, C * C + P_out * 128, device="cuda"),
+                                             torch.randn(2, P_out, C, device="cuda"), P_out, variant=2)
+
+
 def _row_chain_case(dev, seed=0, rows=200, E=256, T=4, B=2):
     import torch.nn as nn
     torch.manual_seed(seed)
