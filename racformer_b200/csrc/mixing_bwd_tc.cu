@@ -12,22 +12,26 @@
 // in tensor memory (a0*b0 and the cross terms in separate accumulators, see csrc/linear.cu), so every product is
 // fp32-grade; the layer norms and their backward run in fp32 on the CUDA cores straight from tensor memory.
 //
-// One persistent CTA (512 threads) per SM walks its items phase by phase. Operand tiles (bf16 x 3 pieces, shared memory):
-//   X3  [p][c]        K-major, 128-byte rows, 128-byte swizzle   A of o1 = x M
-//   M3  [c'][c]       the same tile is B of o1 (K-major, K = c) and B of g_x (MN-major, K = c')
-//   S3  [o][p]        K-major 32-wide atoms, 64-byte swizzle      A of o2 = S t
-//   T3  [p][c']       B of o2 (MN-major, K = p) and B of g_S (K-major, K = c', N = P_in)
-//   G2  [o][c']       g_o2: A of g_S (K-major) and B of g_t (MN-major, K = o)
-//   ST3 [p][o]        S transposed while it is read a second time (two 64-wide K tiles): A of g_t. Overwrites S3.
-//   G1  [p][c']       g_o1: A of g_x (K-major) and B of g_M (MN-major, K = p). Overwrites T3.
-//   XT3 [c][p]        x transposed (32-wide atoms): A of g_M (M = 128 with 64 live rows). Overwrites ST3.
-// Every contraction that runs over the row index of a stored operand gets a transposed copy of that operand (S^T, x^T,
-// read again from L2) instead of an MN-major A descriptor. Rows / columns that are never written only feed accumulator rows
-// that are never read. 216 KB of shared memory, 512 columns of tensor memory.
+// One persistent CTA (512 threads) per SM walks its items phase by phase. Operand tiles (bf16 x 3 pieces, shared memory);
+// every tile serves two products, once K-major and once MN-major (the descriptor's major-ness bit), so nothing is transposed:
+//   X3  [p][c]   128-byte rows, 128-byte swizzle   A of o1 = x M (K-major, K = c)       A of g_M = x^T g_o1 (MN-major, K = p)
+//   M3  [c'][c]  = M^T                             B of o1 (K-major, K = c)             B of g_x = g_o1 M^T (MN-major, K = c')
+//   S3  [o][p]   32-wide atoms, 64-byte swizzle    A of o2 = S t (K-major, K = p)       A of g_t = S^T g_o2 (MN-major, K = o)
+//   T3  [p][c']  t, 128-byte swizzle               B of o2 (MN-major, K = p)            B of g_S = g_o2 t^T (K-major, N = P_in)
+//   G2  [o][c']  g_o2                              A of g_S (K-major, K = c')           B of g_t (MN-major, K = o)
+//   G1  [p][c']  g_o1, overwrites T3               A of g_x (K-major, K = c')           B of g_M (MN-major, K = p)
+// MN-major A (instruction-descriptor bit 15): LBO = distance between the swizzle atoms along M, SBO = distance between the
+// 8-row groups along K (measured: the swapped assignment gives wrong results). Rows that are never written (p >= P_in, and
+// the upper half of g_M's M = 128) only feed accumulator rows that are never read. Overlap: g_S leaves tensor memory while
+// g_t is being computed; the next item's S is split while g_M / g_x are computed.
+// 216 KB of shared memory, 448 of the 512 columns of tensor memory.
 // Implemented for C == 64, P_out == 128, P_in % 16 == 0, 16 <= P_in <= 96 (csrc/mixing_bwd.cu covers P_in <= 128).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef RACF_MIXBT_PROFILE
+#include <cstdio>
+#endif
 
 #include "racformer_ops.h"
 
@@ -37,7 +41,7 @@ namespace mixbt {
 constexpr int kC = 64, kPout = 128, kMaxPin = 96, kThreads = 512;
 constexpr int kXPiece = kMaxPin * 128;      // 12 KB  [96 p][64 c]
 constexpr int kMPiece = kC * 128;           //  8 KB  [64 c'][64 c]
-constexpr int kSPiece = 3 * 8192;           // 24 KB  S3: 3 atoms of [128 o][32 p]; ST3: 2 tiles of [96 p][64 o]; XT3: 3 atoms of [64 c][32 p]
+constexpr int kSPiece = 3 * 8192;           // 24 KB  3 atoms of [128 o][32 p]
 constexpr int kTPiece = kMaxPin * 128;      // 12 KB  [96 p][64 c']
 constexpr int kGPiece = kPout * 128;        // 16 KB  [128 o][64 c']
 constexpr int kX3 = 0;
@@ -48,9 +52,10 @@ constexpr int kG3 = kT3 + 3 * kTPiece;
 constexpr int kSmemBytes = kG3 + 3 * kGPiece;   // 216 KB
 static_assert(kM3 % 1024 == 0 && kS3 % 1024 == 0 && kT3 % 1024 == 0 && kG3 % 1024 == 0, "swizzle atoms are 1 KB aligned");
 constexpr int kTmemCols = 512;
-// tensor-memory columns (main, cross): D1 (0, 64) o1 | D2 (128, 192) o2 | D3 (128, 224) g_S, 96 wide | D4 (320, 384) g_t |
-// D5 (0, 64) g_M | D6 (128, 192) g_x
-constexpr uint32_t kD1 = 0, kD2 = 128, kD3 = 128, kD3x = 224, kD4 = 320, kD5 = 0, kD6 = 128;
+// tensor-memory columns (main, cross): D1 (0, 64) o1 | D2 (128, 192) o2 | D3 (128, 224) g_S, 96 wide, over D2 | D4 (320, 384) g_t |
+// D5 (128, 192) g_M, over D2 / D3 | D6 (320, 384) g_x, over D4. D1 is free again when g_M / g_x are read out: the next item's
+// o1 runs meanwhile.
+constexpr uint32_t kD1 = 0, kD2 = 128, kD3 = 128, kD3x = 224, kD4 = 320, kD5 = 128, kD6 = 320;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -102,6 +107,10 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {     // K-major,
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t addr) {   // [k rows][64 n] bf16, 128-byte rows, 8-row groups 1 KB apart
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
+}
+
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
 // exact three-way split of two floats: x = p0 + p1 + p2, bf16 pieces, round to nearest at each step
@@ -203,52 +212,6 @@ __device__ __forceinline__ void load_split_s(const float* __restrict__ sg, uint8
         }
     }
 }
-// S [128 o][P_in] -> ST3 = S^T: two K tiles (o < 64, o >= 64) of [P_in rows p][64 o], 128-byte swizzle. A thread owns row p and
-// a chunk of 8 o; lanes run along p (coalesced 4-byte loads of S's rows).
-__device__ __forceinline__ void load_split_st(const float* __restrict__ sg, uint8_t* sm, int p_in, int tid) {
-    constexpr int kIt = kMaxPin * 16 / kThreads;               // 3
-    float f[kIt][8];
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-        const int i = tid + it * kThreads;
-        if (i < p_in * 16) {
-            const int j = i / p_in, p = i - j * p_in;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) f[it][jj] = __ldg(sg + (j * 8 + jj) * p_in + p);
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-        const int i = tid + it * kThreads;
-        if (i < p_in * 16) {
-            const int j = i / p_in, p = i - j * p_in;
-            split_store8(f[it], sm + kS3, kSPiece, (j >> 3) * kXPiece + p * 128 + (((j & 7) ^ (p & 7)) << 4));
-        }
-    }
-}
-// x [P_in][64] -> XT3 = x^T: 32-wide K atoms (4 KB apart) of [64 rows c][64 B], 64-byte swizzle. Lanes run along c.
-__device__ __forceinline__ void load_split_xt(const float* __restrict__ xg, uint8_t* sm, int p_in, int tid) {
-    constexpr int kIt = kC * (kMaxPin / 8) / kThreads + ((kC * (kMaxPin / 8)) % kThreads != 0);    // 2
-    float f[kIt][8];
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-        const int i = tid + it * kThreads;
-        if (i < kC * (p_in >> 3)) {
-            const int c = i & 63, j = i >> 6;
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) f[it][jj] = __ldg(xg + (j * 8 + jj) * kC + c);
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-        const int i = tid + it * kThreads;
-        if (i < kC * (p_in >> 3)) {
-            const int c = i & 63, j = i >> 6;
-            split_store8(f[it], sm + kS3, kSPiece, (j >> 2) * 4096 + c * 64 + (((j & 3) ^ ((c >> 1) & 3)) << 4));
-        }
-    }
-}
-
 // One product: D = A B with the six largest piece products; a0*b0 into d_main, the five cross terms into d_cross.
 // a_off / b_off: byte offset of K step ks (16 elements of K) inside a piece tile.
 template <typename AOff, typename BOff>
@@ -286,21 +249,28 @@ __device__ __forceinline__ void split_store_row16(const float (&f)[16], uint8_t*
     split_store8(f + 8, tile, piece_bytes, row * 128 + (((ch + 1) ^ (row & 7)) << 4));
 }
 
+#ifdef RACF_MIXBT_PROFILE      // tuning aid: per-phase cycle counts of CTA 0 (build with RACF_NVCC_DEFINES=-DRACF_MIXBT_PROFILE)
+#define MIXBT_TICK(slot) do { if (tid == 0) { const long long now_ = clock64(); prof[slot] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define MIXBT_TICK(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ params, const float* __restrict__ gy,
                               float* __restrict__ grad_x, float* __restrict__ grad_params, int num_items, int p_in, float eps) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float2 red[kThreads / 32];
 
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sm_addr = smem_u32(sm);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_addr = smem_u32(&bar);
+    const uint32_t bar_a = smem_u32(&bars[0]), bar_b = smem_u32(&bars[1]);   // bar_b: g_S alone (its read-out overlaps g_t)
 
     if (tid == 0) {
-        mbar_init(bar_addr, 1);
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -312,16 +282,17 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    // instruction descriptors: fp32 accumulate, bf16 x bf16, M = 128; bit 16 = B is MN-major
+    // instruction descriptors: fp32 accumulate, bf16 x bf16, M = 128; bit 15 / 16 = A / B is MN-major
     constexpr uint32_t kIdescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idesc_kk = kIdescBase | ((uint32_t)(kC >> 3) << 17);                 // N = 64, both K-major
     constexpr uint32_t idesc_kn = idesc_kk | (1u << 16);                                    // N = 64, B MN-major
+    constexpr uint32_t idesc_nn = idesc_kn | (1u << 15);                                    // N = 64, A and B MN-major
     const uint32_t idesc_gs = kIdescBase | ((uint32_t)(p_in >> 3) << 17);                   // N = P_in, both K-major
     const int ksteps_p = p_in >> 4;
 
-    const uint64_t d_x3 = desc_kmajor<128>(sm_addr + kX3), d_m3_k = desc_kmajor<128>(sm_addr + kM3);
-    const uint64_t d_m3_n = desc_mnmajor_sw128(sm_addr + kM3);
-    const uint64_t d_s3 = desc_kmajor<64>(sm_addr + kS3), d_st3 = desc_kmajor<128>(sm_addr + kS3), d_xt3 = desc_kmajor<64>(sm_addr + kS3);
+    const uint64_t d_x3_k = desc_kmajor<128>(sm_addr + kX3), d_x3_n = desc_mnmajor_sw128(sm_addr + kX3);
+    const uint64_t d_m3_k = desc_kmajor<128>(sm_addr + kM3), d_m3_n = desc_mnmajor_sw128(sm_addr + kM3);
+    const uint64_t d_s3_k = desc_kmajor<64>(sm_addr + kS3), d_s3_n = desc_mnmajor(sm_addr + kS3, 8192, 512, 4);
     const uint64_t d_t3_n = desc_mnmajor_sw128(sm_addr + kT3), d_t3_k = desc_kmajor<128>(sm_addr + kT3);   // also G1
     const uint64_t d_g2_k = desc_kmajor<128>(sm_addr + kG3), d_g2_n = desc_mnmajor_sw128(sm_addr + kG3);
 
@@ -331,37 +302,61 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
     const long long per_item = kC * kC + (long long)kPout * p_in;
     const bool live = row < p_in;
     const float n1_cnt = (float)(p_in * kC), n2_cnt = (float)(kPout * kC);
-    uint32_t phase = 0;
+    uint32_t phase_a = 0, phase_b = 0;
+#ifdef RACF_MIXBT_PROFILE
+    long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+
+    // o1 = x M (recompute) of an item is issued as soon as its X3 / M3 are in place: for the first item here, for the others
+    // at the end of the previous item's loop body, under the read-out of that item's g_M / g_x
+    auto issue_o1 = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+                issue_product(tmem + kD1, tmem + kD1 + 64, d_x3_k, d_m3_k, kXPiece, kMPiece, 4, idesc_kk,
+                              [](int ks) { return ks * 32; }, [](int ks) { return ks * 32; });
+                umma_commit(bar_a);
+            }
+            __syncwarp();
+        }
+    };
+    auto prefetch_item = [&](int it) {          // pull an item's inputs into L2 well before they are read (128-byte lines)
+        const char* px = reinterpret_cast<const char*>(x + (long long)it * p_in * kC);
+        const char* pp = reinterpret_cast<const char*>(params + (long long)it * per_item);
+        const char* pgy = reinterpret_cast<const char*>(gy + (long long)it * (kPout * kC));
+        for (int i = tid * 128; i < p_in * kC * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + i));
+        for (int i = tid * 128; i < (int)per_item * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + i));
+        for (int i = tid * 128; i < kPout * kC * 4; i += kThreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pgy + i));
+    };
 
     if ((int)blockIdx.x < num_items) {
+        const float* pg0 = params + (long long)blockIdx.x * per_item;
         load_split_x(x + (long long)blockIdx.x * p_in * kC, sm, p_in, tid);
-        load_split_m(params + (long long)blockIdx.x * per_item, sm, tid);
+        load_split_m(pg0, sm, tid);
+        issue_o1();
+        load_split_s(pg0 + kC * kC, sm, p_in, tid);
     }
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int nxt = item + gridDim.x;
-        const float* pg = params + (long long)item * per_item;
-        const float* xg = x + (long long)item * p_in * kC;
         float* gpg = grad_params + (long long)item * per_item;
+        MIXBT_TICK(0);
 
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- o1 = x M (recompute) -----------------------------------------------------------------------------------------
-        if (warp == 0) {
-            if (elect_one()) {
-                tc_fence_after();
-                issue_product(tmem + kD1, tmem + kD1 + 64, d_x3, d_m3_k, kXPiece, kMPiece, 4, idesc_kk,
-                              [](int ks) { return ks * 32; }, [](int ks) { return ks * 32; });
-                umma_commit(bar_addr);
-            }
-            __syncwarp();
+        // ---- o1 = x M (recompute) is in flight -------------------------------------------------------------------------------
+        if (nxt < num_items) prefetch_item(nxt);
+        float4 gyv[4];                                       // gy[o = row][col0 .. col0 + 15]: needed after o2, loaded now
+        {
+            const float4* gp = reinterpret_cast<const float4*>(gy + (long long)item * (kPout * kC) + row * kC + col0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gyv[c] = __ldg(gp + c);
         }
-        load_split_s(pg + kC * kC, sm, p_in, tid);          // overlaps the product
-        mbar_wait(bar_addr, phase & 1u);
-        ++phase;
+        mbar_wait(bar_a, phase_a & 1u);
+        ++phase_a;
         tc_fence_after();
+        MIXBT_TICK(1);
 
         // ---- LN1 + ReLU -> T3 -----------------------------------------------------------------------------------------------
         float mean1, rstd1;
@@ -388,26 +383,22 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MIXBT_TICK(2);
 
         // ---- o2 = S t (recompute) -------------------------------------------------------------------------------------------
         if (warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
-                issue_product(tmem + kD2, tmem + kD2 + 64, d_s3, d_t3_n, kSPiece, kTPiece, ksteps_p, idesc_kn,
+                issue_product(tmem + kD2, tmem + kD2 + 64, d_s3_k, d_t3_n, kSPiece, kTPiece, ksteps_p, idesc_kn,
                               [](int ks) { return (ks >> 1) * 8192 + (ks & 1) * 32; }, [](int ks) { return ks * 2048; });
-                umma_commit(bar_addr);
+                umma_commit(bar_a);
             }
             __syncwarp();
         }
-        float4 gyv[4];                                       // gy[o = row][col0 .. col0 + 15], in flight during the product
-        {
-            const float4* gp = reinterpret_cast<const float4*>(gy + (long long)item * (kPout * kC) + row * kC + col0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) gyv[c] = __ldg(gp + c);
-        }
-        mbar_wait(bar_addr, phase & 1u);
-        ++phase;
+        mbar_wait(bar_a, phase_a & 1u);
+        ++phase_a;
         tc_fence_after();
+        MIXBT_TICK(3);
 
         // ---- LN2, ReLU mask, LN2 backward -> G2 = g_o2 -------------------------------------------------------------------------
         {
@@ -444,34 +435,25 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MIXBT_TICK(4);
 
-        // ---- g_S = g_o2 t^T, and S^T -> ST3 while it runs; then g_t = S^T g_o2 ------------------------------------------------
+        // ---- g_S = g_o2 t^T, then g_t = S^T g_o2; g_S leaves tensor memory while g_t runs ---------------------------------------
         if (warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
                 issue_product(tmem + kD3, tmem + kD3x, d_g2_k, d_t3_k, kGPiece, kTPiece, 4, idesc_gs,
                               [](int ks) { return ks * 32; }, [](int ks) { return ks * 32; });
+                umma_commit(bar_b);
+                issue_product(tmem + kD4, tmem + kD4 + 64, d_s3_n, d_g2_n, kSPiece, kGPiece, 8, idesc_nn,
+                              [](int ks) { return ks * 1024; }, [](int ks) { return ks * 2048; });
+                umma_commit(bar_a);
             }
             __syncwarp();
         }
-        load_split_st(pg + kC * kC, sm, p_in, tid);          // S3 is dead: o2 has completed
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) {
-            if (elect_one()) {
-                tc_fence_after();
-                issue_product(tmem + kD4, tmem + kD4 + 64, d_st3, d_g2_n, kSPiece, kGPiece, 8, idesc_kn,
-                              [](int ks) { return (ks >> 2) * kXPiece + (ks & 3) * 32; }, [](int ks) { return ks * 2048; });
-                umma_commit(bar_addr);                       // covers g_S as well
-            }
-            __syncwarp();
-        }
-        mbar_wait(bar_addr, phase & 1u);
-        ++phase;
+        mbar_wait(bar_b, phase_b & 1u);
+        ++phase_b;
         tc_fence_after();
-
-        // ---- g_S -> global; g_t, ReLU mask, LN1 backward -> G1 = g_o1 (over T3); x^T -> XT3 (over ST3) -------------------------
+        MIXBT_TICK(5);
         {
             float* gs = gpg + kC * kC + (long long)row * p_in;
 #pragma unroll
@@ -485,6 +467,15 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
                         *reinterpret_cast<float4*>(gs + c0 + 4 * c) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
                 }
             }
+        }
+        MIXBT_TICK(6);
+        mbar_wait(bar_a, phase_a & 1u);
+        ++phase_a;
+        tc_fence_after();
+        MIXBT_TICK(7);
+
+        // ---- g_t, ReLU mask, LN1 backward -> G1 = g_o1 (over T3: g_S has completed) ---------------------------------------------
+        {
             float n1[16], gn[16];
             load_acc16(tm_lane + kD1 + col0, tm_lane + kD1 + 64 + col0, n1);
             load_acc16(tm_lane + kD4 + col0, tm_lane + kD4 + 64 + col0, gn);
@@ -505,27 +496,34 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
                 split_store_row16(gn, sm + kT3, kTPiece, row, col0);
             }
         }
-        load_split_xt(xg, sm, p_in, tid);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MIXBT_TICK(8);
 
-        // ---- g_M = x^T g_o1 ; g_x = g_o1 M^T ------------------------------------------------------------------------------------
+        // ---- g_M = x^T g_o1 ; g_x = g_o1 M^T ; the next item's S is split meanwhile (S3 is dead: g_t has completed) ---------------
         if (warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
-                issue_product(tmem + kD5, tmem + kD5 + 64, d_xt3, d_t3_n, kSPiece, kTPiece, ksteps_p, idesc_kn,
-                              [](int ks) { return (ks >> 1) * 4096 + (ks & 1) * 32; }, [](int ks) { return ks * 2048; });
+                issue_product(tmem + kD5, tmem + kD5 + 64, d_x3_n, d_t3_n, kXPiece, kTPiece, ksteps_p, idesc_nn,
+                              [](int ks) { return ks * 2048; }, [](int ks) { return ks * 2048; });
                 issue_product(tmem + kD6, tmem + kD6 + 64, d_t3_k, d_m3_n, kTPiece, kMPiece, 4, idesc_kn,
                               [](int ks) { return ks * 32; }, [](int ks) { return ks * 2048; });
-                umma_commit(bar_addr);
+                umma_commit(bar_a);
             }
             __syncwarp();
         }
-        if (nxt < num_items) load_split_x(x + (long long)nxt * p_in * kC, sm, p_in, tid);   // X3 is dead since o1 completed
-        mbar_wait(bar_addr, phase & 1u);
-        ++phase;
+        if (nxt < num_items) load_split_s(params + (long long)nxt * per_item + kC * kC, sm, p_in, tid);
+        MIXBT_TICK(9);
+        mbar_wait(bar_a, phase_a & 1u);
+        ++phase_a;
         tc_fence_after();
+        MIXBT_TICK(10);
+        if (nxt < num_items) {                               // X3 and M3 are dead: g_M and g_x have completed
+            load_split_x(x + (long long)nxt * p_in * kC, sm, p_in, tid);
+            load_split_m(params + (long long)nxt * per_item, sm, tid);
+            issue_o1();                                      // (block-uniform branch: the barrier inside is safe)
+        }
         {
             float f[16];
             if ((warp & 3) < 2) {                            // g_M rows c < 64
@@ -543,9 +541,16 @@ adaptive_mixing_bwd_tc_kernel(const float* __restrict__ x, const float* __restri
                     *reinterpret_cast<float4*>(gx + 4 * c) = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
             }
         }
-        if (nxt < num_items) load_split_m(params + (long long)nxt * per_item, sm, tid);     // M3 is dead since g_x completed
-        // the loop-top barrier orders this item's tensor-memory reads before the next item's products
+        MIXBT_TICK(11);
+        // every thread's tensor-memory reads of this item are complete (tcgen05.wait::ld) before it reaches the next block
+        // barrier, and the products that overwrite D2 .. D6 are issued behind one
     }
+#ifdef RACF_MIXBT_PROFILE
+    if (tid == 0 && blockIdx.x == 0)
+        printf("mixbt cycles (CTA 0): top-sync %lld | mma1 %lld | ln1 %lld | mma2 %lld | ln2+bwd %lld | mma3 wait %lld | gS out %lld | mma4 wait %lld | "
+               "ln1bwd %lld | S-split(next) %lld | mma56 wait %lld | gM,gx out + x,M-split %lld\n", prof[0], prof[1], prof[2], prof[3],
+               prof[4], prof[5], prof[6], prof[7], prof[8], prof[9], prof[10], prof[11]);
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
