@@ -143,13 +143,24 @@ class RowChainFunction(torch.autograd.Function):
             keep.append(p)
             return p.data_ptr()
 
+        version = [0] * chain.num_bufs      # bumped whenever an operator writes a buffer
+        saved_x = {}                         # (buffer, column, n, version) -> tensor: several Linears reading the same rows
+                                             # (the eleven sampling heads) share ONE saved input -- and one weight-gradient GEMM
+
         def save(idx, what, buf, col, n):
+            key = (buf, col, n, version[buf])
+            if what == "x" and key in saved_x:
+                tape[(idx, what)] = saved_x[key]
+                return
             t = torch.empty((rows, n), **f32)
             tape[(idx, what)] = t
+            if what == "x":
+                saved_x[key] = t
             ops.append(RowOp(kind=STORE, src=buf, src_col=col, n=n, ld=n, out=t.data_ptr()))
 
         for idx, e in enumerate(chain.ir):
             k = e["op"]
+            written = e.get("dst", e.get("buf"))
             if k == "load":
                 t2 = mat(tensors[e["t"]], e["n"])
                 ops.append(RowOp(kind=LOAD, dst=e["dst"], dst_col=e["dst_col"], n=e["n"], ld=t2.stride(0), p0=t2.data_ptr()))
@@ -185,6 +196,8 @@ class RowChainFunction(torch.autograd.Function):
                 o = torch.empty((rows, e["n"]), **f32)
                 outs[e["out"]] = o
                 ops.append(RowOp(kind=STORE, src=e["src"], src_col=e["src_col"], n=e["n"], ld=e["n"], out=o.data_ptr()))
+            if k != "store" and written is not None:
+                version[written] += 1
         _launch(ops, rows, chain.num_bufs, chain.width, dev)
         ctx.chain, ctx.tape, ctx.dev = chain, tape, dev
         ctx.save_for_backward(*[t for t in tensors if t is not None])
@@ -200,7 +213,7 @@ class RowChainFunction(torch.autograd.Function):
         rows, f32 = chain.rows, dict(dtype=torch.float32, device=dev)
         grads = [None] * len(tensors)
         needs = list(ctx.needs_input_grad[1:])                     # needs_input_grad[0] is the chain object
-        ops, keep, wgrads, loaded = [], [], [], []
+        ops, keep, loaded = [], [], []
 
         def acc(i, shape):
             """Zero-initialised fp32 accumulator for input i (atomics / several contributions)."""
@@ -221,6 +234,17 @@ class RowChainFunction(torch.autograd.Function):
                 flags[e["dst"]] = True
             elif k == "add":
                 flags[e["dst"]] |= flags[e["src"]]
+        # Linears that read the same saved input share one weight-gradient GEMM: their output gradients are stored side by
+        # side in one [rows, sum of padded N] matrix (grad_W of all of them = that matrix^T @ x, sliced by rows afterwards)
+        stacks, slot = {}, {}
+        for idx, e in enumerate(chain.ir):
+            if e["op"] == "linear" and needs[e["w"]]:
+                st = stacks.setdefault(id(tape[(idx, "x")]), {"members": [], "width": 0, "x": tape[(idx, "x")]})
+                slot[idx] = (st, st["width"])
+                st["members"].append((e, st["width"]))
+                st["width"] += _pad8(e["n"])
+        for st in stacks.values():
+            st["gy"] = torch.zeros((rows, st["width"]), **f32)                      # pad columns stay 0 for the GEMM
         for b in range(chain.num_bufs):
             ops.append(RowOp(kind=ZERO, dst=b, dst_col=0, n=chain.width))
         for idx in range(len(chain.ir) - 1, -1, -1):
@@ -252,13 +276,14 @@ class RowChainFunction(torch.autograd.Function):
                     y = tape[(idx, "y")]
                     ops.append(RowOp(kind=RELU_MASK, dst=e["dst"], dst_col=e["dst_col"], n=N, ld=N, p0=y.data_ptr()))
                 need_w = needs[e["w"]]
-                gy = torch.zeros((rows, _pad8(N)), **f32) if need_w else None       # pad columns stay 0 for the GEMM
-                gb = acc(e["b"], tensors[e["b"]].shape) if e["b"] is not None and needs[e["b"]] else None
-                if gy is not None or gb is not None:
-                    ops.append(RowOp(kind=STORE_COLSUM, src=e["dst"], src_col=e["dst_col"], n=N, ld=_pad8(N),
-                                     out=gy.data_ptr() if gy is not None else None, out2=gb.data_ptr() if gb is not None else None))
+                gy_ptr, gy_ld = None, _pad8(N)
                 if need_w:
-                    wgrads.append((e, gy, tape[(idx, "x")]))
+                    st, off = slot[idx]
+                    gy_ptr, gy_ld = st["gy"].data_ptr() + 4 * off, st["width"]
+                gb = acc(e["b"], tensors[e["b"]].shape) if e["b"] is not None and needs[e["b"]] else None
+                if gy_ptr is not None or gb is not None:
+                    ops.append(RowOp(kind=STORE_COLSUM, src=e["dst"], src_col=e["dst_col"], n=N, ld=gy_ld,
+                                     out=gy_ptr, out2=gb.data_ptr() if gb is not None else None))
                 if carries[idx][e["src"]]:
                     wt = _weight_bwd(e, tensors[e["w"]])
                     keep.append(wt)
@@ -292,14 +317,16 @@ class RowChainFunction(torch.autograd.Function):
         for i, g in loaded:
             grads[i] = g if grads[i] is None else grads[i] + g
         # weight gradients: grad_W [N, K] = gy^T [N, rows] x [rows, K], one tcgen05 GEMM per Linear (tiny shapes on cuBLAS)
-        for e, gy, x in wgrads:
-            N, K = e["n"], e["k"]
-            if rows % 8 == 0 and K % 8 == 0:
-                gw = tc_linear.linear_bf16x3(tc_linear.split_tiled_transposed(gy), tc_linear.split_tiled_transposed(x), None,
-                                             tc_linear.SIX_TERMS, variant=2)[:N]
+        for st in stacks.values():
+            gy, x = st["gy"], st["x"]
+            if rows % 8 == 0 and x.shape[1] % 8 == 0:
+                gw_all = tc_linear.linear_bf16x3(tc_linear.split_tiled_transposed(gy), tc_linear.split_tiled_transposed(x), None,
+                                                 tc_linear.SIX_TERMS, variant=2)
             else:
-                gw = gy[:, :N].t() @ x
-            grads[e["w"]] = gw if grads[e["w"]] is None else grads[e["w"]] + gw
+                gw_all = gy.t() @ x
+            for e, off in st["members"]:
+                gw = gw_all[off:off + e["n"]]
+                grads[e["w"]] = gw if grads[e["w"]] is None else grads[e["w"]] + gw
         for i, (t, g) in enumerate(zip(tensors, grads)):
             if g is not None and t is not None and g.shape != t.shape:
                 grads[i] = g.reshape(t.shape)

@@ -17,7 +17,8 @@ def test_row_program_argument_errors_are_codes():
     assert lib.racf_row_program_forward(None, 1, 8, 8, 1, 4, None) == -1
     assert lib.racf_row_program_forward(ops, 0, 8, 8, 1, 4, None) == -3
     assert lib.racf_row_program_forward(ops, 129, 8, 8, 1, 4, None) == -3         # more than RACF_ROW_MAX_OPS
-    assert lib.racf_row_program_forward(ops, 1, 8, 5, 1, 4, None) == -6          # rows per CTA: 4 or 8
+    assert lib.racf_row_program_forward(ops, 1, 8, 3, 1, 4, None) == -6          # rows per CTA: 4 .. 8
+    assert lib.racf_row_program_forward(ops, 1, 8, 9, 1, 4, None) == -6
     assert lib.racf_row_program_forward(ops, 1, 8, 8, 1, 6, None) == -6          # width % 4
     bad = (RowOp * 1)(RowOp(kind=LOAD, dst=1, n=4, ld=4, p0=16))
     assert lib.racf_row_program_forward(bad, 1, 8, 8, 1, 4, None) == -3          # buffer index out of range
