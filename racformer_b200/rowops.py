@@ -75,10 +75,13 @@ def choose_rows_per_cta(rows, num_bufs, width, device=None):
     fits = [r for r in range(4, 9) if r * per_row <= ROW_BUFFER_BYTES + 3 * CHUNK_COLS * 4 * 8]
     if not fits:
         return 4
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    sms = _sm_count.get(dev)
-    if sms is None:
-        sms = _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count if torch.cuda.is_available() else 148
+    if not torch.cuda.is_available():        # building a program on a machine without a GPU (tests of the host logic)
+        sms = 148
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        sms = _sm_count.get(dev)
+        if sms is None:
+            sms = _sm_count[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
     cost = lambda r: (-(-(-(-int(rows) // r)) // sms)) * r
     return min(fits, key=lambda r: (cost(r), -r))
 
