@@ -416,7 +416,11 @@ class DecoderWorkload:
     def step(self, time_kernels=False):
         if self.use_graph and not time_kernels:
             if self._graphed is None:
+                from racformer_b200 import _lib
                 from racformer_b200.graphs import GraphedDecoderForward
+                calls0 = _lib.CALLS[0]       # own launches per step, counted live: C-ABI calls of one eager forward (each
+                self._forward(self.inp)      # launches at least one kernel); the graph replays exactly these
+                self.launches_per_step = _lib.CALLS[0] - calls0
                 self.DOMINANT = self._pick_dominant()
                 self._graph_event_keys, self._graph_event_sink = {self.DOMINANT}, self.graph_events
                 with self._timed_tensor_core_kernels():

@@ -384,6 +384,15 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
                                      int max_order, int tiled, racf_stream_t stream);
 
 /*
+ * Radar temporal encoder (models/racformer_transformer.py:640-662, ConvGRUCell.forward after the gates convolution), channel-
+ * last tensors: gates [pixels, 3 * hidden] = (z | r | cand) pre-activations, h_prev [pixels, hidden] ->
+ * h = (1 - sigmoid(z)) * h_prev + sigmoid(z) * tanh(cand + sigmoid(r) * h_prev), in PyTorch's fp32 operation order.
+ * hidden % 4 == 0, 16-byte aligned pointers (else RACF_ERR_UNSUPPORTED). Inference only.
+ */
+int racf_convgru_gates_forward(const float* gates, const float* h_prev, long long pixels, int hidden_channels,
+                               float* h, racf_stream_t stream);
+
+/*
  * in [batch][channels][positions] -> out[batch][positions][ld] (the first `channels` floats of every ld-long pixel row)
  * and, when out2 != NULL, the same values into out2 with row length ld2: NCHW -> NHWC in front of the radar temporal
  * encoder's convolutions (models/racformer_transformer.py:645-656), a tiled transpose.

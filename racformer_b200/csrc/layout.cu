@@ -8,6 +8,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <stdint.h>
+
 #include "racf_common.cuh"
 #include "racformer_ops.h"
 
@@ -122,7 +124,46 @@ __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float* __restrict
     }
 }
 
+// ConvGRU cell gates of the radar temporal encoder (models/racformer_transformer.py:640-662) on channel-last tensors:
+//   gates [P pixels][3 Hc] = (z | r | cand) pre-activations (the gates convolution's output), h_prev [P][Hc] ->
+//   h = (1 - sigmoid(z)) h_prev + sigmoid(z) tanh(cand + sigmoid(r) h_prev)                          [P][Hc]
+// One launch instead of nine PyTorch elementwise kernels per recurrence step; separate multiplies / adds where PyTorch
+// runs separate kernels (no FMA contraction), the same libm calls.
+__global__ void __launch_bounds__(256) convgru_gates_kernel(const float* __restrict__ gates, const float* __restrict__ h_prev,
+                                                            float* __restrict__ h, long long quads, int hc4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const long long pix = i / hc4;
+    const int c4 = (int)(i - pix * hc4);
+    const float4* g = reinterpret_cast<const float4*>(gates) + pix * 3 * hc4 + c4;
+    const float4 zv = __ldg(g), rv = __ldg(g + hc4), cv = __ldg(g + 2 * hc4);
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(h_prev) + i);
+    auto cell = [](float zl, float rl, float cl, float hp) {
+        const float z = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-zl)));
+        const float r = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-rl)));
+        const float cand = tanhf(__fadd_rn(cl, __fmul_rn(r, hp)));
+        return __fadd_rn(__fmul_rn(__fsub_rn(1.f, z), hp), __fmul_rn(z, cand));
+    };
+    reinterpret_cast<float4*>(h)[i] = make_float4(cell(zv.x, rv.x, cv.x, hv.x), cell(zv.y, rv.y, cv.y, hv.y),
+                                                  cell(zv.z, rv.z, cv.z, hv.z), cell(zv.w, rv.w, cv.w, hv.w));
+}
+
 }  // namespace racf
+
+extern "C" int racf_convgru_gates_forward(const float* gates, const float* h_prev, long long pixels, int hidden_channels,
+                                          float* h, racf_stream_t stream) {
+    if (!gates || !h_prev || !h) return RACF_ERR_NULL_POINTER;
+    if (pixels <= 0 || hidden_channels <= 0) return RACF_ERR_BAD_SHAPE;
+    if ((hidden_channels & 3) != 0 || ((reinterpret_cast<uintptr_t>(gates) | reinterpret_cast<uintptr_t>(h_prev) |
+                                        reinterpret_cast<uintptr_t>(h)) & 15u))
+        return RACF_ERR_UNSUPPORTED;
+    const long long quads = pixels * (hidden_channels / 4);
+    const long long blocks = (quads + 255) / 256;
+    if (blocks >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
+    racf::convgru_gates_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(gates, h_prev, h, quads,
+                                                                                               hidden_channels / 4);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int racf_chw_to_hwc(const float* in, int batch, int channels, int positions, float* out, int ld, float* out2,
                                int ld2, racf_stream_t stream) {

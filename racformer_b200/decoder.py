@@ -492,8 +492,15 @@ class ConvGRUCell(nn.Module):
                                     padding=kernel_size // 2)
         self.matching_layer = nn.Conv2d(hidden_channels, input_channels, 1)
 
+    fused_gates = True      # inference on CUDA, channel-last tensors: the nine elementwise ops below as one launch
+
     def forward(self, x, h_prev):
         gates = self.gates_conv(torch.cat([x, self.matching_layer(h_prev)], dim=1))
+        if self.fused_gates and not torch.is_grad_enabled() and gates.is_cuda and gates.dim() == 4:
+            from . import points
+            h = points.convgru_gates(gates, h_prev)
+            if h is not None:
+                return h
         z, r, cand = torch.split(gates, self.hidden_channels, dim=1)
         z, r = torch.sigmoid(z), torch.sigmoid(r)
         cand = torch.tanh(cand + r * h_prev)
@@ -511,7 +518,12 @@ class ConvGRU(nn.Module):
 
     def forward(self, x):
         B, T, _, H, W = x.shape
+        # channel-last frames (the inference path of RadarBEVTemporalEncoder) keep the whole recurrence channel-last: no cuDNN
+        # NCHW <-> NHWC conversions around the two convolutions of every step
+        cl = x.is_cuda and x[:, 0].dim() == 4 and x[:, 0].is_contiguous(memory_format=torch.channels_last)
         h = torch.zeros(B, self.hidden_channels, H, W, device=x.device, dtype=x.dtype)
+        if cl:
+            h = h.contiguous(memory_format=torch.channels_last)
         zeros = h.clone()
         steps = 4 if T > 4 else T
         out = []

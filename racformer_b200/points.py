@@ -172,6 +172,26 @@ def to_channels_last(x, concat_channels=0):
     return dense, both
 
 
+def convgru_gates(gates, h_prev):
+    """ConvGRU cell after the gates convolution (racformer_transformer.py:640-662) in one launch. gates [N, 3*Hc, H, W] and
+    h_prev [N, Hc, H, W], both fp32 CUDA tensors in channels_last memory format -> h (channels_last). None when the
+    tensors are not dense channel-last (the caller runs the PyTorch ops)."""
+    N, C3, H, W = gates.shape
+    hc = C3 // 3
+    if not (gates.is_cuda and gates.dtype == torch.float32 and h_prev.dtype == torch.float32 and hc % 4 == 0
+            and tuple(h_prev.shape) == (N, hc, H, W) and gates.permute(0, 2, 3, 1).is_contiguous()
+            and h_prev.permute(0, 2, 3, 1).is_contiguous()):
+        return None
+    h = torch.empty_like(h_prev, memory_format=torch.channels_last)
+    with torch.cuda.device(gates.device):
+        rc = _lib.load().racf_convgru_gates_forward(gates.data_ptr(), h_prev.data_ptr(), N * H * W, hc, h.data_ptr(),
+                                                    _stream(gates.device))
+    if rc == -6:
+        return None
+    _lib.check(rc, "racf_convgru_gates_forward")
+    return h
+
+
 def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_groups=0, tensor_cores=True, variant=0):
     """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
     (csrc/mixing.cu). With split=True the result comes back as its three bf16 pieces [3, QG, out_points, C] (their sum is

@@ -290,3 +290,30 @@ def test_decoder_layer_paired_bev_launch_equals_separate_launches():
         layer.bev_pair_launch = True
     for a, b in zip(paired, separate):
         assert torch.equal(a, b)
+
+
+def test_convgru_gates_kernel_matches_pytorch_ops():
+    """racf_convgru_gates_forward (one launch) against ConvGRUCell's nine elementwise ops (racformer_transformer.py:655-662) on
+    channel-last tensors: same libm calls, separate multiplies / adds -> agreement to the last bit or two."""
+    from racformer_b200 import points
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, hc, H, W = 2, 64, 17, 23
+    gates = (torch.randn(N, 3 * hc, H, W, device="cuda", generator=g) * 2).contiguous(memory_format=torch.channels_last)
+    h_prev = torch.randn(N, hc, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    got = points.convgru_gates(gates, h_prev)
+    z, r, cand = torch.split(gates, hc, dim=1)
+    z, r = torch.sigmoid(z), torch.sigmoid(r)
+    want = (1 - z) * h_prev + z * torch.tanh(cand + r * h_prev)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert float((got - want).abs().max()) <= 2e-7
+    assert points.convgru_gates(gates.contiguous(), h_prev) is None          # NCHW tensors: the caller keeps the PyTorch ops
+    # the encoder with and without the fused gates / channel-last recurrence
+    from racformer_b200.decoder import RadarBEVTemporalEncoder
+    torch.manual_seed(0)
+    enc = RadarBEVTemporalEncoder(64, 16, num_frames=4).cuda().eval()
+    bev = torch.randn(1, 4, 64, 16, 16, device="cuda", generator=g)
+    with torch.no_grad():
+        a = enc(bev)
+        enc.convGRU.convGRUCell.fused_gates = False
+        b = enc(bev)
+    assert float((a - b).abs().max()) <= 1e-5
