@@ -391,6 +391,11 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
  */
 int racf_convgru_gates_forward(const float* gates, const float* h_prev, long long pixels, int hidden_channels,
                                float* h, racf_stream_t stream);
+/* nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) of a channel-last tensor (the same encoder,
+ * models/racformer_transformer.py:618-621): in [batch, height, width, channels] -> out [batch, 2 height, 2 width, channels].
+ * channels % 4 == 0, 16-byte aligned pointers (else RACF_ERR_UNSUPPORTED). Inference only. */
+int racf_upsample2x_bilinear_nhwc(const float* in, int batch, int height, int width, int channels, float* out,
+                                  racf_stream_t stream);
 
 /*
  * in [batch][channels][positions] -> out[batch][positions][ld] (the first `channels` floats of every ld-long pixel row)

@@ -85,6 +85,7 @@ SIGNATURES = {
     "racf_bev_points_backward": (_i, [_c_float_p] * 5 + [ctypes.POINTER(ctypes.c_double), ctypes.c_float] + [_i] * 6
                                  + [_c_float_p] * 7 + [ctypes.c_void_p]),
     "racf_convgru_gates_forward": (_i, [_c_float_p, _c_float_p, ctypes.c_longlong, _i, _c_float_p, ctypes.c_void_p]),
+    "racf_upsample2x_bilinear_nhwc": (_i, [_c_float_p, _i, _i, _i, _i, _c_float_p, ctypes.c_void_p]),
     "racf_row_program_forward": (_i, [ctypes.c_void_p, _i, _i, _i, _i, _i, ctypes.c_void_p]),
     "racf_msda_tap_masks": (_i, [ctypes.c_void_p, _c_float_p, _i, _i, _i, _i, _i, ctypes.c_void_p, ctypes.c_void_p]),
 }

@@ -148,7 +148,46 @@ __global__ void __launch_bounds__(256) convgru_gates_kernel(const float* __restr
                                                   cell(zv.z, rv.z, cv.z, hv.z), cell(zv.w, rv.w, cv.w, hv.w));
 }
 
+// nn.Upsample(scale_factor = 2, mode = "bilinear", align_corners = True) on a channel-last tensor (the radar temporal encoder's
+// hidden state, models/racformer_transformer.py:618-621): in [N, H, W, C] -> out [N, 2H, 2W, C]. A thread owns 4 channels of one
+// output pixel; source coordinate = dst * (in - 1) / (out - 1), the same interpolation weights as ATen's kernel.
+__global__ void __launch_bounds__(256) upsample2x_bilinear_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                                       int W, int c4, long long quads) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const int HO = 2 * H, WO = 2 * W;
+    long long r = i;
+    const int c = (int)(r % c4); r /= c4;
+    const int x2 = (int)(r % WO); r /= WO;
+    const int y2 = (int)(r % HO);
+    const long long n = r / HO;
+    const float rh = HO > 1 ? (float)(H - 1) / (float)(HO - 1) : 0.f, rw = WO > 1 ? (float)(W - 1) / (float)(WO - 1) : 0.f;
+    const float h1r = rh * (float)y2, w1r = rw * (float)x2;
+    const int h1 = (int)h1r, w1 = (int)w1r;
+    const int hp = h1 < H - 1 ? 1 : 0, wp = w1 < W - 1 ? 1 : 0;
+    const float hl1 = h1r - (float)h1, hl0 = 1.f - hl1, wl1 = w1r - (float)w1, wl0 = 1.f - wl1;
+    const float4* src = reinterpret_cast<const float4*>(in) + ((n * H + h1) * W + w1) * c4 + c;
+    const float4 v00 = __ldg(src), v01 = __ldg(src + (long long)wp * c4), v10 = __ldg(src + (long long)hp * W * c4),
+                 v11 = __ldg(src + ((long long)hp * W + wp) * c4);
+    auto mix = [&](float a, float b, float cc, float d) { return hl0 * (wl0 * a + wl1 * b) + hl1 * (wl0 * cc + wl1 * d); };
+    reinterpret_cast<float4*>(out)[i] = make_float4(mix(v00.x, v01.x, v10.x, v11.x), mix(v00.y, v01.y, v10.y, v11.y),
+                                                    mix(v00.z, v01.z, v10.z, v11.z), mix(v00.w, v01.w, v10.w, v11.w));
+}
+
 }  // namespace racf
+
+extern "C" int racf_upsample2x_bilinear_nhwc(const float* in, int batch, int height, int width, int channels, float* out,
+                                             racf_stream_t stream) {
+    if (!in || !out) return RACF_ERR_NULL_POINTER;
+    if (batch <= 0 || height <= 0 || width <= 0 || channels <= 0) return RACF_ERR_BAD_SHAPE;
+    if ((channels & 3) != 0 || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u)) return RACF_ERR_UNSUPPORTED;
+    const long long quads = (long long)batch * 4 * height * width * (channels / 4);
+    const long long blocks = (quads + 255) / 256;
+    if (blocks >= (1LL << 31)) return RACF_ERR_BAD_SHAPE;
+    racf::upsample2x_bilinear_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, height, width,
+                                                                                                          channels / 4, quads);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int racf_convgru_gates_forward(const float* gates, const float* h_prev, long long pixels, int hidden_channels,
                                           float* h, racf_stream_t stream) {

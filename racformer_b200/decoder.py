@@ -411,7 +411,7 @@ class BEVSelfAttention(nn.Module):
 
     tensor_core_value_proj = True     # inference on CUDA: csrc/linear.cu (see AdaptiveMixing.gemm_precision)
 
-    def project_value(self, bev, pos=None):
+    def project_value(self, bev, pos=None, channel_bias=None):
         """([B,T,C,H,W] + pos [C,H,W]) -> value [B*T, H*W, heads, C/heads] (bev_self_attention.py:162-174).
         Query-independent. Inference on CUDA: the add, the permute + copy and the operand split are one kernel and the
         projection (with its bias) runs on the tcgen05 Linear kernel; otherwise the PyTorch ops of the reference."""
@@ -423,14 +423,22 @@ class BEVSelfAttention(nn.Module):
                 self._split_value_proj = linear.SplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
             pixels = bev.permute(0, 1, 3, 4, 2)
             if pixels.is_contiguous():      # channel-last maps (the radar temporal encoder's output): already [B*T*S, C]
-                # [C, S] -> [S, C]: a view of LearnedPositionalEncoding's own [H, W, C] layout (no copy)
-                addend = None if pos is None else pos.reshape(C, -1).t().contiguous()
-                x3 = linear.split_tiled(pixels.reshape(-1, C), addend)
+                # [C, S] -> [S, C]: a view of LearnedPositionalEncoding's own [H, W, C] layout (no copy); a deferred
+                # per-channel bias (the temporal encoder's last convolution) joins the same row-periodic addend
+                addend = None if pos is None else pos.reshape(C, -1).t()
+                if channel_bias is not None:
+                    addend = (channel_bias.expand(pixels[0, 0].numel() // C, C) if addend is None else addend + channel_bias)
+                x3 = linear.split_tiled(pixels.reshape(-1, C), None if addend is None else addend.contiguous())
             else:
+                cpos = None if pos is None else pos.reshape(C, -1)
+                if channel_bias is not None:
+                    cpos = channel_bias[:, None].expand(C, bev[0, 0, 0].numel()) if cpos is None else cpos + channel_bias[:, None]
                 x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(),
-                                                    None if pos is None else pos.reshape(C, -1).contiguous(), tiled=True)
+                                                    None if cpos is None else cpos.contiguous(), tiled=True)
             v = self._split_value_proj(x3=x3)
             return v.reshape(B * T, x3.rows // (B * T), self.num_heads, -1)
+        if channel_bias is not None:
+            bev = bev + channel_bias.view(1, 1, C, 1, 1)
         if pos is not None:
             bev = bev + pos.view(1, 1, C, *bev.shape[3:])
         pixels = bev.reshape(B * T, C, -1).permute(0, 2, 1)
@@ -553,7 +561,14 @@ class RadarBEVTemporalEncoder(nn.Module):
 
     channels_last = True    # inference on CUDA: run the convolutions on channel-last tensors (no cuDNN layout round trips)
 
-    def inner_forward(self, bev):
+    def can_defer_bias(self, bev):
+        """The channel-last inference path can hand temporal_fusion's bias to the consumer instead of adding it itself."""
+        return self.channels_last and not torch.is_grad_enabled() and bev.is_cuda and bev.dtype == torch.float32
+
+    def inner_forward(self, bev, defer_bias=False):
+        """defer_bias (only with can_defer_bias): returns (output WITHOUT temporal_fusion's bias, that bias) -- cuDNN adds a
+        convolution's bias in a separate pass over the 134 MB output; the caller (BEVSampling.prepare_value) adds it where it
+        adds the positional encoding, inside value_proj's operand split."""
         B, T, C, H, W = bev.shape
         r = self.downsample_ratio
         if self.channels_last and not torch.is_grad_enabled() and bev.is_cuda:
@@ -569,8 +584,16 @@ class RadarBEVTemporalEncoder(nn.Module):
                                    memory_format=torch.channels_last)
                 both[:, :C].copy_(x)
             down = self.downsample(x).unflatten(0, (B, T))
-            hid = self.upsample(self.convGRU(down).flatten(0, 1).contiguous(memory_format=torch.channels_last))
+            state = self.convGRU(down).flatten(0, 1).contiguous(memory_format=torch.channels_last)
+            up = None
+            if bev.dtype == torch.float32:
+                from . import points   # 2x bilinear upsampling of the channel-last state in one launch (ATen's NHWC kernel: 70 us)
+                up = points.upsample2x_bilinear(state)
+            hid = self.upsample[1](up) if up is not None else self.upsample(state)
             both[:, C:].copy_(hid)
+            if defer_bias:
+                tf = self.temporal_fusion
+                return F.conv2d(both, tf.weight, None, tf.stride, tf.padding).unflatten(0, (B, T)), tf.bias
             return self.temporal_fusion(both).unflatten(0, (B, T))
         down = self.downsample(bev.flatten(0, 1)).reshape(B, T, self.hidden_dims, H // r, W // r)
         hid = self.upsample(self.convGRU(down).flatten(0, 1)).reshape(B, T, self.hidden_dims, H, W)
@@ -608,12 +631,17 @@ class BEVSampling(nn.Module):
 
     def prepare_value(self, bev_feats):
         """Everything that does not depend on the queries: temporal encoder (radar), + positional encoding, value_proj."""
+        bias = None
         if self.temp_radar:
-            bev_feats = self.temporal_encoder(bev_feats)
+            enc = self.temporal_encoder
+            if bev_feats.shape[0] == 1 and enc.can_defer_bias(bev_feats):
+                bev_feats, bias = enc.inner_forward(bev_feats, defer_bias=True)
+            else:
+                bev_feats = enc(bev_feats)
         B, T, C, H, W = bev_feats.shape
         pos = self.positional_encoding(B, H, W, bev_feats.device).to(bev_feats.dtype)
         if B == 1:
-            return self.attention.project_value(bev_feats, pos.reshape(C, H, W)), (H, W)
+            return self.attention.project_value(bev_feats, pos.reshape(C, H, W), channel_bias=bias), (H, W)
         return self.attention.project_value(bev_feats + pos.view(B, 1, C, H, W)), (H, W)
 
     def fused_point_tensors(self, query_ray, query_feat, meta, d_region, heads=None):

@@ -192,6 +192,21 @@ def convgru_gates(gates, h_prev):
     return h
 
 
+def upsample2x_bilinear(x):
+    """nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) of a channels_last fp32 CUDA tensor [N, C, H, W] ->
+    [N, C, 2H, 2W] (channels_last) in one launch; None when the tensor is not dense channel-last."""
+    N, C, H, W = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and C % 4 == 0 and x.permute(0, 2, 3, 1).is_contiguous()):
+        return None
+    out = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().racf_upsample2x_bilinear_nhwc(x.data_ptr(), N, H, W, C, out.data_ptr(), _stream(x.device))
+    if rc == -6:
+        return None
+    _lib.check(rc, "racf_upsample2x_bilinear_nhwc")
+    return out
+
+
 def adaptive_mixing_core(x, params, out_points, eps=1e-5, split=False, tiled_groups=0, tensor_cores=True, variant=0):
     """x [QG, P_in, C], params [QG, C*C + out_points*P_in] -> relu(LN(S @ relu(LN(x @ M)))) [QG, out_points, C], one kernel
     (csrc/mixing.cu). With split=True the result comes back as its three bf16 pieces [3, QG, out_points, C] (their sum is

@@ -317,3 +317,35 @@ def test_convgru_gates_kernel_matches_pytorch_ops():
         enc.convGRU.convGRUCell.fused_gates = False
         b = enc(bev)
     assert float((a - b).abs().max()) <= 1e-5
+
+
+def test_upsample2x_bilinear_kernel_matches_aten():
+    from racformer_b200 import points
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for N, C, H, W in ((2, 64, 13, 9), (8, 64, 64, 64), (1, 8, 1, 5)):
+        x = torch.randn(N, C, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+        got = points.upsample2x_bilinear(x)
+        want = torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert float((got - want).abs().max()) <= 1e-6
+    assert points.upsample2x_bilinear(torch.randn(2, 8, 4, 4, device="cuda")) is None      # NCHW: PyTorch ops
+
+
+def test_deferred_temporal_fusion_bias_reaches_value_proj():
+    """BEVSampling.prepare_value at batch 1 skips cuDNN's separate bias pass of the temporal encoder's last convolution and adds
+    the bias inside value_proj's operand split, next to the positional encoding: same value map as the plain order."""
+    from racformer_b200.decoder import BEVSampling
+    torch.manual_seed(0)
+    m = BEVSampling(embed_dims=64, num_frames=4, num_points=2, num_heads=4, num_levels=1, pc_range=PC_RANGE,
+                    spatial_shapes=(16, 16), depth_num=3, temp_radar=True).cuda().eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.normal_(0, 0.2)
+        bev = torch.randn(1, 4, 64, 16, 16, device="cuda")
+        value, hw = m.prepare_value(bev)
+        feats = m.temporal_encoder(bev)                                    # bias added by the convolution
+        pos = m.positional_encoding(1, 16, 16, bev.device)
+        want = m.attention.project_value(feats, pos.reshape(64, 16, 16))
+    assert tuple(hw) == (16, 16) and value.shape == want.shape
+    assert float((value - want).abs().max()) <= 2e-5 * float(want.abs().max())
+    assert float(m.temporal_encoder.temporal_fusion.bias.detach().abs().max()) > 0.05      # the test has power
