@@ -411,7 +411,7 @@ class BEVSelfAttention(nn.Module):
 
     tensor_core_value_proj = True     # inference on CUDA: csrc/linear.cu (see AdaptiveMixing.gemm_precision)
 
-    def project_value(self, bev, pos=None, channel_bias=None):
+    def project_value(self, bev, pos=None, channel_bias=None, addend=None):
         """([B,T,C,H,W] + pos [C,H,W]) -> value [B*T, H*W, heads, C/heads] (bev_self_attention.py:162-174).
         Query-independent. Inference on CUDA: the add, the permute + copy and the operand split are one kernel and the
         projection (with its bias) runs on the tcgen05 Linear kernel; otherwise the PyTorch ops of the reference."""
@@ -422,7 +422,12 @@ class BEVSelfAttention(nn.Module):
             if getattr(self, "_split_value_proj", None) is None:
                 self._split_value_proj = linear.SplitLinear(self.value_proj, max_order=linear.SIX_TERMS)
             pixels = bev.permute(0, 1, 3, 4, 2)
-            if pixels.is_contiguous():      # channel-last maps (the radar temporal encoder's output): already [B*T*S, C]
+            if addend is not None:          # prepared by the caller: [S, C] for channel-last maps, [C, S] otherwise
+                if pixels.is_contiguous():
+                    x3 = linear.split_tiled(pixels.reshape(-1, C), addend)
+                else:
+                    x3 = linear.split_bf16x3_chw_to_hwc(bev.reshape(B * T, C, -1).contiguous(), addend, tiled=True)
+            elif pixels.is_contiguous():      # channel-last maps (the radar temporal encoder's output): already [B*T*S, C]
                 # [C, S] -> [S, C]: a view of LearnedPositionalEncoding's own [H, W, C] layout (no copy); a deferred
                 # per-channel bias (the temporal encoder's last convolution) joins the same row-periodic addend
                 addend = None if pos is None else pos.reshape(C, -1).t()
@@ -589,8 +594,11 @@ class RadarBEVTemporalEncoder(nn.Module):
             if bev.dtype == torch.float32:
                 from . import points   # 2x bilinear upsampling of the channel-last state in one launch (ATen's NHWC kernel: 70 us)
                 up = points.upsample2x_bilinear(state)
-            hid = self.upsample[1](up) if up is not None else self.upsample(state)
-            both[:, C:].copy_(hid)
+            if up is not None:      # bias add and the copy into the concatenation buffer as one pass
+                uc = self.upsample[1]
+                torch.add(F.conv2d(up, uc.weight, None, uc.stride, uc.padding), uc.bias.view(1, -1, 1, 1), out=both[:, C:])
+            else:
+                both[:, C:].copy_(self.upsample(state))
             if defer_bias:
                 tf = self.temporal_fusion
                 return F.conv2d(both, tf.weight, None, tf.stride, tf.padding).unflatten(0, (B, T)), tf.bias
@@ -639,6 +647,22 @@ class BEVSampling(nn.Module):
             else:
                 bev_feats = enc(bev_feats)
         B, T, C, H, W = bev_feats.shape
+        if (B == 1 and not torch.is_grad_enabled() and bev_feats.is_cuda and bev_feats.dtype == torch.float32
+                and self.attention.tensor_core_value_proj and C % 8 == 0):
+            # the addend of value_proj's operand split (positional encoding [+ deferred bias]) depends on weights only: built once
+            # per weight version in the layout the split reads ([S, C] rows for channel-last maps, [C, S] otherwise)
+            rows = bev_feats.permute(0, 1, 3, 4, 2).is_contiguous()
+            pe = self.positional_encoding
+            key = (pe.row_embed.weight.data_ptr(), pe.row_embed.weight._version, pe.col_embed.weight.data_ptr(),
+                   pe.col_embed.weight._version, None if bias is None else (bias.data_ptr(), bias._version), H, W, rows,
+                   str(bev_feats.device), _cache_epoch())
+            hit = getattr(self, "_addend", None)
+            if hit is None or hit[0] != key:
+                pos = pe(1, H, W, bev_feats.device).to(bev_feats.dtype).reshape(C, H * W)
+                if bias is not None:
+                    pos = pos + bias.detach()[:, None]
+                hit = self._addend = (key, (pos.t() if rows else pos).contiguous())
+            return self.attention.project_value(bev_feats, addend=hit[1]), (H, W)
         pos = self.positional_encoding(B, H, W, bev_feats.device).to(bev_feats.dtype)
         if B == 1:
             return self.attention.project_value(bev_feats, pos.reshape(C, H, W), channel_bias=bias), (H, W)
