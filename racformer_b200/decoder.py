@@ -838,6 +838,9 @@ class AdaptiveMixing(nn.Module):
         profiles/r01_decoder_forward_kernel_breakdown_fused.json). Same sum, rounded inside the accumulator."""
         lin = self.parameter_generator
         if self._tensor_core_linear(query):
+            x3 = getattr(self, "_query_x3", None)      # the caller has already split these query features (stacked heads)
+            if x3 is not None and x3.rows == query.numel() // query.shape[-1]:
+                return self._split_linear("parameter_generator")(x3=x3, lead=tuple(query.shape[:-1]))
             return self._split_linear("parameter_generator")(query)
         trainable = self._train_linear("parameter_generator", query)
         if trainable is not None:
@@ -894,8 +897,13 @@ class AdaptiveMixing(nn.Module):
             return self._split_out(out)
         return self.out_proj(out)
 
-    def forward(self, x, query):
-        return _maybe_checkpoint(self, self.inner_forward, x, query)
+    def forward(self, x, query, query_x3=None):
+        """query_x3: linear.TiledOperand of `query` when the caller has one (inference; the split is then not repeated)."""
+        self._query_x3 = query_x3
+        try:
+            return _maybe_checkpoint(self, self.inner_forward, x, query)
+        finally:
+            self._query_x3 = None
 
 
 class RaCFormerTransformerDecoderLayer(nn.Module):
@@ -964,7 +972,10 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
                  lss.sampling_offset, lss.ray_points_offset, lss.scale_weights, lss.attention.bev_queue_weight,
                  img.sampling_offset, img.ray_points_offset, img.scale_weights])
         B, Q, _ = query_feat.shape
-        outs = [o.view(B, Q, -1) for o in self._heads(query_feat)]
+        from . import linear
+        x3 = linear.split_tiled(query_feat.reshape(-1, query_feat.shape[-1]).contiguous())
+        self._heads_x3 = x3         # parameter_generator of the mixing block reads the same rows: _forward hands the split on
+        outs = [o.view(B, Q, -1) for o in self._heads(x3=x3)]
         return outs[0:4], outs[4:8], outs[8:11]
 
     def _sampling_heads_train(self, query_feat):
@@ -1229,6 +1240,7 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
                 query_feat = query_feat + self.position_encoder(query_bbox[..., :3])
             query_feat = self.norm1(self.self_attn(query_bbox, query_feat, attn_mask))
         prep_radar, prep_lss = prepared if prepared is not None else (None, None)
+        self._heads_x3 = None
         heads = (self._sampling_heads_train(query_feat) if train_rows else self._sampling_heads(query_feat)) or (None, None, None)
         pair = self._bev_pair(ops, query_bbox, query_feat, prep_radar, prep_lss, meta, d_region, heads) if rows else None
         if pair is not None:
@@ -1239,7 +1251,8 @@ class RaCFormerTransformerDecoderLayer(nn.Module):
             lss = self.sampling_lss_bev(ops, query_bbox, query_feat, lss_bev_feats, meta, d_region=d_region,
                                         prepared=prep_lss, heads=heads[1], raw=rows or train_rows)
         sampled = self.sampling(ops, query_bbox, query_feat, mlvl_feats, meta, d_region=d_region, heads=heads[2])
-        mixed = self.mixing(sampled, query_feat)
+        mixed = self.mixing(sampled, query_feat, query_x3=self._heads_x3)
+        self._heads_x3 = None
         if rows or train_rows:
             query_feat, cls_score, delta = self._tail_rows(mixed, query_feat, radar, lss, train=train_rows)
         else:
