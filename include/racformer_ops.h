@@ -384,7 +384,7 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
                                      int max_order, int tiled, racf_stream_t stream);
 
 /*
- * Radar temporal encoder (models/racformer_transformer.py:640-662, ConvGRUCell.forward after the gates convolution), channel-
+ * Radar temporal encoder (models/racformer_transformer.py:709-720, ConvGRUCell.forward after the gates convolution), channel-
  * last tensors: gates [pixels, 3 * hidden] = (z | r | cand) pre-activations, h_prev [pixels, hidden] ->
  * h = (1 - sigmoid(z)) * h_prev + sigmoid(z) * tanh(cand + sigmoid(r) * h_prev), in PyTorch's fp32 operation order.
  * hidden % 4 == 0, 16-byte aligned pointers (else RACF_ERR_UNSUPPORTED). Inference only.
@@ -392,7 +392,7 @@ int racf_linear_bf16x3_multi_forward(const void* a3, const void* w3, int M, int 
 int racf_convgru_gates_forward(const float* gates, const float* h_prev, long long pixels, int hidden_channels,
                                float* h, racf_stream_t stream);
 /* nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True) of a channel-last tensor (the same encoder,
- * models/racformer_transformer.py:618-621): in [batch, height, width, channels] -> out [batch, 2 height, 2 width, channels].
+ * models/racformer_transformer.py:637-640): in [batch, height, width, channels] -> out [batch, 2 height, 2 width, channels].
  * channels % 4 == 0, 16-byte aligned pointers (else RACF_ERR_UNSUPPORTED). Inference only. */
 int racf_upsample2x_bilinear_nhwc(const float* in, int batch, int height, int width, int channels, float* out,
                                   racf_stream_t stream);

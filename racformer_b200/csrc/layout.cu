@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float* __restrict
     }
 }
 
-// ConvGRU cell gates of the radar temporal encoder (models/racformer_transformer.py:640-662) on channel-last tensors:
+// ConvGRU cell gates of the radar temporal encoder (models/racformer_transformer.py:709-720) on channel-last tensors:
 //   gates [P pixels][3 Hc] = (z | r | cand) pre-activations (the gates convolution's output), h_prev [P][Hc] ->
 //   h = (1 - sigmoid(z)) h_prev + sigmoid(z) tanh(cand + sigmoid(r) h_prev)                          [P][Hc]
 // One launch instead of nine PyTorch elementwise kernels per recurrence step; separate multiplies / adds where PyTorch
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) convgru_gates_kernel(const float* __restr
 }
 
 // nn.Upsample(scale_factor = 2, mode = "bilinear", align_corners = True) on a channel-last tensor (the radar temporal encoder's
-// hidden state, models/racformer_transformer.py:618-621): in [N, H, W, C] -> out [N, 2H, 2W, C]. A thread owns 4 channels of one
+// hidden state, models/racformer_transformer.py:637-640): in [N, H, W, C] -> out [N, 2H, 2W, C]. A thread owns 4 channels of one
 // output pixel; source coordinate = dst * (in - 1) / (out - 1), the same interpolation weights as ATen's kernel.
 __global__ void __launch_bounds__(256) upsample2x_bilinear_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
                                                                        int W, int c4, long long quads) {

@@ -173,7 +173,7 @@ def to_channels_last(x, concat_channels=0):
 
 
 def convgru_gates(gates, h_prev):
-    """ConvGRU cell after the gates convolution (racformer_transformer.py:640-662) in one launch. gates [N, 3*Hc, H, W] and
+    """ConvGRU cell after the gates convolution (racformer_transformer.py:709-720) in one launch. gates [N, 3*Hc, H, W] and
     h_prev [N, Hc, H, W], both fp32 CUDA tensors in channels_last memory format -> h (channels_last). None when the
     tensors are not dense channel-last (the caller runs the PyTorch ops)."""
     N, C3, H, W = gates.shape

@@ -293,7 +293,7 @@ def test_decoder_layer_paired_bev_launch_equals_separate_launches():
 
 
 def test_convgru_gates_kernel_matches_pytorch_ops():
-    """racf_convgru_gates_forward (one launch) against ConvGRUCell's nine elementwise ops (racformer_transformer.py:655-662) on
+    """racf_convgru_gates_forward (one launch) against ConvGRUCell's nine elementwise ops (racformer_transformer.py:713-720) on
     channel-last tensors: same libm calls, separate multiplies / adds -> agreement to the last bit or two."""
     from racformer_b200 import points
     g = torch.Generator(device="cuda").manual_seed(3)
