@@ -11,9 +11,10 @@
 // issue slots 31 %, tensor pipe 7 %). Here one persistent CTA per SM is four roles connected by mbarriers, with three
 // items in flight:
 //
-//   warps 1-7    splitters  the raw fp32 item (x 24 KB, M 16 KB, S 48 KB at P_in = 96) streams through a ring of 4 KB shared-
-//                           memory slots (cp.async.bulk); slot g belongs to warp g % 7, which fetches it, splits it exactly into
-//                           bf16x3 and writes X3 / M3 (= M^T) / S3 in the swizzled UMMA operand layouts
+//   warps 1-14   splitters  the raw fp32 item (x 24 KB, M 16 KB, S 48 KB at P_in = 96) streams through a ring of 4 KB shared-
+//                           memory slots (cp.async.bulk); slot g belongs to warp g % 14, which fetches it, splits it exactly into
+//                           bf16x3 and writes X3 / M3 / S3 in the swizzled UMMA operand layouts (M3 = M as stored: it is the
+//                           MN-major B operand of product 1, so nothing is transposed)
 //   warp 0       MMA        one lane issues product 1 of item n+1 (D1 = x @ M) and product 2 of item n (D2 = S @ t);
 //                           tcgen05.commit releases the operand buffers and publishes the accumulators
 //   warps 8-15   LayerNorm1 D1 -> registers -> LN + ReLU -> split -> T3 (B operand of product 2)
@@ -368,9 +369,10 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
         if (!RACF_MIXWS_SPLIT_ONLY) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             constexpr uint32_t idesc2 = idesc | (kTMajorMN ? (1u << 16) : 0u);
+            constexpr uint32_t idesc1 = idesc | (1u << 16);        // product 1: B = M as stored (MN-major)
             constexpr int kOrder = RACF_MIXWS_EXP == 5 ? 0 : 2;
             const int ksteps2 = p_in >> 4;
-            const uint64_t dx = desc_kmajor<128>(sm_addr + kX3), dm = desc_kmajor<128>(sm_addr + kM3);
+            const uint64_t dx = desc_kmajor<128>(sm_addr + kX3), dm = desc_mnmajor_sw128(sm_addr + kM3);
             const uint64_t ds = desc_kmajor<64>(sm_addr + kS3);
             const uint64_t dt = kTMajorMN ? desc_mnmajor_sw128(sm_addr + kT3) : desc_kmajor<64>(sm_addr + kT3);
             auto product1 = [&](int n) {       // D1[b] = X3 @ M3^T   (one elected lane)
@@ -385,10 +387,10 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
                         for (int pa = 0; pa <= order; ++pa) {
                             umma_bf16(d_cross, dx + (uint64_t)((pa * kXPiece + ks * 32) >> 4),
-                                      dm + (uint64_t)(((order - pa) * kMPiece + ks * 32) >> 4), idesc, acc_cross);
+                                      dm + (uint64_t)(((order - pa) * kMPiece + ks * 2048) >> 4), idesc1, acc_cross);
                             acc_cross = 1;
                         }
-                    umma_bf16(d_main, dx + (uint64_t)((ks * 32) >> 4), dm + (uint64_t)((ks * 32) >> 4), idesc, ks > 0);
+                    umma_bf16(d_main, dx + (uint64_t)((ks * 32) >> 4), dm + (uint64_t)((ks * 2048) >> 4), idesc1, ks > 0);
                 }
                 umma_commit(smem_u32(&bars.xm_free[n & 3]));
                 umma_commit(smem_u32(&bars.d1_full[b]));
@@ -519,19 +521,19 @@ adaptive_mixing_ws_kernel(const float* __restrict__ x, const float* __restrict__
                             }
                         }
                     }
-                } else {                                                       // 16 rows c of M -> M3 = M^T: row c', 8 c per chunk
-                    const int h = w - nx;
+                } else {                                                       // 16 rows c of M, stored as they are: M3 [c][c'] is the
+                    const int h = w - nx;                                      // MN-major B operand of product 1 (K = c, N = c')
 #pragma unroll 1
-                    for (int cg = 0; cg < kCpt / 2; ++cg) {                    // chunks lane + 32 i: c' = (lane + 32 i) & 63, c group i >> 1
-                        float f[2][8];
+                    for (int i0 = 0; i0 < kCpt; i0 += 2) {
+                        float4 a[2], b[2];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[i][j] = raw[(cg * 8 + j) * kC + lane + 32 * i];
+                        for (int i = 0; i < 2; ++i) lds_chunk(raw + (lane + 32 * (i0 + i)) * 8, lane, a[i], b[i]);
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            const int cp = lane + 32 * i;
-                            split_store8(f[i], sm + kM3, kMPiece, cp * 128 + (((h * (kCpt / 2) + cg) ^ (cp & 7)) << 4));
+                            const int c = lane + 32 * (i0 + i);
+                            const int r = h * (kSlotChunks / 8) + (c >> 3), ch = c & 7;
+                            const float f[8] = {a[i].x, a[i].y, a[i].z, a[i].w, b[i].x, b[i].y, b[i].z, b[i].w};
+                            split_store8(f, sm + kM3, kMPiece, r * 128 + ((ch ^ (r & 7)) << 4));
                         }
                     }
                 }
