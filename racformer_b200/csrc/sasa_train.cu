@@ -82,15 +82,40 @@ __device__ __forceinline__ void load_row32(const float* p, float* r) {
 }
 
 // Rows of the "other side" (keys for the query-owning kernels, queries for the key-owning kernel) are staged per warp in
-// shared memory eight at a time and read back as warp-uniform 128-bit loads.
+// shared memory eight at a time and read back as warp-uniform 128-bit loads. The staging is a per-warp double buffer filled
+// with cp.async one block ahead of the arithmetic (as in csrc/sasa.cu, where it took the inference core from 161 to 50 us):
+// with synchronous staging every block paid a global-load latency with nothing to overlap it at 8-16 warps per SM.
 constexpr int kBlock = 8;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// keys j0 .. j0 + 7 of (batch row_base, head h): k (32 floats) | v (32 floats) per key -> st[buf][key][64]
+__device__ __forceinline__ void prefetch_kv(const Args& a, size_t row_base, int h, int j0, int j_end, uint32_t st_s, int buf, int lane) {
+    const int E3 = 3 * a.E;
+#pragma unroll
+    for (int i = 0; i < kBlock * 16 / 32; ++i) {             // 16 float4 per key: 8 of k, 8 of v
+        const int c = lane + 32 * i, key = c >> 4, within = c & 15;
+        const int j = min(j0 + key, j_end - 1);
+        const float* src = a.qkv + (row_base + j) * E3 + (within < 8 ? a.E + h * kD + within * 4 : 2 * a.E + h * kD + (within - 8) * 4);
+        cp_async16(st_s + (uint32_t)((((buf * kBlock + key) * 2 * kD) + within * 4) * 4), src);
+    }
+    cp_async_commit();
+}
 
 // ---------------------------------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kWarps * 32, 2) sasa_train_fwd_kernel(const Args a) {
     extern __shared__ __align__(16) float smem[];
     float* centres = smem;                                   // [Q][2]
     float* part = smem + 2 * ((a.Q + 1) & ~1);               // [kWarps][kD + 2][32]
-    float* stage = part + kWarps * (kD + 2) * 32;            // [kWarps][kBlock][2 * kD]   (k | v)
+    float* stage = part + kWarps * (kD + 2) * 32;            // [kWarps][2][kBlock][2 * kD]   (k | v), double-buffered
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 32;
     const size_t row_base = (size_t)b * a.Q;
@@ -107,16 +132,20 @@ __global__ void __launch_bounds__(kWarps * 32, 2) sasa_train_fwd_kernel(const Ar
     float m = -INFINITY, l = 0.f;
     const int per = (a.Q + kWarps - 1) / kWarps;
     const int j_begin = warp * per, j_end = min(a.Q, j_begin + per);
-    float* st = stage + (size_t)warp * kBlock * 2 * kD;
-    for (int j0 = j_begin; j0 < j_end; j0 += kBlock) {
-        __syncwarp();
-        for (int c = lane; c < kBlock * 16; c += 32) {       // 16 float4 per key: 8 of k, 8 of v
-            const int key = c >> 4, within = c & 15;
-            const int j = min(j0 + key, j_end - 1);
-            const float* src = a.qkv + (row_base + j) * E3 + (within < 8 ? a.E + h * kD + within * 4 : 2 * a.E + h * kD + (within - 8) * 4);
-            *reinterpret_cast<float4*>(st + key * 2 * kD + within * 4) = __ldg(reinterpret_cast<const float4*>(src));
+    float* st2 = stage + (size_t)warp * 2 * kBlock * 2 * kD;
+    const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st2);
+    if (j_begin < j_end) prefetch_kv(a, row_base, h, j_begin, j_end, st_s, 0, lane);
+    int buf = 0;
+    for (int j0 = j_begin; j0 < j_end; j0 += kBlock, buf ^= 1) {
+        __syncwarp();                                        // every lane is done with the buffer the next prefetch overwrites
+        if (j0 + kBlock < j_end) {
+            prefetch_kv(a, row_base, h, j0 + kBlock, j_end, st_s, buf ^ 1, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
+        const float* st = st2 + (size_t)buf * kBlock * 2 * kD;
         float s[kBlock];
 #pragma unroll
         for (int jj = 0; jj < kBlock; ++jj) {
@@ -193,7 +222,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sasa_train_bwd_q_kernel(const 
     extern __shared__ __align__(16) float smem[];
     float* centres = smem;
     float* part = smem + 2 * ((a.Q + 1) & ~1);               // [kWarps][kD + 1][32]: dq, dtau partials
-    float* stage = part + kWarps * (kD + 1) * 32;            // [kWarps][kBlock][2 * kD]
+    float* stage = part + kWarps * (kD + 1) * 32;            // [kWarps][2][kBlock][2 * kD]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 32;
     const size_t row_base = (size_t)b * a.Q;
@@ -217,16 +246,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sasa_train_bwd_q_kernel(const 
     float dtau = 0.f;
     const int per = (a.Q + kWarps - 1) / kWarps;
     const int j_begin = warp * per, j_end = min(a.Q, j_begin + per);
-    float* st = stage + (size_t)warp * kBlock * 2 * kD;
-    for (int j0 = j_begin; j0 < j_end; j0 += kBlock) {
+    float* st2 = stage + (size_t)warp * 2 * kBlock * 2 * kD;
+    const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st2);
+    if (j_begin < j_end) prefetch_kv(a, row_base, h, j_begin, j_end, st_s, 0, lane);
+    int buf = 0;
+    for (int j0 = j_begin; j0 < j_end; j0 += kBlock, buf ^= 1) {
         __syncwarp();
-        for (int c = lane; c < kBlock * 16; c += 32) {
-            const int key = c >> 4, within = c & 15;
-            const int j = min(j0 + key, j_end - 1);
-            const float* src = a.qkv + (row_base + j) * E3 + (within < 8 ? a.E + h * kD + within * 4 : 2 * a.E + h * kD + (within - 8) * 4);
-            *reinterpret_cast<float4*>(st + key * 2 * kD + within * 4) = __ldg(reinterpret_cast<const float4*>(src));
+        if (j0 + kBlock < j_end) {
+            prefetch_kv(a, row_base, h, j0 + kBlock, j_end, st_s, buf ^ 1, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
+        const float* st = st2 + (size_t)buf * kBlock * 2 * kD;
 #pragma unroll 2
         for (int jj = 0; jj < kBlock; ++jj) {
             const int j = j0 + jj;
@@ -289,7 +322,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sasa_train_bwd_kv_kernel(const
     extern __shared__ __align__(16) float smem[];
     float* centres = smem;
     float* part = smem + 2 * ((a.Q + 1) & ~1);               // [kWarps][2 * kD][32]: dk, dv partials
-    float* stage = part + kWarps * 2 * kD * 32;              // [kWarps][kBlock][kQRow]
+    float* stage = part + kWarps * 2 * kD * 32;              // [kWarps][2][kBlock][kQRow]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 32;
     const size_t row_base = (size_t)b * a.Q;
@@ -305,26 +338,41 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sasa_train_bwd_kv_kernel(const
     const float kx = centres[2 * kj], ky = centres[2 * kj + 1];
     const int per = (a.Q + kWarps - 1) / kWarps;
     const int i_begin = warp * per, i_end = min(a.Q, i_begin + per);
-    float* st = stage + (size_t)warp * kBlock * kQRow;
-    for (int i0 = i_begin; i0 < i_end; i0 += kBlock) {
-        __syncwarp();
-        for (int c = lane; c < kBlock * 16; c += 32) {       // 8 float4 of q, 8 of do per query
-            const int qq = c >> 4, within = c & 15;
+    float* st2 = stage + (size_t)warp * 2 * kBlock * kQRow;
+    const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(st2);
+    auto prefetch_q = [&](int i0, int bufn) {                 // 8 float4 of q, 8 of do per query + lse, D, tau (cp.async), centre
+#pragma unroll
+        for (int t = 0; t < kBlock * 16 / 32; ++t) {
+            const int c = lane + 32 * t, qq = c >> 4, within = c & 15;
             const int i = min(i0 + qq, i_end - 1);
             const float* src = within < 8 ? a.qkv + (row_base + i) * E3 + h * kD + within * 4
                                           : a.grad_out + (row_base + i) * a.E + h * kD + (within - 8) * 4;
-            *reinterpret_cast<float4*>(st + qq * kQRow + within * 4) = __ldg(reinterpret_cast<const float4*>(src));
+            cp_async16(st_s + (uint32_t)(((bufn * kBlock + qq) * kQRow + within * 4) * 4), src);
         }
         if (lane < kBlock) {
             const int i = min(i0 + lane, i_end - 1);
-            float* r = st + lane * kQRow + 2 * kD;
-            r[0] = a.lse[((size_t)b * a.H + h) * a.Q + i];
-            r[1] = a.dsum[((size_t)b * a.H + h) * a.Q + i];
-            r[2] = -__ldg(a.tau + (row_base + i) * a.H + h);
-            r[3] = centres[2 * i];
-            r[4] = centres[2 * i + 1];
+            const uint32_t r = st_s + (uint32_t)(((bufn * kBlock + lane) * kQRow + 2 * kD) * 4);
+            cp_async4(r, a.lse + ((size_t)b * a.H + h) * a.Q + i);
+            cp_async4(r + 4, a.dsum + ((size_t)b * a.H + h) * a.Q + i);
+            cp_async4(r + 8, a.tau + (row_base + i) * a.H + h);               // negated when it is read
+            float* rc = st2 + ((size_t)bufn * kBlock + lane) * kQRow + 2 * kD;
+            rc[3] = centres[2 * i];
+            rc[4] = centres[2 * i + 1];
+        }
+        cp_async_commit();
+    };
+    if (i_begin < i_end) prefetch_q(i_begin, 0);
+    int buf = 0;
+    for (int i0 = i_begin; i0 < i_end; i0 += kBlock, buf ^= 1) {
+        __syncwarp();
+        if (i0 + kBlock < i_end) {
+            prefetch_q(i0 + kBlock, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
+        const float* st = st2 + (size_t)buf * kBlock * kQRow;
 #pragma unroll 2
         for (int qq = 0; qq < kBlock; ++qq) {
             const int i = i0 + qq;
@@ -340,7 +388,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sasa_train_bwd_kv_kernel(const
                 da = fmaf(gv.x, v[4 * t], da); da = fmaf(gv.y, v[4 * t + 1], da);
                 da = fmaf(gv.z, v[4 * t + 2], da); da = fmaf(gv.w, v[4 * t + 3], da);
             }
-            const float lse = r[2 * kD], D = r[2 * kD + 1], neg_tau = r[2 * kD + 2];
+            const float lse = r[2 * kD], D = r[2 * kD + 1], neg_tau = -r[2 * kD + 2];
             const float dx = r[2 * kD + 3] - kx, dy = r[2 * kD + 4] - ky;
             const float dist = sqrtf(fmaf(dy, dy, __fmul_rn(dx, dx)));
             const bool ok = a.blocked_t == nullptr || a.blocked_t[(size_t)kj * a.Q + i] == 0;
@@ -409,7 +457,7 @@ extern "C" int racf_sasa_attention_train_forward(const float* qkv, const float* 
     if (!out || !lse) return RACF_ERR_NULL_POINTER;
     if (reinterpret_cast<uintptr_t>(out) & 15u) return RACF_ERR_UNSUPPORTED;
     a.out = out; a.lse = lse;
-    const size_t smem = (size_t)(2 * ((num_query + 1) & ~1) + kWarps * (kD + 2) * 32 + kWarps * kBlock * 2 * kD) * sizeof(float);
+    const size_t smem = (size_t)(2 * ((num_query + 1) & ~1) + kWarps * (kD + 2) * 32 + kWarps * 2 * kBlock * 2 * kD) * sizeof(float);
     if (smem > 100u * 1024u) return RACF_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(sasa_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -435,8 +483,8 @@ extern "C" int racf_sasa_attention_train_backward(const float* qkv, const float*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid((unsigned)((num_query + 31) / 32), (unsigned)num_heads, (unsigned)batch);
     const size_t cen = (size_t)2 * ((num_query + 1) & ~1);
-    const size_t smem_q = (cen + kWarps * (kD + 1) * 32 + kWarps * kBlock * 2 * kD) * sizeof(float);
-    const size_t smem_kv = (cen + kWarps * 2 * kD * 32 + kWarps * kBlock * kQRow) * sizeof(float);
+    const size_t smem_q = (cen + kWarps * (kD + 1) * 32 + kWarps * 2 * kBlock * 2 * kD) * sizeof(float);
+    const size_t smem_kv = (cen + kWarps * 2 * kD * 32 + kWarps * 2 * kBlock * kQRow) * sizeof(float);
     if (smem_q > 200u * 1024u || smem_kv > 200u * 1024u) return RACF_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(sasa_train_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sasa_train_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
