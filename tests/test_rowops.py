@@ -257,3 +257,35 @@ def test_row_program_builder_rejects_cpu_tensors_and_bad_shapes():
         p.add(0, 1, 4)
     with pytest.raises(RuntimeError, match="too long"):
         p.add(0, 1, 4)
+
+
+def test_rows_per_cta_choice_minimises_waves_times_rows():
+    """Host logic of rowops.choose_rows_per_cta (no GPU: 148 SMs assumed): a launch costs waves x rows per CTA; ties go to the
+    larger tile; the row buffers must fit the shared memory the weight-tile ring leaves."""
+    from racformer_b200.rowops import choose_rows_per_cta
+    assert choose_rows_per_cta(900, 3, 768) == 7        # 129 CTAs, one wave (8 rows: 113 CTAs x 8; 6 rows: two waves)
+    assert choose_rows_per_cta(2440, 3, 768) == 6       # 407 CTAs = three waves of 6 (8 rows: 305 CTAs = three waves of 8)
+    assert choose_rows_per_cta(148 * 8, 2, 256) == 8    # exactly one wave of full tiles
+    assert choose_rows_per_cta(100, 2, 256) == 4        # few rows: the smallest tile, one wave either way
+    assert choose_rows_per_cta(900, 3, 1536) == 4       # wide buffers: only 4 rows fit
+    for rows in (1, 37, 900, 1220, 2440, 7200, 50000):
+        for nb, w in ((2, 256), (3, 768), (2, 1024)):
+            r = choose_rows_per_cta(rows, nb, w)
+            assert 4 <= r <= 8 and r * (nb * w * 4 + 3 * 256 * 4) <= 98 * 1024
+
+
+def test_weight_cache_epoch_invalidates_keys():
+    from racformer_b200 import caches
+    e0 = caches.cache_epoch()
+    caches.invalidate_weight_caches()
+    assert caches.cache_epoch() == e0 + 1
+    from racformer_b200.decoder import RaCFormerTransformer
+    from tests.decoder_cases import SMALL
+    m = RaCFormerTransformer(**SMALL)
+    e1 = caches.cache_epoch()
+    m.eval()                                            # mode change: EMA-style .data updates may have happened in between
+    assert caches.cache_epoch() == e1 + 1
+    m.eval()                                            # no change of mode: captured graphs stay valid
+    assert caches.cache_epoch() == e1 + 1
+    m.load_state_dict(m.state_dict())
+    assert caches.cache_epoch() == e1 + 2
